@@ -1,0 +1,82 @@
+"""ctypes binding of libfcx.so -- the C ABI declared in include/fcx.h.
+
+The product path has NO CPU fallback: if the CUDA library cannot be loaded the
+import-time error is re-raised on first use, loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfcx.so")
+
+_dp = ctypes.c_void_p  # double* (host or device address)
+_sz = ctypes.c_size_t
+_ci = ctypes.c_int
+_cd = ctypes.c_double
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/fcx.h one to one
+SIGNATURES = {
+    "fcx_version": (_ci, []),
+    "fcx_strerror": (ctypes.c_char_p, [_ci]),
+    "fcx_last_cuda_error": (ctypes.c_char_p, []),
+    "fcx_stress_strain_dim": (_ci, [_ci]),
+    "fcx_geometric_dim": (_ci, [_ci]),
+    "fcx_set_device": (_ci, [_ci]),
+    "fcx_elastic_evaluate": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp, _vp]),
+    "fcx_mises_evaluate": (_ci, [_dp, _sz, _dp, _dp, _dp, _dp, _dp, _ci, _vp, _vp, _vp]),
+    "fcx_kelvin_evaluate": (_ci, [_ci, _dp, _dp, _cd, _cd, _cd, _cd, _cd, _sz, _dp, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_maxwell_evaluate": (_ci, [_ci, _dp, _dp, _cd, _cd, _cd, _sz, _dp, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_strain_from_grad_u": (_ci, [_ci, _sz, _dp, _dp, _vp]),
+    "fcx_gather_grad": (_ci, [_ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_elastic_evaluate_host": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp]),
+    "fcx_mises_evaluate_host": (_ci, [_dp, _sz, _dp, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_kelvin_evaluate_host": (_ci, [_ci, _dp, _dp, _cd, _cd, _cd, _cd, _cd, _sz, _dp, _dp, _dp, _dp, _dp]),
+    "fcx_maxwell_evaluate_host": (_ci, [_ci, _dp, _dp, _cd, _cd, _cd, _sz, _dp, _dp, _dp, _dp, _dp]),
+    "fcx_host_register": (_ci, [_vp, _sz]),
+    "fcx_host_unregister": (_ci, [_vp]),
+    "fcx_host_chunk_qps": (_sz, [_sz]),
+    "fcx_host_release": (None, []),
+    "fcx_launch_count": (ctypes.c_ulonglong, []),
+    "fcx_tune": (_ci, [ctypes.c_char_p, _ci]),
+}
+
+_lib = None
+
+
+class FcxLibraryError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load libfcx.so (once).  Raises FcxLibraryError if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FcxLibraryError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or `make -C fenics_constitutive_b200/csrc`. "
+                "fenics_constitutive_b200 has no CPU fallback."
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is missing: loud
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "fcx") -> int:
+    """Map a negative C status to a Python exception (SURVEY.md 8b 'Errors')."""
+    if rc >= 0:
+        return rc
+    L = lib()
+    msg = L.fcx_strerror(rc).decode()
+    if rc == -2:  # FCX_ERR_TIMESTEP: the reference asserts (spring_kelvin_model.py:72)
+        raise AssertionError(msg)
+    if rc == -4:
+        raise RuntimeError(f"{what}: {msg}: {L.fcx_last_cuda_error().decode()}")
+    raise ValueError(f"{what}: {msg}")

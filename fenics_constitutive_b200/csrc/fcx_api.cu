@@ -1,0 +1,372 @@
+// fcx_api.cu -- device-pointer entry points of the C ABI (include/fcx.h):
+// parameter set-up on the host (same expressions as the reference's __init__ /
+// evaluate preambles), kernel selection by constraint, persistent-grid launch.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/fcx.h"
+#include "fcx_internal.h"
+#include "fcx_models.cuh"
+
+namespace fcx {
+
+thread_local char g_cuda_error[256] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int note_cuda_error(cudaError_t e, const char *where)
+{
+    if (e == cudaSuccess)
+        return FCX_OK;
+    snprintf(g_cuda_error, sizeof g_cuda_error, "%s: %s", where, cudaGetErrorString(e));
+    return FCX_ERR_CUDA;
+}
+
+static int g_sm_count = 0;
+int sm_count()
+{
+    if (g_sm_count == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_sm_count = n;
+        else
+            return 148;  // B200
+    }
+    return g_sm_count;
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Tunables (fcx_tune): CTAs per SM for the persistent grid; 0 = occupancy query.
+static int g_ctas_per_sm = 0;
+
+constexpr int TILE = 128;
+
+template <class M>
+static int launch_tile(const typename M::Params &prm, const SegPtrs<M::nseg()> &io,
+                       double *tangent, size_t n, bool bulk_ok, unsigned char *flag, int *status,
+                       cudaStream_t stream)
+{
+    if (n == 0)
+        return FCX_OK;
+    auto kern = fcx_tile_kernel<M, TILE>;
+    constexpr size_t smem = tile_smem_bytes<M, TILE>();
+    static int occ = -1;  // per instantiation
+    if (occ < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaFuncSetAttribute");
+        int o = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, TILE, smem);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+        occ = o > 0 ? o : 1;
+    }
+    const int per_sm = g_ctas_per_sm > 0 ? g_ctas_per_sm : occ;
+    const unsigned long long ntiles = (n + TILE - 1) / TILE;
+    unsigned long long grid = (unsigned long long)sm_count() * per_sm;
+    if (grid > ntiles)
+        grid = ntiles;
+    kern<<<(unsigned)grid, TILE, smem, stream>>>(prm, io, tangent, (unsigned long long)n,
+                                                 bulk_ok ? 1 : 0, flag, status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "fcx_tile_kernel launch");
+}
+
+template <class M>
+static int launch_uniaxial(const typename M::Params &prm, const SegPtrs<M::nseg()> &io,
+                           double *tangent, size_t n, bool vec_ok, cudaStream_t stream)
+{
+    if (n == 0)
+        return FCX_OK;
+    const unsigned long long work = (n + 1) / 2;
+    unsigned long long grid = (work + 255) / 256;
+    const unsigned long long cap = (unsigned long long)sm_count() * 8;
+    if (grid > cap)
+        grid = cap;
+    fcx_uniaxial_kernel<M><<<(unsigned)grid, 256, 0, stream>>>(prm, io, tangent,
+                                                              (unsigned long long)n, vec_ok ? 1 : 0);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "fcx_uniaxial_kernel launch");
+}
+
+// ---- host-side parameter builders (shared with fcx_host.cu) ----------------
+
+// fc/models/spring_kelvin_model.py:73-85
+template <int S, int G>
+static void kelvin_params(typename KelvinModel<S, G>::Params &P, const double *D0,
+                          const double *I2, double mu0, double lam0, double mu1, double tau,
+                          double del_t)
+{
+    const double factor = 1 / del_t + 1 / tau + mu0 / (tau * mu1);
+    P.inv_factor = 1 / factor;
+    P.c_sig = 1 / (tau * 2 * mu1);
+    P.c_ev = 1 / tau;
+    P.c_e = mu0 / (tau * mu1);
+    P.c_tr = lam0 / (tau * 2 * mu1);
+    P.two_mu0 = 2 * mu0;
+    const double dscale = 1 - mu0 / (tau * mu1 * factor);
+    for (int k = 0; k < S * S; ++k) {
+        P.D0[k] = D0[k];
+        P.Dt[k] = dscale * D0[k];
+    }
+    for (int k = 0; k < S; ++k)
+        P.I2[k] = I2[k];
+}
+
+// fc/models/spring_maxwell_model.py:70-82
+template <int S, int G>
+static void maxwell_params(typename MaxwellModel<S, G>::Params &P, const double *D0,
+                           const double *D1, double mu1, double tau, double del_t)
+{
+    const double factor = 1 / del_t + 1 / tau;
+    P.inv_factor = 1 / factor;
+    P.c_tot = 1 / (tau * 2 * mu1);
+    P.c_ev = 1 / tau;
+    P.two_mu1 = 2 * mu1;
+    const double dscale = 1 - 1 / (tau * factor);
+    for (int k = 0; k < S * S; ++k) {
+        P.D1[k] = D1[k];
+        P.D01[k] = D0[k] + D1[k];
+        P.Dt[k] = D0[k] + dscale * D1[k];
+    }
+}
+
+template <int S, int G>
+static int elastic_dispatch(const double *D, size_t n, const double *grad, double *stress,
+                            double *tangent, cudaStream_t st)
+{
+    using M = ElasticModel<S, G>;
+    typename M::Params P;
+    for (int k = 0; k < S * S; ++k)
+        P.D[k] = D[k];
+    SegPtrs<2> io{{const_cast<double *>(grad), stress}};
+    const bool al = aligned16(grad) && aligned16(stress) && aligned16(tangent);
+    if constexpr (S == 1)
+        return launch_uniaxial<M>(P, io, tangent, n, al, st);
+    else
+        return launch_tile<M>(P, io, tangent, n, al, nullptr, nullptr, st);
+}
+
+template <int S, int G>
+static int kelvin_dispatch(const double *D0, const double *I2, double mu0, double lam0, double mu1,
+                           double tau, double del_t, size_t n, const double *grad, double *stress,
+                           double *tangent, double *ev, double *et, cudaStream_t st)
+{
+    using M = KelvinModel<S, G>;
+    typename M::Params P;
+    kelvin_params<S, G>(P, D0, I2, mu0, lam0, mu1, tau, del_t);
+    SegPtrs<4> io{{const_cast<double *>(grad), stress, ev, et}};
+    const bool al = aligned16(grad) && aligned16(stress) && aligned16(tangent) && aligned16(ev) &&
+                    aligned16(et);
+    if constexpr (S == 1)
+        return launch_uniaxial<M>(P, io, tangent, n, al, st);
+    else
+        return launch_tile<M>(P, io, tangent, n, al, nullptr, nullptr, st);
+}
+
+template <int S, int G>
+static int maxwell_dispatch(const double *D0, const double *D1, double mu1, double tau,
+                            double del_t, size_t n, const double *grad, double *stress,
+                            double *tangent, double *ev, double *et, cudaStream_t st)
+{
+    using M = MaxwellModel<S, G>;
+    typename M::Params P;
+    maxwell_params<S, G>(P, D0, D1, mu1, tau, del_t);
+    SegPtrs<4> io{{const_cast<double *>(grad), stress, ev, et}};
+    const bool al = aligned16(grad) && aligned16(stress) && aligned16(tangent) && aligned16(ev) &&
+                    aligned16(et);
+    if constexpr (S == 1)
+        return launch_uniaxial<M>(P, io, tangent, n, al, st);
+    else
+        return launch_tile<M>(P, io, tangent, n, al, nullptr, nullptr, st);
+}
+
+// strain_from_grad_u as a standalone op (fc/models/utils.py:132-208)
+template <int S, int G>
+__global__ void strain_kernel(const double *__restrict__ grad, double *__restrict__ strain,
+                              unsigned long long n)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+         q += stride) {
+        double g[G * G], e[S];
+#pragma unroll
+        for (int i = 0; i < G * G; ++i)
+            g[i] = grad[q * (G * G) + i];
+        mandel_strain<S, G>(g, e);
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+            strain[q * S + i] = e[i];
+    }
+}
+
+}  // namespace fcx
+
+using namespace fcx;
+
+extern "C" {
+
+int fcx_version(void) { return FCX_VERSION; }
+
+const char *fcx_strerror(int code)
+{
+    switch (code) {
+    case FCX_OK: return "ok";
+    case FCX_ERR_CONSTRAINT: return "unknown or unsupported stress-strain constraint";
+    case FCX_ERR_TIMESTEP: return "Time step must be defined and positive.";
+    case FCX_ERR_NULL: return "required pointer is NULL";
+    case FCX_ERR_CUDA: return "CUDA runtime error (see fcx_last_cuda_error)";
+    case FCX_ERR_ARG: return "invalid argument";
+    default:
+        return code > 0 ? "Newton-Raphson method did not converge for plastic multiplier."
+                        : "unknown error";
+    }
+}
+
+const char *fcx_last_cuda_error(void) { return g_cuda_error; }
+
+int fcx_stress_strain_dim(int c) { return (c < 1 || c > 5) ? -1 : (c <= 2 ? 1 : (c <= 4 ? 4 : 6)); }
+int fcx_geometric_dim(int c) { return (c < 1 || c > 5) ? -1 : (c <= 2 ? 1 : (c <= 4 ? 2 : 3)); }
+
+unsigned long long fcx_launch_count(void) { return g_launches.load(); }
+
+int fcx_tune(const char *key, int value)
+{
+    if (key && strcmp(key, "ctas_per_sm") == 0) {
+        const int old = g_ctas_per_sm;
+        g_ctas_per_sm = value;
+        return old;
+    }
+    return FCX_ERR_ARG;
+}
+
+int fcx_set_device(int device)
+{
+    g_sm_count = 0;
+    return note_cuda_error(cudaSetDevice(device), "cudaSetDevice");
+}
+
+int fcx_elastic_evaluate(int constraint, const double *D, size_t n, const double *grad,
+                         double *stress, double *tangent, void *stream)
+{
+    if (n == 0)
+        return FCX_OK;
+    if (!D || !grad || !stress || !tangent)
+        return FCX_ERR_NULL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (constraint) {
+    case FCX_UNIAXIAL_STRAIN:
+    case FCX_UNIAXIAL_STRESS: return elastic_dispatch<1, 1>(D, n, grad, stress, tangent, st);
+    case FCX_PLANE_STRAIN:
+    case FCX_PLANE_STRESS: return elastic_dispatch<4, 2>(D, n, grad, stress, tangent, st);
+    case FCX_FULL: return elastic_dispatch<6, 3>(D, n, grad, stress, tangent, st);
+    default: return FCX_ERR_CONSTRAINT;
+    }
+}
+
+int fcx_mises_evaluate(const double *params, size_t n, const double *grad, double *stress,
+                       double *tangent, double *eps_n, double *alpha, int eps_layout,
+                       unsigned char *plastic_flag, int *status, void *stream)
+{
+    if (n == 0)
+        return FCX_OK;
+    if (!params || !grad || !stress || !tangent || !eps_n || !alpha)
+        return FCX_ERR_NULL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MisesParams P{params[0], params[1], params[2], params[3], params[4]};
+    SegPtrs<4> io{{const_cast<double *>(grad), stress, eps_n, alpha}};
+    bool al = aligned16(grad) && aligned16(stress) && aligned16(tangent) && aligned16(eps_n) &&
+              aligned16(alpha);
+    if (eps_layout == FCX_LAYOUT_SOA) {
+        al = al && (n % 2 == 0);  // plane starts must stay 16-byte aligned
+        return launch_tile<MisesModel<true>>(P, io, tangent, n, al, plastic_flag, status, st);
+    }
+    if (eps_layout != FCX_LAYOUT_AOS)
+        return FCX_ERR_ARG;
+    return launch_tile<MisesModel<false>>(P, io, tangent, n, al, plastic_flag, status, st);
+}
+
+int fcx_kelvin_evaluate(int constraint, const double *D0, const double *I2, double mu0,
+                        double lam0, double mu1, double tau, double del_t, size_t n,
+                        const double *grad, double *stress, double *tangent, double *ev,
+                        double *et, void *stream)
+{
+    if (!(del_t > 0))
+        return FCX_ERR_TIMESTEP;
+    if (n == 0)
+        return FCX_OK;
+    if (!D0 || !I2 || !grad || !stress || !tangent || !ev || !et)
+        return FCX_ERR_NULL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (constraint) {
+    case FCX_UNIAXIAL_STRAIN:
+    case FCX_UNIAXIAL_STRESS:
+        return kelvin_dispatch<1, 1>(D0, I2, mu0, lam0, mu1, tau, del_t, n, grad, stress, tangent, ev, et, st);
+    case FCX_PLANE_STRAIN:
+    case FCX_PLANE_STRESS:
+        return kelvin_dispatch<4, 2>(D0, I2, mu0, lam0, mu1, tau, del_t, n, grad, stress, tangent, ev, et, st);
+    case FCX_FULL:
+        return kelvin_dispatch<6, 3>(D0, I2, mu0, lam0, mu1, tau, del_t, n, grad, stress, tangent, ev, et, st);
+    default: return FCX_ERR_CONSTRAINT;
+    }
+}
+
+int fcx_maxwell_evaluate(int constraint, const double *D0, const double *D1, double mu1,
+                         double tau, double del_t, size_t n, const double *grad, double *stress,
+                         double *tangent, double *ev, double *et, void *stream)
+{
+    if (!(del_t > 0))
+        return FCX_ERR_TIMESTEP;
+    if (n == 0)
+        return FCX_OK;
+    if (!D0 || !D1 || !grad || !stress || !tangent || !ev || !et)
+        return FCX_ERR_NULL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (constraint) {
+    case FCX_UNIAXIAL_STRAIN:
+    case FCX_UNIAXIAL_STRESS:
+        return maxwell_dispatch<1, 1>(D0, D1, mu1, tau, del_t, n, grad, stress, tangent, ev, et, st);
+    case FCX_PLANE_STRAIN:
+    case FCX_PLANE_STRESS:
+        return maxwell_dispatch<4, 2>(D0, D1, mu1, tau, del_t, n, grad, stress, tangent, ev, et, st);
+    case FCX_FULL:
+        return maxwell_dispatch<6, 3>(D0, D1, mu1, tau, del_t, n, grad, stress, tangent, ev, et, st);
+    default: return FCX_ERR_CONSTRAINT;
+    }
+}
+
+int fcx_strain_from_grad_u(int constraint, size_t n, const double *grad, double *strain,
+                           void *stream)
+{
+    if (n == 0)
+        return FCX_OK;
+    if (!grad || !strain)
+        return FCX_ERR_NULL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long grid = (n + 255) / 256;
+    const unsigned long long cap = (unsigned long long)sm_count() * 8;
+    if (grid > cap)
+        grid = cap;
+    switch (constraint) {
+    case FCX_UNIAXIAL_STRAIN:
+    case FCX_UNIAXIAL_STRESS:
+        strain_kernel<1, 1><<<(unsigned)grid, 256, 0, st>>>(grad, strain, n);
+        break;
+    case FCX_PLANE_STRAIN:
+    case FCX_PLANE_STRESS:
+        strain_kernel<4, 2><<<(unsigned)grid, 256, 0, st>>>(grad, strain, n);
+        break;
+    case FCX_FULL:
+        strain_kernel<6, 3><<<(unsigned)grid, 256, 0, st>>>(grad, strain, n);
+        break;
+    default: return FCX_ERR_CONSTRAINT;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "strain_kernel launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,509 @@
+// fcx_models.cuh -- per-quadrature-point arithmetic of the four constitutive
+// laws, written as Model policies for the tile pipeline (fcx_tile.cuh) and the
+// uniaxial elementwise kernel.  Operation order follows the reference
+// (file:line cited per block; fc = src/fenics_constitutive) so results track
+// its numpy models to rounding; the library is compiled with -fmad=false so
+// nvcc does not fuse a*b+c differently from numpy.
+#pragma once
+#include "fcx_tile.cuh"
+
+namespace fcx {
+
+// Python's `1 / 2**0.5` (fc/models/utils.py:202-204) = 0x1.6a09e667f3bccp-1,
+// one ulp below the correctly rounded 1/sqrt(2).
+__device__ __forceinline__ double shear_factor() { return 0x1.6a09e667f3bccp-1; }
+// np.sqrt(2 / 3)
+__device__ __forceinline__ double sqrt23() { return 0x1.a20bd700c2c3ep-1; }
+
+// fc/models/utils.py:132-208 (strain_from_grad_u), one QP.
+template <int S, int G>
+__device__ __forceinline__ void mandel_strain(const double *g, double *e)
+{
+    if (G == 1) {
+        e[0] = g[0];  // :153-156
+    } else if (G == 2) {
+        e[0] = g[0];  // :165-168 / :182-185
+        e[1] = g[3];
+        e[2] = 0.0;
+        e[3] = shear_factor() * (g[1] + g[2]);
+    } else {
+        e[0] = g[0];  // :199-204
+        e[1] = g[4];
+        e[2] = g[8];
+        e[3] = shear_factor() * (g[1] + g[3]);
+        e[4] = shear_factor() * (g[2] + g[6]);
+        e[5] = shear_factor() * (g[5] + g[7]);
+    }
+}
+
+// y_j = sum_i x_i M[i][j]  (numpy `x @ M`), M in kernel-parameter space.
+template <int S>
+__device__ __forceinline__ void vec_mat(const double *x, const double *M, double *y)
+{
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+            acc += x[i] * M[i * S + j];
+        y[j] = acc;
+    }
+}
+
+// Dense, coalesced store of a tile's tangent when every QP has the same s*s
+// matrix (elastic, Kelvin, Maxwell): Dsm holds the matrix in shared memory;
+// consecutive threads write consecutive 16-byte pairs of the [cnt][s*s] block.
+template <int S>
+__device__ __forceinline__ void store_const_tangent(const double *Dsm, double *tang, int cnt,
+                                                    int tid, int nthreads, bool vec_ok)
+{
+    constexpr int SS = S * S;
+    if (vec_ok) {
+        constexpr int NP = SS / 2;  // 16-byte pairs per QP
+        const int npairs = cnt * NP;
+        for (int p = tid; p < npairs; p += nthreads) {
+            const int ij = p % NP;
+            const double2 v = reinterpret_cast<const double2 *>(Dsm)[ij];
+            st_stream_v2(tang + 2 * (size_t)p, v.x, v.y);
+        }
+    } else {
+        for (int p = tid; p < cnt * SS; p += nthreads)
+            tang[p] = Dsm[p % SS];
+    }
+}
+
+// ===========================================================================
+// LinearElasticityModel -- fc/models/linear_elasticity_model.py:26-45
+//   segments: 0 grad_del_u [g*g] (read)   1 stress [s] (in place)
+// ===========================================================================
+template <int S, int G>
+struct ElasticModel {
+    struct Params {
+        double D[S * S];  // get_elastic_tangent (fc/models/utils.py:25-93), row-major
+    };
+    static constexpr __host__ __device__ int nseg() { return 2; }
+    static constexpr __host__ __device__ int w(int k) { return k == 0 ? G * G : S; }
+    static constexpr __host__ __device__ int off(int k) { return k == 0 ? 0 : G * G; }
+    static constexpr __host__ __device__ int wsum() { return G * G + S; }
+    static constexpr __host__ __device__ bool wr(int k) { return k == 1; }
+    static constexpr __host__ __device__ bool soa(int) { return false; }
+    static constexpr __host__ __device__ int sdim() { return S; }
+    static constexpr __host__ __device__ int aux_doubles(int) { return S * S; }
+    static constexpr __host__ __device__ int min_ctas() { return 4; }
+    static constexpr __host__ __device__ bool has_flag() { return false; }
+
+    __device__ static void init_aux(const Params &p, double *aux, int tid, int nthreads)
+    {
+        for (int i = tid; i < S * S; i += nthreads)
+            aux[i] = p.D[i];
+    }
+
+    // stress += strain_increment @ D   (:44)
+    __device__ static __forceinline__ void update(const Params &p, const double *g, double *sig)
+    {
+        double e[S], de[S];
+        mandel_strain<S, G>(g, e);
+        vec_mat<S>(e, p.D, de);
+#pragma unroll
+        for (int k = 0; k < S; ++k)
+            sig[k] += de[k];
+    }
+
+    template <class V>
+    __device__ static __forceinline__ void qp(const Params &p, const V &v, double *, int, bool &,
+                                              bool &)
+    {
+        double g[G * G], sig[S];
+#pragma unroll
+        for (int i = 0; i < G * G; ++i)
+            g[i] = v.template ld<0>(i);
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+            sig[i] = v.template ld<1>(i);
+        update(p, g, sig);
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+            v.template st<1>(i, sig[i]);
+    }
+
+    // tangent[:] = tile(D.flatten(), n)   (:45)
+    __device__ static __forceinline__ void store_tangent(const Params &, const double *aux,
+                                                         double *tang, int cnt, int tid,
+                                                         int nthreads, bool vec_ok)
+    {
+        store_const_tangent<S>(aux, tang, cnt, tid, nthreads, vec_ok);
+    }
+
+    // uniaxial form: a[0] = grad, a[1] = stress
+    __device__ static __forceinline__ void qp1(const Params &p, double *a, double &tang)
+    {
+        update(p, &a[0], &a[1]);
+        tang = p.D[0];
+    }
+};
+
+// ===========================================================================
+// SpringKelvinModel -- fc/models/spring_kelvin_model.py:43-88
+//   segments: 0 grad [g*g] (read)  1 stress [s]  2 strain_visco [s]  3 strain [s]
+// ===========================================================================
+template <int S, int G>
+struct KelvinModel {
+    struct Params {
+        double D0[S * S];  // self.D_0 (:38)
+        double Dt[S * S];  // (1 - mu0/(tau*mu1*factor)) * D_0   (:85)
+        double I2[S];      // get_identity (:39)
+        double inv_factor; // 1 / factor, factor = 1/dt + 1/tau + mu0/(tau*mu1)   (:73,:75-76)
+        double c_sig;      // 1 / (tau*2*mu1)      (:78)
+        double c_ev;       // 1 / tau              (:79)
+        double c_e;        // mu0 / (tau*mu1)      (:80)
+        double c_tr;       // lam0 / (tau*2*mu1)   (:81)
+        double two_mu0;    // 2 * mu0              (:84)
+    };
+    static constexpr __host__ __device__ int nseg() { return 4; }
+    static constexpr __host__ __device__ int w(int k) { return k == 0 ? G * G : S; }
+    static constexpr __host__ __device__ int off(int k) { return k == 0 ? 0 : G * G + (k - 1) * S; }
+    static constexpr __host__ __device__ int wsum() { return G * G + 3 * S; }
+    static constexpr __host__ __device__ bool wr(int k) { return k >= 1; }
+    static constexpr __host__ __device__ bool soa(int) { return false; }
+    static constexpr __host__ __device__ int sdim() { return S; }
+    static constexpr __host__ __device__ int aux_doubles(int) { return S * S; }
+    static constexpr __host__ __device__ int min_ctas() { return 3; }
+    static constexpr __host__ __device__ bool has_flag() { return false; }
+
+    __device__ static void init_aux(const Params &p, double *aux, int tid, int nthreads)
+    {
+        for (int i = tid; i < S * S; i += nthreads)
+            aux[i] = p.Dt[i];
+    }
+
+    __device__ static __forceinline__ void update(const Params &p, const double *g, double *sig,
+                                                  double *ev, double *et)
+    {
+        double e[S], eD[S];
+        mandel_strain<S, G>(g, e);
+        double tr = 0.0;  // np.sum(strain_increment[:, :geometric_dim], axis=1)   (:69-71)
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+            tr += e[k];
+        vec_mat<S>(e, p.D0, eD);
+        const double ctr = p.c_tr * tr;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            // (:74-83)
+            const double dv =
+                p.inv_factor * (p.c_sig * sig[k] - p.c_ev * ev[k] + p.c_e * e[k] + ctr * p.I2[k]);
+            sig[k] += eD[k] - p.two_mu0 * dv;  // (:84)
+            ev[k] += dv;                       // (:87)
+            et[k] += e[k];                     // (:88)
+        }
+    }
+
+    template <class V>
+    __device__ static __forceinline__ void qp(const Params &p, const V &v, double *, int, bool &,
+                                              bool &)
+    {
+        double g[G * G], sig[S], ev[S], et[S];
+#pragma unroll
+        for (int i = 0; i < G * G; ++i)
+            g[i] = v.template ld<0>(i);
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            sig[i] = v.template ld<1>(i);
+            ev[i] = v.template ld<2>(i);
+            et[i] = v.template ld<3>(i);
+        }
+        update(p, g, sig, ev, et);
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            v.template st<1>(i, sig[i]);
+            v.template st<2>(i, ev[i]);
+            v.template st<3>(i, et[i]);
+        }
+    }
+
+    __device__ static __forceinline__ void store_tangent(const Params &, const double *aux,
+                                                         double *tang, int cnt, int tid,
+                                                         int nthreads, bool vec_ok)
+    {
+        store_const_tangent<S>(aux, tang, cnt, tid, nthreads, vec_ok);
+    }
+
+    __device__ static __forceinline__ void qp1(const Params &p, double *a, double &tang)
+    {
+        update(p, &a[0], &a[1], &a[2], &a[3]);
+        tang = p.Dt[0];
+    }
+};
+
+// ===========================================================================
+// SpringMaxwellModel -- fc/models/spring_maxwell_model.py:40-88
+//   segments as for Kelvin.
+// ===========================================================================
+template <int S, int G>
+struct MaxwellModel {
+    struct Params {
+        double D1[S * S];   // self.D_1 (:37)
+        double D01[S * S];  // D_0 + D_1 (:80)
+        double Dt[S * S];   // D_0 + (1 - 1/(tau*factor)) * D_1   (:82)
+        double inv_factor;  // 1 / factor, factor = 1/dt + 1/tau    (:70,:72-73)
+        double c_tot;       // 1 / (tau*2*mu1)   (:75)
+        double c_ev;        // 1 / tau           (:76)
+        double two_mu1;     // 2 * mu1           (:80)
+    };
+    static constexpr __host__ __device__ int nseg() { return 4; }
+    static constexpr __host__ __device__ int w(int k) { return k == 0 ? G * G : S; }
+    static constexpr __host__ __device__ int off(int k) { return k == 0 ? 0 : G * G + (k - 1) * S; }
+    static constexpr __host__ __device__ int wsum() { return G * G + 3 * S; }
+    static constexpr __host__ __device__ bool wr(int k) { return k >= 1; }
+    static constexpr __host__ __device__ bool soa(int) { return false; }
+    static constexpr __host__ __device__ int sdim() { return S; }
+    static constexpr __host__ __device__ int aux_doubles(int) { return S * S; }
+    static constexpr __host__ __device__ int min_ctas() { return 3; }
+    static constexpr __host__ __device__ bool has_flag() { return false; }
+
+    __device__ static void init_aux(const Params &p, double *aux, int tid, int nthreads)
+    {
+        for (int i = tid; i < S * S; i += nthreads)
+            aux[i] = p.Dt[i];
+    }
+
+    __device__ static __forceinline__ void update(const Params &p, const double *g, double *sig,
+                                                  double *ev, double *et)
+    {
+        double e[S], tot[S], totD[S], eD[S];
+        mandel_strain<S, G>(g, e);
+#pragma unroll
+        for (int k = 0; k < S; ++k)
+            tot[k] = p.c_tot * (et[k] + e[k]);  // (:69, :75)
+        vec_mat<S>(tot, p.D1, totD);
+        vec_mat<S>(e, p.D01, eD);
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            const double dv = p.inv_factor * (totD[k] - p.c_ev * ev[k]);  // (:71-78)
+            sig[k] += eD[k] - p.two_mu1 * dv;                             // (:80-81)
+            ev[k] += dv;                                                  // (:85)
+            et[k] += e[k];                                                // (:86)
+        }
+    }
+
+    template <class V>
+    __device__ static __forceinline__ void qp(const Params &p, const V &v, double *, int, bool &,
+                                              bool &)
+    {
+        double g[G * G], sig[S], ev[S], et[S];
+#pragma unroll
+        for (int i = 0; i < G * G; ++i)
+            g[i] = v.template ld<0>(i);
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            sig[i] = v.template ld<1>(i);
+            ev[i] = v.template ld<2>(i);
+            et[i] = v.template ld<3>(i);
+        }
+        update(p, g, sig, ev, et);
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            v.template st<1>(i, sig[i]);
+            v.template st<2>(i, ev[i]);
+            v.template st<3>(i, et[i]);
+        }
+    }
+
+    __device__ static __forceinline__ void store_tangent(const Params &, const double *aux,
+                                                         double *tang, int cnt, int tid,
+                                                         int nthreads, bool vec_ok)
+    {
+        store_const_tangent<S>(aux, tang, cnt, tid, nthreads, vec_ok);
+    }
+
+    __device__ static __forceinline__ void qp1(const Params &p, double *a, double &tang)
+    {
+        update(p, &a[0], &a[1], &a[2], &a[3]);
+        tang = p.Dt[0];
+    }
+};
+
+// ===========================================================================
+// VonMises3D -- fc/models/mises_plasticity_isotropic_hardening.py:57-175
+//   segments: 0 grad [9] (read)  1 stress [6]  2 eps_n [6] (AoS or SoA)  3 alpha [1]
+//   per-QP tangent record in shared memory (REC doubles, odd stride):
+//     [0] A = ka + cpp*xpp_diag  [1] B = ka + cpp*xpp_off  [2] cpp = 2mu(1 - 2mu*xc2)
+//     [3] cnn = 4mu^2 (xc2 - xc1)   [4..9] xn
+// ===========================================================================
+struct MisesParams {
+    double ka, mu, y0, y00, w;  // p_ka, p_mu, p_y0, p_y00, p_w   (:51-55)
+};
+
+// Scalar Newton for the plastic multiplier, :100-151.  Stays in registers.
+// exp(-w*alpha) of the trial check is the first iterate's exp (gamma_0 = 0).
+__device__ __forceinline__ void mises_return_map(const MisesParams &P, double sigtrn,
+                                                 double alpha_n, double phitr, double exp0,
+                                                 double &gamma, double &xg_final, bool &failed)
+{
+    const double c23 = sqrt23();
+    const double two_mu = 2 * P.mu;
+    const double dy = P.y00 - P.y0;
+    const double dfc = (2.0 / 3.0) * dy * P.w;  // (2/3)*(y00-y0)*w   (:124-125)
+    double gamma_0 = 1, gamma_1 = 0, xr = 1;
+    int it = 0;
+    // first pass of the loop (:129-139) with gamma_0 = 0: f(0) == phitr
+    gamma_0 = gamma_1;
+    it = 1;
+    xr = phitr;
+    double xg = -two_mu - dfc * exp0;
+    gamma_1 = gamma_0 - xr / xg;
+    while (fabs(xr) > 1e-12 && fabs(gamma_1 - gamma_0) > 1e-8 * fabs(gamma_1)) {
+        gamma_0 = gamma_1;
+        it = it + 1;
+        const double ex = exp(-P.w * (alpha_n + c23 * gamma_0));
+        xr = sigtrn - two_mu * gamma_0 - c23 * (P.y0 + dy * (1 - ex));  // f   (:111-121)
+        xg = -two_mu - dfc * ex;                                        // df  (:123-126)
+        gamma_1 = gamma_0 - xr / xg;
+        if (it > 100) {  // (:141-143)
+            failed = true;
+            break;
+        }
+    }
+    xg_final = -two_mu - dfc * exp(-P.w * (alpha_n + c23 * gamma_1));  // (:147)
+    gamma = gamma_1;
+}
+
+template <bool EPS_SOA>
+struct MisesModel {
+    using Params = MisesParams;
+    static constexpr int REC = 11;  // 10 used; odd stride -> conflict-free 64-bit smem access
+    static constexpr __host__ __device__ int nseg() { return 4; }
+    static constexpr __host__ __device__ int w(int k) { return k == 0 ? 9 : (k == 3 ? 1 : 6); }
+    static constexpr __host__ __device__ int off(int k) { return k == 0 ? 0 : (k == 1 ? 9 : (k == 2 ? 15 : 21)); }
+    static constexpr __host__ __device__ int wsum() { return 22; }
+    static constexpr __host__ __device__ bool wr(int k) { return k >= 1; }
+    static constexpr __host__ __device__ bool soa(int k) { return EPS_SOA && k == 2; }
+    static constexpr __host__ __device__ int sdim() { return 6; }
+    static constexpr __host__ __device__ int aux_doubles(int tile) { return REC * tile; }
+    static constexpr __host__ __device__ int min_ctas() { return 4; }
+    static constexpr __host__ __device__ bool has_flag() { return true; }
+
+    __device__ static void init_aux(const Params &, double *, int, int) {}
+
+    template <class V>
+    __device__ static __forceinline__ void qp(const Params &P, const V &v, double *aux, int t,
+                                              bool &plastic, bool &failed)
+    {
+        double g[9], sig[6], ep[6];
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            g[i] = v.template ld<0>(i);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            sig[i] = v.template ld<1>(i);
+            ep[i] = v.template ld<2>(i);
+        }
+        const double alpha_n = v.template ld<3>(0);
+
+        const double c23 = sqrt23();
+        const double two_mu = 2 * P.mu;
+        double eps[6];
+        mandel_strain<6, 3>(g, eps);
+        const double tr_eps = (eps[0] + eps[1]) + eps[2];  // :75
+        const double tr_sig = (sig[0] + sig[1]) + sig[2];  // :81
+        const double te3 = tr_eps / 3;                     // tr_eps * I2 / 3   (:76)
+        const double ts3 = tr_sig / 3;                     // (:81)
+        double del_sigtr[6], sigtr[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double eps_dev = (k < 3) ? eps[k] - te3 : eps[k];       // :76
+            del_sigtr[k] = two_mu * eps_dev;                              // :79
+            const double stress_n_dev = (k < 3) ? sig[k] - ts3 : sig[k];  // :80-82
+            sigtr[k] = stress_n_dev + del_sigtr[k];                       // :83-85
+        }
+        double dot = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            dot += sigtr[k] * sigtr[k];
+        const double sigtrn = sqrt(dot);  // :88
+        const double exp0 = exp(-P.w * alpha_n);
+        const double phitr = sigtrn - c23 * (P.y0 + (P.y00 - P.y0) * (1 - exp0));  // :91-94
+
+        double xn[6], gamma_1 = 0, xc1 = 0, xc2 = 0;
+        plastic = phitr > 0;  // :98
+        if (plastic) {
+            double xg;
+            mises_return_map(P, sigtrn, alpha_n, phitr, exp0, gamma_1, xg, failed);
+            const double inv_n = 1.0 / sigtrn;
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                xn[k] = sigtr[k] * inv_n;  // flow direction (:108)
+            xc1 = -1 / xg;                 // :150
+            xc2 = gamma_1 * inv_n;         // :151
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                xn[k] = 0.0;  // :154-158
+        }
+        const double ktr = P.ka * tr_eps;
+        const double tmg = two_mu * gamma_1;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            ep[k] += gamma_1 * xn[k];                                                     // :161
+            const double sh = ((k < 3) ? ktr + del_sigtr[k] : del_sigtr[k]) - tmg * xn[k];  // :165
+            sig[k] += sh;                                                                 // :167
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            v.template st<1>(i, sig[i]);
+            v.template st<2>(i, ep[i]);
+        }
+        v.template st<3>(0, alpha_n + c23 * gamma_1);  // :162
+
+        // Tangent record (:170-175).  ka*xioi + cpp*xpp takes four values per QP:
+        // A on the volumetric diagonal, B on its off-diagonal, cpp on the shear
+        // diagonal, 0 elsewhere (xioi :33-42, xpp = I4 - (1/3) xioi :48).
+        double *rec = aux + t * REC;
+        const double cpp = two_mu * (1 - two_mu * xc2);  // :172
+        const double third = (1.0 / 3.0) * 1.0;
+        rec[0] = P.ka + cpp * (1.0 - third);
+        rec[1] = P.ka + cpp * (0.0 - third);
+        rec[2] = cpp;
+        rec[3] = 4 * P.mu * P.mu * (xc2 - xc1);  // :173
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            rec[4 + k] = xn[k];
+    }
+
+    // aah = ka*xioi + cpp*xpp + cnn*outer(xn, xn), row-major 36 per QP (:170-175),
+    // generated pair-by-pair so that consecutive threads write consecutive
+    // 16-byte chunks of the tile's [cnt][36] block.
+    __device__ static __forceinline__ double entry(const double *rec, int i, int j)
+    {
+        const bool vol = (i < 3) && (j < 3);
+        const bool diag = (i == j);
+        const double base = vol ? (diag ? rec[0] : rec[1]) : (diag ? rec[2] : 0.0);
+        return base + rec[3] * (rec[4 + i] * rec[4 + j]);
+    }
+
+    __device__ static __forceinline__ void store_tangent(const Params &, const double *aux,
+                                                         double *tang, int cnt, int tid,
+                                                         int nthreads, bool vec_ok)
+    {
+        if (vec_ok) {
+            const int npairs = cnt * 18;
+            for (int p = tid; p < npairs; p += nthreads) {
+                const int q = p / 18;
+                const int pr = p - q * 18;
+                const int i = pr / 3;
+                const int j = 2 * (pr - 3 * i);
+                const double *rec = aux + q * REC;
+                st_stream_v2(tang + 2 * (size_t)p, entry(rec, i, j), entry(rec, i, j + 1));
+            }
+        } else {
+            for (int p = tid; p < cnt * 36; p += nthreads) {
+                const int q = p / 36;
+                const int ij = p - q * 36;
+                const int i = ij / 6, j = ij - 6 * i;
+                tang[p] = entry(aux + q * REC, i, j);
+            }
+        }
+    }
+};
+
+}  // namespace fcx

@@ -1,0 +1,272 @@
+// fcx_tile.cuh -- the persistent, double-buffered tile pipeline shared by every
+// constitutive kernel with Mandel dim s in {4, 6}.
+//
+// Why a tile pipeline: the drop-in contract is array-of-structs (reference
+// models/interfaces.py:82-101) -- a thread that owns one QP sees
+// strides of 72/48/288 bytes, which would waste most of every 128-byte line.
+// But a TILE of consecutive QPs is one contiguous byte range in every array.
+// So each CTA
+//   1. pulls the tile's ranges global->shared with 1-D bulk async copies (TMA
+//      engine, completion on an mbarrier), double-buffered so the next tile is
+//      in flight while the current one is computed;
+//   2. lets thread t compute QP t entirely in registers, reading/writing its
+//      slots of the shared stage (in place);
+//   3. pushes the in-place segments (stress, history) back shared->global with
+//      bulk async stores, and
+//   4. writes the s*s tangent block of the tile -- >50 % of all traffic --
+//      warp-cooperatively as a dense, fully coalesced stream of 16-byte stores
+//      regenerated from a few per-QP scalars kept in shared memory
+//      (Model::store_tangent), so the 288 B/QP never sit in shared memory.
+// Grid = min(#tiles, SMs x resident CTAs); tiles are strided over CTAs.
+//
+// Tail tiles (n % TILE != 0) and pointers that are not 16-byte aligned take a
+// generic-proxy path with plain coalesced loads/stores through the same stage.
+#pragma once
+#include "fcx_ptx.cuh"
+
+namespace fcx {
+
+template <int N>
+struct SegPtrs {
+    double *p[N];
+};
+
+// Accessor for one QP's slot of segment K inside a shared stage.
+template <class M, int TILE>
+struct QpView {
+    double *stage;
+    int t;
+    template <int K>
+    __device__ __forceinline__ double ld(int i) const
+    {
+        if (M::soa(K))
+            return stage[M::off(K) * TILE + i * TILE + t];
+        return stage[M::off(K) * TILE + t * M::w(K) + i];
+    }
+    template <int K>
+    __device__ __forceinline__ void st(int i, double v) const
+    {
+        if (M::soa(K))
+            stage[M::off(K) * TILE + i * TILE + t] = v;
+        else
+            stage[M::off(K) * TILE + t * M::w(K) + i] = v;
+    }
+};
+
+template <class M, int TILE>
+constexpr size_t tile_smem_bytes()
+{
+    return sizeof(double) * (2 * M::wsum() * TILE + M::aux_doubles(TILE)) + 2 * sizeof(uint64_t);
+}
+
+template <class M, int TILE>
+__global__ void __launch_bounds__(TILE, M::min_ctas())
+    fcx_tile_kernel(const __grid_constant__ typename M::Params prm,
+                    const __grid_constant__ SegPtrs<M::nseg()> io, double *__restrict__ tangent,
+                    const unsigned long long n, const int bulk_ok,
+                    unsigned char *__restrict__ flag, int *__restrict__ status)
+{
+    constexpr int NSEG = M::nseg();
+    constexpr int WSUM = M::wsum();
+    constexpr int SS = M::sdim() * M::sdim();
+    extern __shared__ __align__(128) double smem[];
+    double *aux = smem + 2 * WSUM * TILE;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(aux + M::aux_doubles(TILE));
+
+    const int tid = threadIdx.x;
+    const unsigned long long ntiles = (n + TILE - 1) / TILE;
+
+    M::init_aux(prm, aux, tid, TILE);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // thread 0 only: start the bulk loads of a full tile into stage s
+    auto issue_load = [&](unsigned long long tile, int s) {
+        const unsigned long long q0 = tile * TILE;
+        mbar_arrive_expect_tx(&bars[s], (uint32_t)(WSUM * TILE * sizeof(double)));
+        double *dst = smem + s * WSUM * TILE;
+#pragma unroll
+        for (int k = 0; k < NSEG; ++k) {
+            if (M::soa(k)) {
+#pragma unroll
+                for (int i = 0; i < M::w(k); ++i)
+                    bulk_g2s(dst + (M::off(k) + i) * TILE, io.p[k] + (size_t)i * n + q0,
+                             TILE * sizeof(double), &bars[s]);
+            } else {
+                bulk_g2s(dst + M::off(k) * TILE, io.p[k] + q0 * M::w(k),
+                         TILE * M::w(k) * sizeof(double), &bars[s]);
+            }
+        }
+    };
+    auto is_bulk = [&](unsigned long long tile) {
+        return bulk_ok && (tile + 1) * TILE <= n;
+    };
+
+    unsigned long long tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles && is_bulk(tile))
+        issue_load(tile, 0);
+
+    uint32_t parity0 = 0, parity1 = 0;
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        const unsigned long long q0 = tile * TILE;
+        const int cnt = (n - q0 < (unsigned long long)TILE) ? (int)(n - q0) : TILE;
+        double *stage = smem + s * WSUM * TILE;
+        const bool bulk = is_bulk(tile);
+
+        // prefetch the next tile of this CTA into the other stage (free since
+        // the closing barrier of the previous iteration)
+        const unsigned long long next = tile + gridDim.x;
+        if (tid == 0 && next < ntiles && is_bulk(next))
+            issue_load(next, s ^ 1);
+
+        if (bulk) {
+            if (s == 0) {
+                mbar_wait(&bars[0], parity0);
+                parity0 ^= 1;
+            } else {
+                mbar_wait(&bars[1], parity1);
+                parity1 ^= 1;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NSEG; ++k) {
+                if (M::soa(k)) {
+                    for (int i = 0; i < M::w(k); ++i)
+                        for (int j = tid; j < cnt; j += TILE)
+                            stage[(M::off(k) + i) * TILE + j] = io.p[k][(size_t)i * n + q0 + j];
+                } else {
+                    const double *src = io.p[k] + q0 * M::w(k);
+                    for (int j = tid; j < cnt * M::w(k); j += TILE)
+                        stage[M::off(k) * TILE + j] = src[j];
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- per-QP update, registers only; results go back in place ----
+        if (tid < cnt) {
+            bool plastic = false, failed = false;
+            QpView<M, TILE> v{stage, tid};
+            M::qp(prm, v, aux, tid, plastic, failed);
+            if (M::has_flag() && flag != nullptr)
+                flag[q0 + tid] = plastic ? 1 : 0;
+            if (M::has_flag() && failed && status != nullptr) {
+                atomicAdd(&status[0], 1);
+                const unsigned long long q = q0 + tid;
+                atomicMin(&status[1], q > 0x7fffffffULL ? 0x7fffffff : (int)q);
+            }
+        }
+        if (bulk)
+            fence_proxy_async_smem();
+        __syncthreads();
+
+        // ---- write back the in-place segments ----
+        if (bulk) {
+            if (tid == 0) {
+#pragma unroll
+                for (int k = 0; k < NSEG; ++k) {
+                    if (!M::wr(k))
+                        continue;
+                    if (M::soa(k)) {
+#pragma unroll
+                        for (int i = 0; i < M::w(k); ++i)
+                            bulk_s2g(io.p[k] + (size_t)i * n + q0, stage + (M::off(k) + i) * TILE,
+                                     TILE * sizeof(double));
+                    } else {
+                        bulk_s2g(io.p[k] + q0 * M::w(k), stage + M::off(k) * TILE,
+                                 TILE * M::w(k) * sizeof(double));
+                    }
+                }
+                bulk_commit();
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NSEG; ++k) {
+                if (!M::wr(k))
+                    continue;
+                if (M::soa(k)) {
+                    for (int i = 0; i < M::w(k); ++i)
+                        for (int j = tid; j < cnt; j += TILE)
+                            io.p[k][(size_t)i * n + q0 + j] = stage[(M::off(k) + i) * TILE + j];
+                } else {
+                    double *dst = io.p[k] + q0 * M::w(k);
+                    for (int j = tid; j < cnt * M::w(k); j += TILE)
+                        dst[j] = stage[M::off(k) * TILE + j];
+                }
+            }
+        }
+
+        // ---- tangent block of the tile: dense coalesced stream ----
+        M::store_tangent(prm, aux, tangent + q0 * SS, cnt, tid, TILE, bulk_ok != 0);
+
+        if (bulk && tid == 0)
+            bulk_wait_read_all();  // stage may be refilled after the barrier
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Elementwise kernel for the uniaxial constraints (s = g = 1): every array is
+// [n] doubles, so plain vectorised grid-stride access is already coalesced.
+// Each thread owns two consecutive QPs (16-byte loads/stores).
+template <class M>
+__global__ void __launch_bounds__(256)
+    fcx_uniaxial_kernel(const __grid_constant__ typename M::Params prm,
+                        const __grid_constant__ SegPtrs<M::nseg()> io,
+                        double *__restrict__ tangent, const unsigned long long n, const int vec_ok)
+{
+    constexpr int NSEG = M::nseg();
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec_ok) {
+        const unsigned long long npair = n / 2;
+        for (unsigned long long p = gtid; p < npair; p += stride) {
+            double a[NSEG], b[NSEG], ta, tb;
+#pragma unroll
+            for (int k = 0; k < NSEG; ++k) {
+                const double2 v = reinterpret_cast<const double2 *>(io.p[k])[p];
+                a[k] = v.x;
+                b[k] = v.y;
+            }
+            M::qp1(prm, a, ta);
+            M::qp1(prm, b, tb);
+#pragma unroll
+            for (int k = 0; k < NSEG; ++k)
+                if (M::wr(k))
+                    reinterpret_cast<double2 *>(io.p[k])[p] = make_double2(a[k], b[k]);
+            reinterpret_cast<double2 *>(tangent)[p] = make_double2(ta, tb);
+        }
+        if ((n & 1ULL) && gtid == 0) {
+            double a[NSEG], ta;
+#pragma unroll
+            for (int k = 0; k < NSEG; ++k)
+                a[k] = io.p[k][n - 1];
+            M::qp1(prm, a, ta);
+#pragma unroll
+            for (int k = 0; k < NSEG; ++k)
+                if (M::wr(k))
+                    io.p[k][n - 1] = a[k];
+            tangent[n - 1] = ta;
+        }
+    } else {
+        for (unsigned long long q = gtid; q < n; q += stride) {
+            double a[NSEG], ta;
+#pragma unroll
+            for (int k = 0; k < NSEG; ++k)
+                a[k] = io.p[k][q];
+            M::qp1(prm, a, ta);
+#pragma unroll
+            for (int k = 0; k < NSEG; ++k)
+                if (M::wr(k))
+                    io.p[k][q] = a[k];
+            tangent[q] = ta;
+        }
+    }
+}
+
+}  // namespace fcx

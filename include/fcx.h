@@ -1,0 +1,180 @@
+/*
+ * fcx.h -- C ABI of libfcx.so: B200-native (sm_100a, fp64) per-quadrature-point
+ * constitutive updates, the drop-in for fenics-constitutive's
+ *     IncrSmallStrainModel.evaluate(t, del_t, grad_del_u, stress, tangent, history)
+ * (reference: src/fenics_constitutive/models/interfaces.py:82-101).
+ *
+ * This header is what a maintainer of the reference would bind (ctypes / cffi /
+ * pybind11 / pyo3-free) in place of `fenics_constitutive._bindings`
+ * (reference: bindings/src/lib.rs:76-129, whose batch driver is
+ * comfe-rs/src/interfaces.rs:354-456).  Same granularity: ONE call per
+ * `evaluate`, covering all quadrature points (QPs) of the rank.
+ *
+ * Array contract (identical to the reference): flat, C-contiguous
+ * float64.  g = geometric dim, s = Mandel dim of the constraint.
+ *     grad_del_u [n][g][g]   read-only, ufl.nabla_grad convention
+ *     stress     [n][s]      in: sigma_n, out: sigma_{n+1}   (Mandel)
+ *     tangent    [n][s][s]   write-only, row-major
+ *     history    [n][dim]    in: committed values, out: trial values
+ * Mandel order [xx, yy, zz, xy, xz, yz], shear scaled by Python's 1/2**0.5
+ * (reference: models/utils.py:199-204).
+ *
+ * Two families of entry points:
+ *   fcx_<model>_evaluate       DEVICE pointers; enqueue-only on `stream`
+ *                              (a cudaStream_t passed as void*, NULL = default
+ *                              stream); never synchronises.
+ *   fcx_<model>_evaluate_host  HOST pointers (pageable or pinned); chunked,
+ *                              multi-stream H2D -> kernel -> D2H pipeline;
+ *                              returns after the results are in host memory.
+ * All functions return FCX_OK (0), a negative FCX_ERR_* code, or -- for the
+ * Mises host entry point -- the positive number of QPs whose return-mapping
+ * Newton iteration did not converge (the reference raises RuntimeError there,
+ * models/mises_plasticity_isotropic_hardening.py:141-143).
+ * No function throws, aborts or keeps a caller pointer past its return
+ * (device entry points: past completion of the enqueued work).
+ */
+#ifndef FCX_H
+#define FCX_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCX_VERSION 100 /* 0.1.0 */
+
+/* StressStrainConstraint values, reference models/interfaces.py:23-27 */
+enum fcx_constraint {
+    FCX_UNIAXIAL_STRAIN = 1, /* s=1 g=1 */
+    FCX_UNIAXIAL_STRESS = 2, /* s=1 g=1 */
+    FCX_PLANE_STRAIN = 3,    /* s=4 g=2 */
+    FCX_PLANE_STRESS = 4,    /* s=4 g=2 */
+    FCX_FULL = 5             /* s=6 g=3 */
+};
+
+enum fcx_status {
+    FCX_OK = 0,
+    FCX_ERR_CONSTRAINT = -1, /* unknown / unsupported constraint for the model   */
+    FCX_ERR_TIMESTEP = -2,   /* del_t <= 0 (reference asserts, spring_kelvin_model.py:72) */
+    FCX_ERR_NULL = -3,       /* a required pointer is NULL                        */
+    FCX_ERR_CUDA = -4,       /* a CUDA runtime call failed; see fcx_last_cuda_error() */
+    FCX_ERR_ARG = -5         /* other invalid argument                            */
+};
+
+/* History layout of the Mises plastic strain `eps_n`:
+ * AOS = the reference contract [n][6]; SOA = six planes [6][n] (device-resident
+ * state owned by a GPU solver; coalesced without staging). */
+enum fcx_layout { FCX_LAYOUT_AOS = 0, FCX_LAYOUT_SOA = 1 };
+
+int fcx_version(void);
+const char *fcx_strerror(int code);
+/* Text of the last CUDA error seen by this thread's calls ("" if none). */
+const char *fcx_last_cuda_error(void);
+/* s and g of a constraint (reference models/interfaces.py:30-73); -1 if unknown. */
+int fcx_stress_strain_dim(int constraint);
+int fcx_geometric_dim(int constraint);
+/* Bind the calling thread to a CUDA device (one rank per GPU: LOCAL_RANK). */
+int fcx_set_device(int device);
+
+/* ------------------------------------------------------------------ device */
+
+/* LinearElasticityModel.evaluate -- reference models/linear_elasticity_model.py:26-45:
+ *   stress += strain_from_grad_u(grad) @ D ;  tangent[:] = tile(D.flatten(), n)
+ * D: HOST pointer to s*s doubles (row-major), e.g. get_elastic_tangent(E,nu,c)
+ * (models/utils.py:25-93) or comfe-rs' 2mu*P_dev+3kappa*P_vol
+ * (comfe-rs/src/linear_elasticity.rs:60-73).  Copied at call time. */
+int fcx_elastic_evaluate(int constraint, const double *D_host, size_t n,
+                         const double *grad_del_u, double *stress, double *tangent,
+                         void *stream);
+
+/* VonMises3D.evaluate -- reference models/mises_plasticity_isotropic_hardening.py:57-175.
+ * params = {p_ka, p_mu, p_y0, p_y00, p_w} (HOST, :51-55).  FULL constraint only.
+ * eps_n [n][6] (or [6][n] if eps_layout == FCX_LAYOUT_SOA), alpha [n].
+ * plastic_flag: optional DEVICE u8[n], 1 where the trial state is plastic
+ *   (phitr > 0, :98); may be NULL.
+ * status: optional DEVICE int[2]; status[0] is incremented once per QP whose
+ *   Newton loop exceeded 100 iterations (:141-143), status[1] receives
+ *   min(QP index) of such points via atomicMin (caller initialises to INT_MAX);
+ *   may be NULL. */
+int fcx_mises_evaluate(const double *params_host, size_t n, const double *grad_del_u,
+                       double *stress, double *tangent, double *eps_n, double *alpha,
+                       int eps_layout, unsigned char *plastic_flag, int *status,
+                       void *stream);
+
+/* SpringKelvinModel.evaluate -- reference models/spring_kelvin_model.py:43-88.
+ * D0 (s*s), I2 (s): HOST pointers to the constants of __init__ (:24-41);
+ * mu0, lam0, mu1, tau as built there.  history: strain_visco [n][s], strain [n][s]. */
+int fcx_kelvin_evaluate(int constraint, const double *D0_host, const double *I2_host,
+                        double mu0, double lam0, double mu1, double tau, double del_t,
+                        size_t n, const double *grad_del_u, double *stress, double *tangent,
+                        double *strain_visco, double *strain, void *stream);
+
+/* SpringMaxwellModel.evaluate -- reference models/spring_maxwell_model.py:40-88.
+ * D0, D1 (s*s): HOST pointers to the constants of __init__ (:24-38). */
+int fcx_maxwell_evaluate(int constraint, const double *D0_host, const double *D1_host,
+                         double mu1, double tau, double del_t, size_t n,
+                         const double *grad_del_u, double *stress, double *tangent,
+                         double *strain_visco, double *strain, void *stream);
+
+/* strain_from_grad_u -- reference models/utils.py:132-208.  strain [n][s]. */
+int fcx_strain_from_grad_u(int constraint, size_t n, const double *grad_del_u,
+                           double *strain, void *stream);
+
+/* Companion gather: IncrementalDisplacement.evaluate_local_incremental_gradient,
+ * reference solver/_incrementalunknowns.py:19-27,40-49:
+ *   grad[c][q][i][j] = d(u - u_prev)_j / dx_i   (ufl.nabla_grad)
+ * for affine cells, from precomputed tables:
+ *   dphi_ref [nq][nd][gdim]  reference-element basis gradients at the QPs (DEVICE)
+ *   Jinv     [ncells][gdim][gdim]  dX/dx per cell (DEVICE)
+ *   dofmap   [ncells][nd]    node index of each local basis function (DEVICE, int32)
+ *   u, u_prev  blocked nodal vectors [nnodes][gdim] (DEVICE); u_prev may be NULL.
+ * Output grad [ncells*nq][gdim][gdim] is exactly the grad_del_u of the
+ * evaluate calls above (cell-major QP order, reference tests/solver/test_maps.py:119-121). */
+int fcx_gather_grad(int gdim, size_t ncells, int nq, int nd, const int *dofmap,
+                    const double *u, const double *u_prev, const double *dphi_ref,
+                    const double *Jinv, double *grad_del_u, void *stream);
+
+/* -------------------------------------------------------------------- host */
+
+int fcx_elastic_evaluate_host(int constraint, const double *D, size_t n,
+                              const double *grad_del_u, double *stress, double *tangent);
+
+/* Returns >0 = number of non-converged QPs (see above). plastic_flag: optional HOST u8[n]. */
+int fcx_mises_evaluate_host(const double *params, size_t n, const double *grad_del_u,
+                            double *stress, double *tangent, double *eps_n, double *alpha,
+                            unsigned char *plastic_flag);
+
+int fcx_kelvin_evaluate_host(int constraint, const double *D0, const double *I2, double mu0,
+                             double lam0, double mu1, double tau, double del_t, size_t n,
+                             const double *grad_del_u, double *stress, double *tangent,
+                             double *strain_visco, double *strain);
+
+int fcx_maxwell_evaluate_host(int constraint, const double *D0, const double *D1, double mu1,
+                              double tau, double del_t, size_t n, const double *grad_del_u,
+                              double *stress, double *tangent, double *strain_visco,
+                              double *strain);
+
+/* Page-lock / unlock a caller-owned host array so the *_host entry points DMA
+ * it directly (cudaHostRegister).  A solver would call this once per
+ * quadrature array at set-up (reference solver/_solver.py:75-85 is where those
+ * arrays are created). */
+int fcx_host_register(void *ptr, size_t bytes);
+int fcx_host_unregister(void *ptr);
+/* QPs per pipeline chunk of the *_host entry points (default 1<<19); 0 = query. */
+size_t fcx_host_chunk_qps(size_t new_value);
+/* Release the streams / staging buffers cached by the *_host entry points. */
+void fcx_host_release(void);
+
+/* ------------------------------------------------------------- diagnostics */
+
+/* Number of kernel launches issued by this library in this process. */
+unsigned long long fcx_launch_count(void);
+/* Select a kernel variant for experiments: key "mises_tile", "mises_compact",
+ * ...; returns previous value or FCX_ERR_ARG for an unknown key. */
+int fcx_tune(const char *key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCX_H */
