@@ -42,6 +42,10 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 
 // Tunables (fcx_tune): CTAs per SM for the persistent grid; 0 = occupancy query.
 static int g_ctas_per_sm = 0;
+// Newton iteration cap of the Mises return mapping (reference nmax = 100,
+// mises_plasticity_isotropic_hardening.py:106); lowered only by tests that
+// exercise the non-convergence reporting.
+static int g_mises_nmax = 100;
 
 constexpr int TILE = 128;
 
@@ -241,6 +245,11 @@ int fcx_tune(const char *key, int value)
         g_ctas_per_sm = value;
         return old;
     }
+    if (key && strcmp(key, "mises_nmax") == 0) {
+        const int old = g_mises_nmax;
+        g_mises_nmax = value;
+        return old;
+    }
     return FCX_ERR_ARG;
 }
 
@@ -277,7 +286,7 @@ int fcx_mises_evaluate(const double *params, size_t n, const double *grad, doubl
     if (!params || !grad || !stress || !tangent || !eps_n || !alpha)
         return FCX_ERR_NULL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MisesParams P{params[0], params[1], params[2], params[3], params[4]};
+    MisesParams P{params[0], params[1], params[2], params[3], params[4], g_mises_nmax};
     SegPtrs<4> io{{const_cast<double *>(grad), stress, eps_n, alpha}};
     bool al = aligned16(grad) && aligned16(stress) && aligned16(tangent) && aligned16(eps_n) &&
               aligned16(alpha);

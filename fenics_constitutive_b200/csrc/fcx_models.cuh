@@ -332,6 +332,7 @@ struct MaxwellModel {
 // ===========================================================================
 struct MisesParams {
     double ka, mu, y0, y00, w;  // p_ka, p_mu, p_y0, p_y00, p_w   (:51-55)
+    int nmax;                   // Newton iteration cap, 100 in the reference (:106)
 };
 
 // Scalar Newton for the plastic multiplier, :100-151.  Stays in registers.
@@ -359,7 +360,7 @@ __device__ __forceinline__ void mises_return_map(const MisesParams &P, double si
         xr = sigtrn - two_mu * gamma_0 - c23 * (P.y0 + dy * (1 - ex));  // f   (:111-121)
         xg = -two_mu - dfc * ex;                                        // df  (:123-126)
         gamma_1 = gamma_0 - xr / xg;
-        if (it > 100) {  // (:141-143)
+        if (it > P.nmax) {  // (:141-143)
             failed = true;
             break;
         }

@@ -170,8 +170,9 @@ void fcx_host_release(void);
 
 /* Number of kernel launches issued by this library in this process. */
 unsigned long long fcx_launch_count(void);
-/* Select a kernel variant for experiments: key "mises_tile", "mises_compact",
- * ...; returns previous value or FCX_ERR_ARG for an unknown key. */
+/* Tunables: "ctas_per_sm" (persistent-grid CTAs per SM, 0 = occupancy query),
+ * "mises_nmax" (Newton iteration cap, reference value 100).  Returns the
+ * previous value, or FCX_ERR_ARG for an unknown key. */
 int fcx_tune(const char *key, int value);
 
 #ifdef __cplusplus

@@ -41,6 +41,7 @@ def lib() -> ctypes.CDLL:
         u8p = ctypes.POINTER(ctypes.c_ubyte)
         sz, ci, cd = ctypes.c_size_t, ctypes.c_int, ctypes.c_double
         L.oracle_max_threads.restype = ci
+        L.oracle_has_openmp.restype = ci
         L.oracle_strain_from_grad_u.argtypes = [ci, sz, dp, dp]
         L.oracle_strain_from_grad_u.restype = None
         L.oracle_lame_parameters.argtypes = [cd, cd, dp, dp]
@@ -66,4 +67,14 @@ def lib() -> ctypes.CDLL:
 
 
 def max_threads() -> int:
-    return int(lib().oracle_max_threads())
+    """Host threads the oracle may use: the CPUs this process is allowed to run on
+    (OMP_NUM_THREADS is often pinned to 1 in ML images; `num_threads(n)` in
+    fcx_oracle.c overrides it).  1 if the library was built without OpenMP."""
+    import os
+
+    if int(lib().oracle_has_openmp()) == 0:
+        return 1
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
