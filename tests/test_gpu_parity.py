@@ -208,6 +208,31 @@ def test_visco_100_increments_history_carry(cls, ocls):
             assert_close(tg.cpu().numpy(), ref_t, 36, TOL_ELASTIC, f"tangent step {step}")
 
 
+@pytest.mark.parametrize("name", CONSTRAINT_NAMES)
+def test_elastic_visco_bit_exact_vs_oracle(name):
+    """Stronger than the 1e-12 bar: the library is built with -fmad=false and follows
+    the oracle's operation order (oracle: -ffp-contract=off), and + - * / are
+    correctly rounded on both sides, so the non-transcendental models agree with
+    the oracle bit for bit."""
+    c = C[name]
+    g, s = c.geometric_dim, c.stress_strain_dim
+    n = 30_011
+    rng = np.random.default_rng(123)
+    grad = rng.standard_normal(n * g * g) * 1e-3
+    init = [rng.standard_normal(n * s) * 0.05, rng.standard_normal(n * s) * 1e-4, rng.standard_normal(n * s) * 1e-3]
+    for cls, ocls, params in ((LinearElasticityModel, om.LinearElasticityModel, ELASTIC),
+                              (SpringKelvinModel, om.SpringKelvinModel, VISCO),
+                              (SpringMaxwellModel, om.SpringMaxwellModel, VISCO)):
+        ref = [a.copy() for a in init]
+        got = [a.copy() for a in init]
+        ref_t, got_t = np.zeros(n * s * s), np.zeros(n * s * s)
+        hist = lambda v: None if cls is LinearElasticityModel else {"strain_visco": v[1], "strain": v[2]}  # noqa: E731
+        ocls(params, c).evaluate(0, 0.7, grad, ref[0], ref_t, hist(ref))
+        run(cls(params, c), 0.7, grad, got[0], got_t, hist(got), "device")
+        for a, b in zip(got + [got_t], ref + [ref_t]):
+            assert np.array_equal(a, b), f"{cls.__name__} {name} not bit-exact"
+
+
 # ----------------------------------------------------------------- edge cases
 
 def test_empty_inputs():
