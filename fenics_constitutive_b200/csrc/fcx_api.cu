@@ -47,15 +47,15 @@ static int g_ctas_per_sm = 0;
 // exercise the non-convergence reporting.
 static int g_mises_nmax = 100;
 
-constexpr int TILE = 128;
+// Tunables (fcx_tune): QPs per tile (64/128/256) and L2 cache-hint flags.
+static int g_tile = 128;
+static int g_hints = 0;  // bit1: evict_first on bulk loads, bit2: on bulk stores
 
-template <class M>
-static int launch_tile(const typename M::Params &prm, const SegPtrs<M::nseg()> &io,
-                       double *tangent, size_t n, bool bulk_ok, unsigned char *flag, int *status,
-                       cudaStream_t stream)
+template <class M, int TILE>
+static int launch_tile_t(const typename M::Params &prm, const SegPtrs<M::nseg()> &io,
+                         double *tangent, size_t n, bool bulk_ok, unsigned char *flag,
+                         int *status, cudaStream_t stream)
 {
-    if (n == 0)
-        return FCX_OK;
     auto kern = fcx_tile_kernel<M, TILE>;
     constexpr size_t smem = tile_smem_bytes<M, TILE>();
     static int occ = -1;  // per instantiation
@@ -74,10 +74,25 @@ static int launch_tile(const typename M::Params &prm, const SegPtrs<M::nseg()> &
     unsigned long long grid = (unsigned long long)sm_count() * per_sm;
     if (grid > ntiles)
         grid = ntiles;
-    kern<<<(unsigned)grid, TILE, smem, stream>>>(prm, io, tangent, (unsigned long long)n,
-                                                 bulk_ok ? 1 : 0, flag, status);
+    const int flags = (bulk_ok ? 1 : 0) | (g_hints & 6);
+    kern<<<(unsigned)grid, TILE, smem, stream>>>(prm, io, tangent, (unsigned long long)n, flags,
+                                                 flag, status);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return note_cuda_error(cudaGetLastError(), "fcx_tile_kernel launch");
+}
+
+template <class M>
+static int launch_tile(const typename M::Params &prm, const SegPtrs<M::nseg()> &io,
+                       double *tangent, size_t n, bool bulk_ok, unsigned char *flag, int *status,
+                       cudaStream_t stream)
+{
+    if (n == 0)
+        return FCX_OK;
+    switch (g_tile) {
+    case 64: return launch_tile_t<M, 64>(prm, io, tangent, n, bulk_ok, flag, status, stream);
+    case 256: return launch_tile_t<M, 256>(prm, io, tangent, n, bulk_ok, flag, status, stream);
+    default: return launch_tile_t<M, 128>(prm, io, tangent, n, bulk_ok, flag, status, stream);
+    }
 }
 
 template <class M>
@@ -208,6 +223,32 @@ __global__ void strain_kernel(const double *__restrict__ grad, double *__restric
     }
 }
 
+// Diagnostic: the simplest possible streaming kernel with the Mises kernel's
+// read:write byte mix (per pair of QPs: 22 double2 read, 49 double2 written),
+// perfectly coalesced, no shared memory, no arithmetic to speak of.  Its
+// throughput is the practical DRAM ceiling for this mix on the box at hand.
+template <int NR, int NW>
+__global__ void __launch_bounds__(256)
+    diag_stream_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst,
+                       unsigned long long iters)
+{
+    const unsigned long long T = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long gt = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned long long it = 0; it < iters; ++it) {
+        double acc = 0.0;
+        double2 v[NR];
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+            v[k] = src[(it * NR + k) * T + gt];
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+            acc += v[k].x + v[k].y;
+#pragma unroll
+        for (int k = 0; k < NW; ++k)
+            st_stream_v2(reinterpret_cast<double *>(dst + (it * NW + k) * T + gt), acc, acc + k);
+    }
+}
+
 }  // namespace fcx
 
 using namespace fcx;
@@ -245,12 +286,40 @@ int fcx_tune(const char *key, int value)
         g_ctas_per_sm = value;
         return old;
     }
+    if (key && strcmp(key, "tile") == 0) {
+        if (value != 64 && value != 128 && value != 256)
+            return FCX_ERR_ARG;
+        const int old = g_tile;
+        g_tile = value;
+        return old;
+    }
+    if (key && strcmp(key, "l2_hints") == 0) {
+        const int old = g_hints;
+        g_hints = value;
+        return old;
+    }
     if (key && strcmp(key, "mises_nmax") == 0) {
         const int old = g_mises_nmax;
         g_mises_nmax = value;
         return old;
     }
     return FCX_ERR_ARG;
+}
+
+/* Diagnostic stream with the Mises byte mix; n_qps is rounded down to a whole
+ * number of grid iterations.  Returns the number of QP-equivalents processed. */
+long long fcx_diag_stream_mix(const double *src, double *dst, size_t n_qps, void *stream)
+{
+    const unsigned long long threads = (unsigned long long)sm_count() * 8 * 256;
+    const unsigned long long iters = (n_qps / 2) / threads;
+    if (iters == 0)
+        return 0;
+    diag_stream_kernel<22, 49><<<sm_count() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const double2 *>(src), reinterpret_cast<double2 *>(dst), iters);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (note_cuda_error(cudaGetLastError(), "diag_stream_kernel launch") != FCX_OK)
+        return FCX_ERR_CUDA;
+    return (long long)(iters * threads * 2);
 }
 
 int fcx_set_device(int device)

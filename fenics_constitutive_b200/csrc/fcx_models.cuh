@@ -89,7 +89,7 @@ struct ElasticModel {
     static constexpr __host__ __device__ bool soa(int) { return false; }
     static constexpr __host__ __device__ int sdim() { return S; }
     static constexpr __host__ __device__ int aux_doubles(int) { return S * S; }
-    static constexpr __host__ __device__ int min_ctas() { return 4; }
+    static constexpr __host__ __device__ int min_ctas(int tile) { return 512 / tile; }
     static constexpr __host__ __device__ bool has_flag() { return false; }
 
     __device__ static void init_aux(const Params &p, double *aux, int tid, int nthreads)
@@ -167,7 +167,7 @@ struct KelvinModel {
     static constexpr __host__ __device__ bool soa(int) { return false; }
     static constexpr __host__ __device__ int sdim() { return S; }
     static constexpr __host__ __device__ int aux_doubles(int) { return S * S; }
-    static constexpr __host__ __device__ int min_ctas() { return 3; }
+    static constexpr __host__ __device__ int min_ctas(int tile) { return 512 / tile; }
     static constexpr __host__ __device__ bool has_flag() { return false; }
 
     __device__ static void init_aux(const Params &p, double *aux, int tid, int nthreads)
@@ -258,7 +258,7 @@ struct MaxwellModel {
     static constexpr __host__ __device__ bool soa(int) { return false; }
     static constexpr __host__ __device__ int sdim() { return S; }
     static constexpr __host__ __device__ int aux_doubles(int) { return S * S; }
-    static constexpr __host__ __device__ int min_ctas() { return 3; }
+    static constexpr __host__ __device__ int min_ctas(int tile) { return 512 / tile; }
     static constexpr __host__ __device__ bool has_flag() { return false; }
 
     __device__ static void init_aux(const Params &p, double *aux, int tid, int nthreads)
@@ -381,7 +381,7 @@ struct MisesModel {
     static constexpr __host__ __device__ bool soa(int k) { return EPS_SOA && k == 2; }
     static constexpr __host__ __device__ int sdim() { return 6; }
     static constexpr __host__ __device__ int aux_doubles(int tile) { return REC * tile; }
-    static constexpr __host__ __device__ int min_ctas() { return 4; }
+    static constexpr __host__ __device__ int min_ctas(int tile) { return 512 / tile; }
     static constexpr __host__ __device__ bool has_flag() { return true; }
 
     __device__ static void init_aux(const Params &, double *, int, int) {}

@@ -63,6 +63,33 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
         : "memory");
 }
 
+// L2 eviction-priority policy for data that is touched exactly once.
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ void bulk_g2s_hint(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                              uint64_t *bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+        "l"(__cvta_generic_to_global(gmem_src)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+__device__ __forceinline__ void bulk_s2g_hint(void *gmem_dst, const void *smem_src, uint32_t bytes,
+                                              uint64_t policy)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::
+                     "l"(__cvta_generic_to_global(gmem_dst)),
+                 "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
+                 : "memory");
+}
+
 // shared -> global bulk copy, tracked by the issuing thread's bulk async-group.
 __device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes)
 {

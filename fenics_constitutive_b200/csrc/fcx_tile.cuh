@@ -60,12 +60,18 @@ constexpr size_t tile_smem_bytes()
 }
 
 template <class M, int TILE>
-__global__ void __launch_bounds__(TILE, M::min_ctas())
+__global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
     fcx_tile_kernel(const __grid_constant__ typename M::Params prm,
                     const __grid_constant__ SegPtrs<M::nseg()> io, double *__restrict__ tangent,
-                    const unsigned long long n, const int bulk_ok,
+                    const unsigned long long n, const int flags,
                     unsigned char *__restrict__ flag, int *__restrict__ status)
 {
+    // flags: bit0 = bulk (TMA) path allowed (all pointers 16-byte aligned),
+    //        bit1 = L2 evict_first hint on the bulk loads, bit2 = on the bulk stores
+    const bool bulk_ok = (flags & 1) != 0;
+    const bool hint_ld = (flags & 2) != 0;
+    const bool hint_st = (flags & 4) != 0;
+    const uint64_t pol = policy_evict_first();
     constexpr int NSEG = M::nseg();
     constexpr int WSUM = M::wsum();
     constexpr int SS = M::sdim() * M::sdim();
@@ -96,6 +102,9 @@ __global__ void __launch_bounds__(TILE, M::min_ctas())
                 for (int i = 0; i < M::w(k); ++i)
                     bulk_g2s(dst + (M::off(k) + i) * TILE, io.p[k] + (size_t)i * n + q0,
                              TILE * sizeof(double), &bars[s]);
+            } else if (hint_ld) {
+                bulk_g2s_hint(dst + M::off(k) * TILE, io.p[k] + q0 * M::w(k),
+                              TILE * M::w(k) * sizeof(double), &bars[s], pol);
             } else {
                 bulk_g2s(dst + M::off(k) * TILE, io.p[k] + q0 * M::w(k),
                          TILE * M::w(k) * sizeof(double), &bars[s]);
@@ -177,6 +186,9 @@ __global__ void __launch_bounds__(TILE, M::min_ctas())
                         for (int i = 0; i < M::w(k); ++i)
                             bulk_s2g(io.p[k] + (size_t)i * n + q0, stage + (M::off(k) + i) * TILE,
                                      TILE * sizeof(double));
+                    } else if (hint_st) {
+                        bulk_s2g_hint(io.p[k] + q0 * M::w(k), stage + M::off(k) * TILE,
+                                      TILE * M::w(k) * sizeof(double), pol);
                     } else {
                         bulk_s2g(io.p[k] + q0 * M::w(k), stage + M::off(k) * TILE,
                                  TILE * M::w(k) * sizeof(double));
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(TILE, M::min_ctas())
         }
 
         // ---- tangent block of the tile: dense coalesced stream ----
-        M::store_tangent(prm, aux, tangent + q0 * SS, cnt, tid, TILE, bulk_ok != 0);
+        M::store_tangent(prm, aux, tangent + q0 * SS, cnt, tid, TILE, bulk_ok);
 
         if (bulk && tid == 0)
             bulk_wait_read_all();  // stage may be refilled after the barrier

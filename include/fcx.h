@@ -175,6 +175,12 @@ unsigned long long fcx_launch_count(void);
  * previous value, or FCX_ERR_ARG for an unknown key. */
 int fcx_tune(const char *key, int value);
 
+/* Streaming kernel with the Mises kernel's read:write byte mix (176 B read,
+ * 392 B written per QP-equivalent), perfectly coalesced: measures the practical
+ * DRAM ceiling for that mix.  src holds >= 22*n doubles, dst >= 49*n doubles
+ * (DEVICE).  Returns the QP-equivalents actually processed (<= n_qps). */
+long long fcx_diag_stream_mix(const double *src, double *dst, size_t n_qps, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

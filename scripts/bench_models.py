@@ -125,6 +125,29 @@ def main():
             report(f"{cls.__name__}_{c.name}", 8 * (g * g + 6 * s + s * s), ms)
             del grad, stress, ev, et, tangent
 
+    # --- companion gather: ~1M P2 tets (BASELINE config 5 mesh size), q_degree 2 ---
+    from fenics_constitutive_b200 import gather as G
+
+    coords, cv, dofmap = G.unit_cube_p2_tets(55, 55, 55)
+    Jinv = G.affine_inverse_jacobians(coords, cv)
+    pts, _ = G.simplex_quadrature(3, 2)
+    op = G.IncrementalGradient(3, dofmap, G.lagrange_gradients(3, 2, pts), Jinv)
+    u = rnd(coords.size, 1e-3)
+    u_prev = rnd(coords.size, 1e-3)
+    gout = torch.empty(op.num_qps * 9, dtype=torch.float64, device=dev)
+    nq_total = op.num_qps
+    for tag, prev in (("u_and_u_prev", u_prev), ("du_only", None)):
+        ms = time_steps(lambda i: op.evaluate(u, prev, gout), K)
+        # compulsory bytes per cell: dofmap 40 + Jinv 72 + out 288 (+ nodal values, L2-resident)
+        bytes_cell = 40 + 72 + 288
+        gbs = bytes_cell * op.ncells / (ms * 1e-3) / 1e9
+        row = {"kernel": f"gather_P2tet_q2_{tag}", "cells": op.ncells, "qps": nq_total, "ms": ms,
+               "qp_per_s": nq_total / (ms * 1e-3), "bytes_per_cell_compulsory": bytes_cell,
+               "GBps_compulsory": gbs, "frac_of_measured_hbm": gbs / P}
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+    del gout, u, u_prev, op
+
     # --- reference point: torch copy bandwidth on this very GPU ---
     a = torch.empty(1 << 29, dtype=torch.float64, device=dev)
     b = torch.empty_like(a)

@@ -1,0 +1,123 @@
+"""Companion gather.  CPU part: tables, mesh and the oracle
+restatement reproduce analytic gradients.  GPU part: fcx_gather_grad vs the oracle.
+The reference for this row is a dolfinx Expression (absent here), so parity is
+anchored on the mathematical definition: nabla_grad of a P2 field is exact for
+quadratic displacement fields."""
+import numpy as np
+import pytest
+
+from fenics_constitutive_b200 import gather as G
+from oracle import models as om
+
+
+def quad_field(x):
+    """A quadratic vector field and its nabla_grad: grad[i][j] = d u_j / d x_i."""
+    A = np.array([[0.3, -0.2, 0.5], [0.1, 0.4, -0.6], [-0.7, 0.2, 0.9]])
+    Q = np.array([[[0.2, 0.1, 0.0], [0.1, -0.3, 0.4], [0.0, 0.4, 0.5]],
+                  [[-0.1, 0.2, 0.3], [0.2, 0.6, 0.0], [0.3, 0.0, -0.2]],
+                  [[0.4, 0.0, -0.1], [0.0, 0.1, 0.2], [-0.1, 0.2, 0.3]]])  # symmetric per component
+    u = x @ A.T + np.einsum("ni,jik,nk->nj", x, Q, x)
+    grad = A.T[None, :, :] + 2.0 * np.einsum("jik,nk->nij", Q, x)          # [n][i][j]
+    return u, grad
+
+
+def test_basis_gradients_sum_to_zero():
+    for gdim in (1, 2, 3):
+        for degree in (1, 2):
+            pts, w = G.simplex_quadrature(gdim, 2)
+            d = G.lagrange_gradients(gdim, degree, pts)
+            assert np.allclose(d.sum(axis=1), 0.0, atol=1e-14)
+            assert np.isclose(w.sum(), [1.0, 0.5, 1 / 6][gdim - 1])
+
+
+def test_mesh_and_oracle_gather_exact_for_quadratics():
+    coords, cv, dofmap = G.unit_cube_p2_tets(3, 2, 2)
+    assert dofmap.shape == (6 * 12, 10) and coords.shape == (7 * 5 * 5, 3)
+    Jinv = G.affine_inverse_jacobians(coords, cv)
+    vol = 1.0 / (6.0 * np.abs(np.linalg.det(Jinv)))
+    assert np.isclose(vol.sum(), 1.0) and np.all(np.linalg.det(Jinv) > 0)
+    # edge dofs really are the midpoints
+    for e, (i, j) in enumerate(G._EDGES[3]):
+        assert np.allclose(coords[dofmap[:, 4 + e]], 0.5 * (coords[cv[:, i]] + coords[cv[:, j]]))
+    pts, _ = G.simplex_quadrature(3, 2)
+    dphi = G.lagrange_gradients(3, 2, pts)
+    u, _ = quad_field(coords)
+    u_prev = 0.25 * u
+    grad = om.gather_grad(3, dofmap, u.reshape(-1), u_prev.reshape(-1), dphi, Jinv).reshape(-1, 4, 3, 3)
+    # physical QP coordinates
+    xq = np.einsum("qa,cad->cqd", np.concatenate([1 - pts.sum(1, keepdims=True), pts], 1), coords[cv])
+    _, exact = quad_field(xq.reshape(-1, 3))
+    assert np.allclose(grad.reshape(-1, 3, 3), 0.75 * exact, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_prev", [True, False])
+def test_gpu_gather_vs_oracle_p2_tets(with_prev):
+    import torch
+
+    coords, cv, dofmap = G.unit_cube_p2_tets(7, 5, 6)  # 1260 cells: ragged vs the 128-cell CTA
+    Jinv = G.affine_inverse_jacobians(coords, cv)
+    pts, _ = G.simplex_quadrature(3, 2)
+    dphi = G.lagrange_gradients(3, 2, pts)
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal(coords.size)
+    u_prev = rng.standard_normal(coords.size) if with_prev else None
+    ref = om.gather_grad(3, dofmap, u, u_prev, dphi, Jinv)
+    op = G.IncrementalGradient(3, dofmap, dphi, Jinv)
+    out = torch.full((op.num_qps * 9,), float("nan"), dtype=torch.float64, device="cuda")
+    op.evaluate(torch.from_numpy(u).cuda(), torch.from_numpy(u_prev).cuda() if with_prev else None, out)
+    got = out.cpu().numpy()
+    scale = np.abs(ref).max()
+    assert np.max(np.abs(got - ref)) <= 1e-12 * scale
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gdim,degree,qdeg", [(3, 1, 1), (2, 2, 2), (2, 1, 1), (1, 2, 2), (1, 1, 1), (3, 2, 1), (2, 2, 1)])
+def test_gpu_gather_other_elements(gdim, degree, qdeg):
+    """Every compiled specialisation plus the generic fallback ((2,6,1) has none)."""
+    import torch
+
+    rng = np.random.default_rng(gdim * 10 + degree)
+    pts, _ = G.simplex_quadrature(gdim, qdeg)
+    dphi = G.lagrange_gradients(gdim, degree, pts)
+    nd = dphi.shape[1]
+    ncells, nnodes = 1000 + gdim, 700
+    dofmap = rng.integers(0, nnodes, size=(ncells, nd)).astype(np.int32)
+    Jinv = rng.standard_normal((ncells, gdim, gdim)) + 3 * np.eye(gdim)
+    u, u_prev = rng.standard_normal(nnodes * gdim), rng.standard_normal(nnodes * gdim)
+    ref = om.gather_grad(gdim, dofmap, u, u_prev, dphi, Jinv)
+    op = G.IncrementalGradient(gdim, dofmap, dphi, Jinv)
+    out = torch.zeros(op.num_qps * gdim * gdim, dtype=torch.float64, device="cuda")
+    op.evaluate(torch.from_numpy(u).cuda(), torch.from_numpy(u_prev).cuda(), out)
+    assert np.max(np.abs(out.cpu().numpy() - ref)) <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_gpu_gather_feeds_evaluate():
+    """form() order of the reference (solver/_lawonsubmesh.py:72-95): gather, then evaluate."""
+    import torch
+
+    from fenics_constitutive_b200 import synthetic
+    from fenics_constitutive_b200.models import VonMises3D
+
+    coords, cv, dofmap = G.unit_cube_p2_tets(4, 4, 4)
+    Jinv = G.affine_inverse_jacobians(coords, cv)
+    pts, _ = G.simplex_quadrature(3, 2)
+    dphi = G.lagrange_gradients(3, 2, pts)
+    u, _ = quad_field(coords)
+    u = (u * 6e-3).reshape(-1)
+    op = G.IncrementalGradient(3, dofmap, dphi, Jinv)
+    n = op.num_qps
+    grad = torch.empty(n * 9, dtype=torch.float64, device="cuda")
+    op.evaluate(torch.from_numpy(u).cuda(), None, grad)
+    z = lambda m: torch.zeros(m, dtype=torch.float64, device="cuda")  # noqa: E731
+    st, tg, ep, al = z(n * 6), z(n * 36), z(n * 6), z(n)
+    VonMises3D(synthetic.MISES_PARAMS).evaluate(0.0, 1.0, grad, st, tg, {"eps_n": ep, "alpha": al})
+    g_ref = om.gather_grad(3, dofmap, u, None, dphi, Jinv)
+    ref = [np.zeros(n * 6), np.zeros(n * 36), np.zeros(n * 6), np.zeros(n)]
+    orc = om.VonMises3D(synthetic.MISES_PARAMS)
+    orc.evaluate(0, 1, g_ref, ref[0], ref[1], {"eps_n": ref[2], "alpha": ref[3]})
+    assert 0.02 < orc.plastic_flag.mean() < 0.98
+    from _util import TOL_PLASTIC, assert_close
+    assert_close(st.cpu().numpy(), ref[0], 6, TOL_PLASTIC, "stress")
+    assert_close(tg.cpu().numpy(), ref[1], 36, TOL_PLASTIC, "tangent")
