@@ -9,6 +9,7 @@
 
 #include "../../include/fcx.h"
 #include "fcx_internal.h"
+#include "fcx_mises_ostage.cuh"
 #include "fcx_models.cuh"
 
 namespace fcx {
@@ -49,12 +50,19 @@ static int g_mises_nmax = 100;
 
 // Tunables (fcx_tune): QPs per tile (64/128/256) and L2 cache-hint flags.
 static int g_tile = 128;
-static int g_hints = 0;  // bit1: evict_first on bulk loads, bit2: on bulk stores
+// Mises AoS kernel: 1 = output-staged (tangent through shared memory + bulk
+// store, fcx_mises_ostage.cuh), 0 = generic tile pipeline with the
+// warp-cooperative tangent store.
+static int g_mises_variant = 1;
+// Output-staged kernel: hand tiles out through an atomic ticket counter.
+static int g_dynamic_tiles = 0;
+static int g_hints = 8;  // bit1: evict_first on bulk loads, bit2: on bulk stores,
+                         // bit3: constant tangents written by bulk stores from shared memory
 
 template <class M, int TILE>
 static int launch_tile_t(const typename M::Params &prm, const SegPtrs<M::nseg()> &io,
                          double *tangent, size_t n, bool bulk_ok, unsigned char *flag,
-                         int *status, cudaStream_t stream)
+                         int *status, cudaStream_t stream, unsigned long long qbase)
 {
     auto kern = fcx_tile_kernel<M, TILE>;
     constexpr size_t smem = tile_smem_bytes<M, TILE>();
@@ -74,9 +82,9 @@ static int launch_tile_t(const typename M::Params &prm, const SegPtrs<M::nseg()>
     unsigned long long grid = (unsigned long long)sm_count() * per_sm;
     if (grid > ntiles)
         grid = ntiles;
-    const int flags = (bulk_ok ? 1 : 0) | (g_hints & 6);
+    const int flags = (bulk_ok ? 1 : 0) | (g_hints & 14);
     kern<<<(unsigned)grid, TILE, smem, stream>>>(prm, io, tangent, (unsigned long long)n, flags,
-                                                 flag, status);
+                                                 flag, status, qbase);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return note_cuda_error(cudaGetLastError(), "fcx_tile_kernel launch");
 }
@@ -84,15 +92,63 @@ static int launch_tile_t(const typename M::Params &prm, const SegPtrs<M::nseg()>
 template <class M>
 static int launch_tile(const typename M::Params &prm, const SegPtrs<M::nseg()> &io,
                        double *tangent, size_t n, bool bulk_ok, unsigned char *flag, int *status,
-                       cudaStream_t stream)
+                       cudaStream_t stream, unsigned long long qbase = 0)
 {
     if (n == 0)
         return FCX_OK;
     switch (g_tile) {
-    case 64: return launch_tile_t<M, 64>(prm, io, tangent, n, bulk_ok, flag, status, stream);
-    case 256: return launch_tile_t<M, 256>(prm, io, tangent, n, bulk_ok, flag, status, stream);
-    default: return launch_tile_t<M, 128>(prm, io, tangent, n, bulk_ok, flag, status, stream);
+    case 64: return launch_tile_t<M, 64>(prm, io, tangent, n, bulk_ok, flag, status, stream, qbase);
+    case 256: return launch_tile_t<M, 256>(prm, io, tangent, n, bulk_ok, flag, status, stream, qbase);
+    default: return launch_tile_t<M, 128>(prm, io, tangent, n, bulk_ok, flag, status, stream, qbase);
     }
+}
+
+// Output-staged Mises kernel (fcx_mises_ostage.cuh) over `ntiles` full tiles.
+template <int TILE, int MINCTAS>
+static int launch_mises_ostage(const MisesParams &P, const double *grad, double *stress,
+                               double *tangent, double *eps_n, double *alpha,
+                               unsigned long long ntiles, unsigned char *flag, int *status,
+                               cudaStream_t stream)
+{
+    auto kern = fcx_mises_ostage_kernel<TILE, MINCTAS>;
+    constexpr size_t smem = mises_ostage_smem_bytes<TILE>();
+    static int occ = -1;
+    if (occ < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaFuncSetAttribute(mises_ostage)");
+        int o = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, TILE, smem);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaOccupancy(mises_ostage)");
+        occ = o > 0 ? o : 1;
+    }
+    const int per_sm = g_ctas_per_sm > 0 ? g_ctas_per_sm : occ;
+    unsigned long long grid = (unsigned long long)sm_count() * per_sm;
+    if (grid > ntiles)
+        grid = ntiles;
+    unsigned long long *ticket = nullptr;
+    if (g_dynamic_tiles) {
+        // one counter per device, zeroed on the launch stream before every launch
+        int dev = 0;
+        cudaGetDevice(&dev);
+        static unsigned long long *counters[64] = {nullptr};
+        if (dev >= 0 && dev < 64) {
+            if (counters[dev] == nullptr &&
+                cudaMalloc(&counters[dev], sizeof(unsigned long long)) != cudaSuccess)
+                counters[dev] = nullptr;
+            ticket = counters[dev];
+        }
+        if (ticket != nullptr) {
+            cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream);
+            if (e != cudaSuccess)
+                return note_cuda_error(e, "cudaMemsetAsync(ticket)");
+        }
+    }
+    kern<<<(unsigned)grid, TILE, smem, stream>>>(P, grad, stress, tangent, eps_n, alpha, ntiles,
+                                                 flag, status, ticket);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "fcx_mises_ostage_kernel launch");
 }
 
 template <class M>
@@ -298,6 +354,18 @@ int fcx_tune(const char *key, int value)
         g_hints = value;
         return old;
     }
+    if (key && strcmp(key, "mises_variant") == 0) {
+        if (value != 0 && value != 1)
+            return FCX_ERR_ARG;
+        const int old = g_mises_variant;
+        g_mises_variant = value;
+        return old;
+    }
+    if (key && strcmp(key, "dynamic_tiles") == 0) {
+        const int old = g_dynamic_tiles;
+        g_dynamic_tiles = value ? 1 : 0;
+        return old;
+    }
     if (key && strcmp(key, "mises_nmax") == 0) {
         const int old = g_mises_nmax;
         g_mises_nmax = value;
@@ -365,6 +433,27 @@ int fcx_mises_evaluate(const double *params, size_t n, const double *grad, doubl
     }
     if (eps_layout != FCX_LAYOUT_AOS)
         return FCX_ERR_ARG;
+    if (g_mises_variant == 1 && al && g_tile != 256) {
+        // full tiles through the output-staged kernel, the tail (< one tile)
+        // through the generic pipeline
+        const size_t T = (size_t)g_tile;
+        const unsigned long long ntiles = n / T;
+        const size_t nfull = (size_t)ntiles * T;
+        int rc = FCX_OK;
+        if (ntiles > 0)
+            rc = (g_tile == 64)
+                     ? launch_mises_ostage<64, 8>(P, grad, stress, tangent, eps_n, alpha, ntiles,
+                                                  plastic_flag, status, st)
+                     : launch_mises_ostage<128, 4>(P, grad, stress, tangent, eps_n, alpha, ntiles,
+                                                   plastic_flag, status, st);
+        if (rc != FCX_OK || nfull == n)
+            return rc;
+        SegPtrs<4> tail{{const_cast<double *>(grad) + nfull * 9, stress + nfull * 6,
+                         eps_n + nfull * 6, alpha + nfull}};
+        return launch_tile<MisesModel<false>>(P, tail, tangent + nfull * 36, n - nfull, al,
+                                              plastic_flag ? plastic_flag + nfull : nullptr,
+                                              status, st, nfull);
+    }
     return launch_tile<MisesModel<false>>(P, io, tangent, n, al, plastic_flag, status, st);
 }
 

@@ -88,14 +88,16 @@ struct ElasticModel {
     static constexpr __host__ __device__ bool wr(int k) { return k == 1; }
     static constexpr __host__ __device__ bool soa(int) { return false; }
     static constexpr __host__ __device__ int sdim() { return S; }
-    static constexpr __host__ __device__ int aux_doubles(int) { return S * S; }
+    // aux = the s*s tangent repeated for CQ QPs: source block of the bulk tangent stores
+    static constexpr __host__ __device__ int const_tangent_qps() { return 32; }
+    static constexpr __host__ __device__ int aux_doubles(int) { return 32 * S * S; }
     static constexpr __host__ __device__ int min_ctas(int tile) { return 512 / tile; }
     static constexpr __host__ __device__ bool has_flag() { return false; }
 
     __device__ static void init_aux(const Params &p, double *aux, int tid, int nthreads)
     {
-        for (int i = tid; i < S * S; i += nthreads)
-            aux[i] = p.D[i];
+        for (int i = tid; i < 32 * S * S; i += nthreads)
+            aux[i] = p.D[i % (S * S)];
     }
 
     // stress += strain_increment @ D   (:44)
@@ -166,14 +168,16 @@ struct KelvinModel {
     static constexpr __host__ __device__ bool wr(int k) { return k >= 1; }
     static constexpr __host__ __device__ bool soa(int) { return false; }
     static constexpr __host__ __device__ int sdim() { return S; }
-    static constexpr __host__ __device__ int aux_doubles(int) { return S * S; }
+    // aux = the s*s tangent repeated for CQ QPs: source block of the bulk tangent stores
+    static constexpr __host__ __device__ int const_tangent_qps() { return 32; }
+    static constexpr __host__ __device__ int aux_doubles(int) { return 32 * S * S; }
     static constexpr __host__ __device__ int min_ctas(int tile) { return 512 / tile; }
     static constexpr __host__ __device__ bool has_flag() { return false; }
 
     __device__ static void init_aux(const Params &p, double *aux, int tid, int nthreads)
     {
-        for (int i = tid; i < S * S; i += nthreads)
-            aux[i] = p.Dt[i];
+        for (int i = tid; i < 32 * S * S; i += nthreads)
+            aux[i] = p.Dt[i % (S * S)];
     }
 
     __device__ static __forceinline__ void update(const Params &p, const double *g, double *sig,
@@ -257,14 +261,16 @@ struct MaxwellModel {
     static constexpr __host__ __device__ bool wr(int k) { return k >= 1; }
     static constexpr __host__ __device__ bool soa(int) { return false; }
     static constexpr __host__ __device__ int sdim() { return S; }
-    static constexpr __host__ __device__ int aux_doubles(int) { return S * S; }
+    // aux = the s*s tangent repeated for CQ QPs: source block of the bulk tangent stores
+    static constexpr __host__ __device__ int const_tangent_qps() { return 32; }
+    static constexpr __host__ __device__ int aux_doubles(int) { return 32 * S * S; }
     static constexpr __host__ __device__ int min_ctas(int tile) { return 512 / tile; }
     static constexpr __host__ __device__ bool has_flag() { return false; }
 
     __device__ static void init_aux(const Params &p, double *aux, int tid, int nthreads)
     {
-        for (int i = tid; i < S * S; i += nthreads)
-            aux[i] = p.Dt[i];
+        for (int i = tid; i < 32 * S * S; i += nthreads)
+            aux[i] = p.Dt[i % (S * S)];
     }
 
     __device__ static __forceinline__ void update(const Params &p, const double *g, double *sig,
@@ -369,6 +375,80 @@ __device__ __forceinline__ void mises_return_map(const MisesParams &P, double si
     gamma = gamma_1;
 }
 
+// One quadrature point of VonMises3D.evaluate (:75-175), registers only.
+// In/out: sig (sigma_n -> sigma_{n+1}), ep (eps_n), alpha.  Out: the four
+// tangent coefficients
+//   coef[0] = ka + cpp*xpp_diag   coef[1] = ka + cpp*xpp_off   (volumetric 3x3 block)
+//   coef[2] = cpp = 2mu(1 - 2mu*xc2)                            (shear diagonal)
+//   coef[3] = cnn = 4mu^2 (xc2 - xc1)                           (weight of xn (x) xn)
+// and the flow direction xn (zero for an elastic point), from which
+// aah = ka*xioi + cpp*xpp + cnn*outer(xn, xn) (:170-175) is regenerated.
+__device__ __forceinline__ void mises_point(const MisesParams &P, const double *g, double *sig,
+                                            double *ep, double &alpha, double *coef, double *xn,
+                                            bool &plastic, bool &failed)
+{
+    const double alpha_n = alpha;
+    const double c23 = sqrt23();
+    const double two_mu = 2 * P.mu;
+    double eps[6];
+    mandel_strain<6, 3>(g, eps);
+    const double tr_eps = (eps[0] + eps[1]) + eps[2];  // :75
+    const double tr_sig = (sig[0] + sig[1]) + sig[2];  // :81
+    const double te3 = tr_eps / 3;                     // tr_eps * I2 / 3   (:76)
+    const double ts3 = tr_sig / 3;                     // (:81)
+    double del_sigtr[6], sigtr[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double eps_dev = (k < 3) ? eps[k] - te3 : eps[k];       // :76
+        del_sigtr[k] = two_mu * eps_dev;                              // :79
+        const double stress_n_dev = (k < 3) ? sig[k] - ts3 : sig[k];  // :80-82
+        sigtr[k] = stress_n_dev + del_sigtr[k];                       // :83-85
+    }
+    double dot = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        dot += sigtr[k] * sigtr[k];
+    const double sigtrn = sqrt(dot);  // :88
+    const double exp0 = exp(-P.w * alpha_n);
+    const double phitr = sigtrn - c23 * (P.y0 + (P.y00 - P.y0) * (1 - exp0));  // :91-94
+
+    double gamma_1 = 0, xc1 = 0, xc2 = 0;
+    plastic = phitr > 0;  // :98
+    if (plastic) {
+        double xg;
+        mises_return_map(P, sigtrn, alpha_n, phitr, exp0, gamma_1, xg, failed);
+        const double inv_n = 1.0 / sigtrn;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            xn[k] = sigtr[k] * inv_n;  // flow direction (:108)
+        xc1 = -1 / xg;                 // :150
+        xc2 = gamma_1 * inv_n;         // :151
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            xn[k] = 0.0;  // :154-158
+    }
+    const double ktr = P.ka * tr_eps;
+    const double tmg = two_mu * gamma_1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        ep[k] += gamma_1 * xn[k];                                                       // :161
+        const double sh = ((k < 3) ? ktr + del_sigtr[k] : del_sigtr[k]) - tmg * xn[k];  // :165
+        sig[k] += sh;                                                                   // :167
+    }
+    alpha = alpha_n + c23 * gamma_1;  // :162
+
+    // ka*xioi + cpp*xpp takes four values per QP: coef[0] on the volumetric
+    // diagonal, coef[1] on its off-diagonal, cpp on the shear diagonal, 0
+    // elsewhere (xioi :33-42, xpp = I4 - (1/3) xioi :48).
+    const double cpp = two_mu * (1 - two_mu * xc2);  // :172
+    const double third = (1.0 / 3.0) * 1.0;
+    coef[0] = P.ka + cpp * (1.0 - third);
+    coef[1] = P.ka + cpp * (0.0 - third);
+    coef[2] = cpp;
+    coef[3] = 4 * P.mu * P.mu * (xc2 - xc1);  // :173
+}
+
 template <bool EPS_SOA>
 struct MisesModel {
     using Params = MisesParams;
@@ -380,6 +460,7 @@ struct MisesModel {
     static constexpr __host__ __device__ bool wr(int k) { return k >= 1; }
     static constexpr __host__ __device__ bool soa(int k) { return EPS_SOA && k == 2; }
     static constexpr __host__ __device__ int sdim() { return 6; }
+    static constexpr __host__ __device__ int const_tangent_qps() { return 0; }
     static constexpr __host__ __device__ int aux_doubles(int tile) { return REC * tile; }
     static constexpr __host__ __device__ int min_ctas(int tile) { return 512 / tile; }
     static constexpr __host__ __device__ bool has_flag() { return true; }
@@ -399,73 +480,19 @@ struct MisesModel {
             sig[i] = v.template ld<1>(i);
             ep[i] = v.template ld<2>(i);
         }
-        const double alpha_n = v.template ld<3>(0);
-
-        const double c23 = sqrt23();
-        const double two_mu = 2 * P.mu;
-        double eps[6];
-        mandel_strain<6, 3>(g, eps);
-        const double tr_eps = (eps[0] + eps[1]) + eps[2];  // :75
-        const double tr_sig = (sig[0] + sig[1]) + sig[2];  // :81
-        const double te3 = tr_eps / 3;                     // tr_eps * I2 / 3   (:76)
-        const double ts3 = tr_sig / 3;                     // (:81)
-        double del_sigtr[6], sigtr[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const double eps_dev = (k < 3) ? eps[k] - te3 : eps[k];       // :76
-            del_sigtr[k] = two_mu * eps_dev;                              // :79
-            const double stress_n_dev = (k < 3) ? sig[k] - ts3 : sig[k];  // :80-82
-            sigtr[k] = stress_n_dev + del_sigtr[k];                       // :83-85
-        }
-        double dot = 0.0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-            dot += sigtr[k] * sigtr[k];
-        const double sigtrn = sqrt(dot);  // :88
-        const double exp0 = exp(-P.w * alpha_n);
-        const double phitr = sigtrn - c23 * (P.y0 + (P.y00 - P.y0) * (1 - exp0));  // :91-94
-
-        double xn[6], gamma_1 = 0, xc1 = 0, xc2 = 0;
-        plastic = phitr > 0;  // :98
-        if (plastic) {
-            double xg;
-            mises_return_map(P, sigtrn, alpha_n, phitr, exp0, gamma_1, xg, failed);
-            const double inv_n = 1.0 / sigtrn;
-#pragma unroll
-            for (int k = 0; k < 6; ++k)
-                xn[k] = sigtr[k] * inv_n;  // flow direction (:108)
-            xc1 = -1 / xg;                 // :150
-            xc2 = gamma_1 * inv_n;         // :151
-        } else {
-#pragma unroll
-            for (int k = 0; k < 6; ++k)
-                xn[k] = 0.0;  // :154-158
-        }
-        const double ktr = P.ka * tr_eps;
-        const double tmg = two_mu * gamma_1;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            ep[k] += gamma_1 * xn[k];                                                     // :161
-            const double sh = ((k < 3) ? ktr + del_sigtr[k] : del_sigtr[k]) - tmg * xn[k];  // :165
-            sig[k] += sh;                                                                 // :167
-        }
+        double alpha = v.template ld<3>(0);
+        double coef[4], xn[6];
+        mises_point(P, g, sig, ep, alpha, coef, xn, plastic, failed);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             v.template st<1>(i, sig[i]);
             v.template st<2>(i, ep[i]);
         }
-        v.template st<3>(0, alpha_n + c23 * gamma_1);  // :162
-
-        // Tangent record (:170-175).  ka*xioi + cpp*xpp takes four values per QP:
-        // A on the volumetric diagonal, B on its off-diagonal, cpp on the shear
-        // diagonal, 0 elsewhere (xioi :33-42, xpp = I4 - (1/3) xioi :48).
+        v.template st<3>(0, alpha);
         double *rec = aux + t * REC;
-        const double cpp = two_mu * (1 - two_mu * xc2);  // :172
-        const double third = (1.0 / 3.0) * 1.0;
-        rec[0] = P.ka + cpp * (1.0 - third);
-        rec[1] = P.ka + cpp * (0.0 - third);
-        rec[2] = cpp;
-        rec[3] = 4 * P.mu * P.mu * (xc2 - xc1);  // :173
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            rec[k] = coef[k];
 #pragma unroll
         for (int k = 0; k < 6; ++k)
             rec[4 + k] = xn[k];

@@ -108,6 +108,13 @@ __device__ __forceinline__ void bulk_wait_read_all()
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// Same, but the most recently committed group may still be reading (used when
+// that group's source is a never-modified constant block).
+__device__ __forceinline__ void bulk_wait_read_1()
+{
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+
 // Order generic-proxy shared-memory writes before async-proxy reads of them.
 __device__ __forceinline__ void fence_proxy_async_smem()
 {

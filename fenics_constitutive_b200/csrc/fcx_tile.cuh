@@ -64,13 +64,19 @@ __global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
     fcx_tile_kernel(const __grid_constant__ typename M::Params prm,
                     const __grid_constant__ SegPtrs<M::nseg()> io, double *__restrict__ tangent,
                     const unsigned long long n, const int flags,
-                    unsigned char *__restrict__ flag, int *__restrict__ status)
+                    unsigned char *__restrict__ flag, int *__restrict__ status,
+                    const unsigned long long qbase)
 {
+    // qbase: index of this launch's first QP in the caller's arrays (only used
+    //        for the first-failing-point report in status[1])
     // flags: bit0 = bulk (TMA) path allowed (all pointers 16-byte aligned),
     //        bit1 = L2 evict_first hint on the bulk loads, bit2 = on the bulk stores
     const bool bulk_ok = (flags & 1) != 0;
     const bool hint_ld = (flags & 2) != 0;
     const bool hint_st = (flags & 4) != 0;
+    // bit3: constant-tangent models stream the tile's tangent block with bulk
+    //       stores from a constant shared-memory block instead of thread stores
+    const bool ct_bulk = (flags & 8) != 0 && M::const_tangent_qps() > 0;
     const uint64_t pol = policy_evict_first();
     constexpr int NSEG = M::nseg();
     constexpr int WSUM = M::wsum();
@@ -83,6 +89,8 @@ __global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
     const unsigned long long ntiles = (n + TILE - 1) / TILE;
 
     M::init_aux(prm, aux, tid, TILE);
+    if (M::const_tangent_qps() > 0)
+        fence_proxy_async_smem();  // aux is a bulk-store source (constant tangent block)
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
                 flag[q0 + tid] = plastic ? 1 : 0;
             if (M::has_flag() && failed && status != nullptr) {
                 atomicAdd(&status[0], 1);
-                const unsigned long long q = q0 + tid;
+                const unsigned long long q = qbase + q0 + tid;
                 atomicMin(&status[1], q > 0x7fffffffULL ? 0x7fffffff : (int)q);
             }
         }
@@ -214,12 +222,33 @@ __global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
         }
 
         // ---- tangent block of the tile: dense coalesced stream ----
-        M::store_tangent(prm, aux, tangent + q0 * SS, cnt, tid, TILE, bulk_ok);
+        if (bulk && ct_bulk) {
+            // every QP has the same s*s matrix: aux holds it repeated CQ times;
+            // TILE/CQ bulk stores from that never-modified block cover the tile
+            constexpr int CQ = M::const_tangent_qps() > 0 ? M::const_tangent_qps() : 1;
+            if (tid == 0) {
+#pragma unroll
+                for (int b = 0; b < TILE / CQ; ++b)
+                    bulk_s2g(tangent + (q0 + (unsigned long long)b * CQ) * SS, aux,
+                             CQ * SS * sizeof(double));
+                bulk_commit();
+            }
+        } else {
+            M::store_tangent(prm, aux, tangent + q0 * SS, cnt, tid, TILE, bulk_ok);
+        }
 
-        if (bulk && tid == 0)
-            bulk_wait_read_all();  // stage may be refilled after the barrier
+        if (bulk && tid == 0) {
+            // stage may be refilled after the barrier; the tangent group of a
+            // constant-tangent model reads only the constant block and may lag
+            if (ct_bulk)
+                bulk_wait_read_1();
+            else
+                bulk_wait_read_all();
+        }
         __syncthreads();
     }
+    if (tid == 0)
+        bulk_wait_read_all();  // shared memory must outlive every pending bulk store
 }
 
 // ---------------------------------------------------------------------------
