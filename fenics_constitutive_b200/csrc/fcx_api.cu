@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/fcx.h"
 #include "fcx_internal.h"
@@ -54,10 +55,46 @@ static int g_tile = 128;
 // store, fcx_mises_ostage.cuh), 0 = generic tile pipeline with the
 // warp-cooperative tangent store.
 static int g_mises_variant = 1;
-// Output-staged kernel: hand tiles out through an atomic ticket counter.
-static int g_dynamic_tiles = 0;
+static int g_mises_tile = 64;  // QPs per tile of the output-staged kernel (64 or 128)
+// Hand tiles out through an atomic ticket counter (all tile kernels).
+static int g_dynamic_tiles = 1;
 static int g_hints = 8;  // bit1: evict_first on bulk loads, bit2: on bulk stores,
                          // bit3: constant tangents written by bulk stores from shared memory
+
+// Atomic tile-ticket counters: one per (device, stream) so that launches that
+// may run concurrently (different streams) never share a counter; launches on
+// one stream serialise, and the counter is zeroed on that stream before each.
+static unsigned long long *ticket_for(cudaStream_t stream)
+{
+    struct Slot {
+        int dev;
+        cudaStream_t st;
+        unsigned long long *ptr;
+    };
+    static Slot slots[256];
+    static int nslots = 0;
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        return nullptr;
+    unsigned long long *ptr = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (int i = 0; i < nslots; ++i)
+            if (slots[i].dev == dev && slots[i].st == stream)
+                ptr = slots[i].ptr;
+        if (ptr == nullptr && nslots < 256) {
+            void *p = nullptr;
+            if (cudaMalloc(&p, 128) != cudaSuccess)
+                return nullptr;
+            ptr = static_cast<unsigned long long *>(p);
+            slots[nslots++] = Slot{dev, stream, ptr};
+        }
+    }
+    if (ptr != nullptr && cudaMemsetAsync(ptr, 0, sizeof(unsigned long long), stream) != cudaSuccess)
+        return nullptr;
+    return ptr;  // nullptr -> static tile stride
+}
 
 template <class M, int TILE>
 static int launch_tile_t(const typename M::Params &prm, const SegPtrs<M::nseg()> &io,
@@ -83,8 +120,9 @@ static int launch_tile_t(const typename M::Params &prm, const SegPtrs<M::nseg()>
     if (grid > ntiles)
         grid = ntiles;
     const int flags = (bulk_ok ? 1 : 0) | (g_hints & 14);
+    unsigned long long *ticket = (g_dynamic_tiles && ntiles > grid) ? ticket_for(stream) : nullptr;
     kern<<<(unsigned)grid, TILE, smem, stream>>>(prm, io, tangent, (unsigned long long)n, flags,
-                                                 flag, status, qbase);
+                                                 flag, status, qbase, ticket);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return note_cuda_error(cudaGetLastError(), "fcx_tile_kernel launch");
 }
@@ -127,24 +165,7 @@ static int launch_mises_ostage(const MisesParams &P, const double *grad, double 
     unsigned long long grid = (unsigned long long)sm_count() * per_sm;
     if (grid > ntiles)
         grid = ntiles;
-    unsigned long long *ticket = nullptr;
-    if (g_dynamic_tiles) {
-        // one counter per device, zeroed on the launch stream before every launch
-        int dev = 0;
-        cudaGetDevice(&dev);
-        static unsigned long long *counters[64] = {nullptr};
-        if (dev >= 0 && dev < 64) {
-            if (counters[dev] == nullptr &&
-                cudaMalloc(&counters[dev], sizeof(unsigned long long)) != cudaSuccess)
-                counters[dev] = nullptr;
-            ticket = counters[dev];
-        }
-        if (ticket != nullptr) {
-            cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream);
-            if (e != cudaSuccess)
-                return note_cuda_error(e, "cudaMemsetAsync(ticket)");
-        }
-    }
+    unsigned long long *ticket = (g_dynamic_tiles && ntiles > grid) ? ticket_for(stream) : nullptr;
     kern<<<(unsigned)grid, TILE, smem, stream>>>(P, grad, stress, tangent, eps_n, alpha, ntiles,
                                                  flag, status, ticket);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -354,6 +375,13 @@ int fcx_tune(const char *key, int value)
         g_hints = value;
         return old;
     }
+    if (key && strcmp(key, "mises_tile") == 0) {
+        if (value != 64 && value != 128)
+            return FCX_ERR_ARG;
+        const int old = g_mises_tile;
+        g_mises_tile = value;
+        return old;
+    }
     if (key && strcmp(key, "mises_variant") == 0) {
         if (value != 0 && value != 1)
             return FCX_ERR_ARG;
@@ -433,15 +461,15 @@ int fcx_mises_evaluate(const double *params, size_t n, const double *grad, doubl
     }
     if (eps_layout != FCX_LAYOUT_AOS)
         return FCX_ERR_ARG;
-    if (g_mises_variant == 1 && al && g_tile != 256) {
+    if (g_mises_variant == 1 && al) {
         // full tiles through the output-staged kernel, the tail (< one tile)
         // through the generic pipeline
-        const size_t T = (size_t)g_tile;
+        const size_t T = (size_t)g_mises_tile;
         const unsigned long long ntiles = n / T;
         const size_t nfull = (size_t)ntiles * T;
         int rc = FCX_OK;
         if (ntiles > 0)
-            rc = (g_tile == 64)
+            rc = (g_mises_tile == 64)
                      ? launch_mises_ostage<64, 8>(P, grad, stress, tangent, eps_n, alpha, ntiles,
                                                   plastic_flag, status, st)
                      : launch_mises_ostage<128, 4>(P, grad, stress, tangent, eps_n, alpha, ntiles,

