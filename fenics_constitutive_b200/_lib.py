@@ -31,6 +31,12 @@ SIGNATURES = {
     "fcx_maxwell_evaluate": (_ci, [_ci, _dp, _dp, _cd, _cd, _cd, _sz, _dp, _dp, _dp, _dp, _dp, _vp]),
     "fcx_strain_from_grad_u": (_ci, [_ci, _sz, _dp, _dp, _vp]),
     "fcx_gather_grad": (_ci, [_ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_mises_form": (_ci, [_dp, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
+                             _dp, _vp, _vp, _vp]),
+    "fcx_internal_force": (_ci, [_ci, _ci, _sz, _ci, _ci, _dp, _dp, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_tangent_apply": (_ci, [_ci, _ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_tangent_diag": (_ci, [_ci, _ci, _sz, _ci, _ci, _dp, _dp, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_gather_sum": (_ci, [_ci, _sz, _vp, _vp, _dp, _dp, _cd, _cd, _vp]),
     "fcx_elastic_evaluate_host": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp]),
     "fcx_mises_evaluate_host": (_ci, [_dp, _sz, _dp, _dp, _dp, _dp, _dp, _vp]),
     "fcx_kelvin_evaluate_host": (_ci, [_ci, _dp, _dp, _cd, _cd, _cd, _cd, _cd, _sz, _dp, _dp, _dp, _dp, _dp]),

@@ -10,6 +10,7 @@
 
 #include "../../include/fcx.h"
 #include "fcx_internal.h"
+#include "fcx_mises_form.cuh"
 #include "fcx_mises_ostage.cuh"
 #include "fcx_models.cuh"
 
@@ -170,6 +171,36 @@ static int launch_mises_ostage(const MisesParams &P, const double *grad, double 
                                                  flag, status, ticket);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return note_cuda_error(cudaGetLastError(), "fcx_mises_ostage_kernel launch");
+}
+
+// Fused form() pipeline for VonMises3D (fcx_mises_form.cuh).
+template <int ND, int NQ>
+static int launch_mises_form(const MisesParams &P, MisesFormArgs A, cudaStream_t stream)
+{
+    constexpr int TILE = 64;
+    auto kern = fcx_mises_form_kernel<ND, NQ, TILE, 8>;
+    constexpr size_t smem = mises_form_smem_bytes<ND, NQ, TILE>();
+    static int occ = -1;
+    if (occ < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaFuncSetAttribute(mises_form)");
+        int o = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, TILE, smem);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaOccupancy(mises_form)");
+        occ = o > 0 ? o : 1;
+    }
+    constexpr int CPT = TILE / NQ;
+    const unsigned long long ntiles = (A.ncells + CPT - 1) / CPT;
+    const int per_sm = g_ctas_per_sm > 0 ? g_ctas_per_sm : occ;
+    unsigned long long grid = (unsigned long long)sm_count() * per_sm;
+    if (grid > ntiles)
+        grid = ntiles;
+    A.ticket = (g_dynamic_tiles && ntiles > grid) ? ticket_for(stream) : nullptr;
+    kern<<<(unsigned)grid, TILE, smem, stream>>>(P, A);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "fcx_mises_form_kernel launch");
 }
 
 template <class M>
@@ -483,6 +514,49 @@ int fcx_mises_evaluate(const double *params, size_t n, const double *grad, doubl
                                               status, st, nfull);
     }
     return launch_tile<MisesModel<false>>(P, io, tangent, n, al, plastic_flag, status, st);
+}
+
+int fcx_mises_form(const double *params, size_t ncells, int nq, int nd, const int *dofmap,
+                   const double *u, const double *u_prev, const double *dphi_ref,
+                   const double *Jinv, const double *stress_prev, double *stress_cur,
+                   double *tangent, const double *eps_n0, double *eps_n1, const double *alpha0,
+                   double *alpha1, double *grad_out, unsigned char *plastic_flag, int *status,
+                   void *stream)
+{
+    if (ncells == 0)
+        return FCX_OK;
+    if (!params || !dofmap || !u || !dphi_ref || !Jinv || !stress_prev || !stress_cur || !tangent ||
+        !eps_n0 || !eps_n1 || !alpha0 || !alpha1)
+        return FCX_ERR_NULL;
+    MisesParams P{params[0], params[1], params[2], params[3], params[4], g_mises_nmax};
+    MisesFormArgs A;
+    A.dofmap = dofmap;
+    A.u = u;
+    A.u_prev = u_prev;
+    A.dphi_ref = dphi_ref;
+    A.Jinv = Jinv;
+    A.stress_prev = stress_prev;
+    A.eps0 = eps_n0;
+    A.alpha0 = alpha0;
+    A.stress_cur = stress_cur;
+    A.tangent = tangent;
+    A.eps1 = eps_n1;
+    A.alpha1 = alpha1;
+    A.grad_out = grad_out;
+    A.flag = plastic_flag;
+    A.status = status;
+    A.ticket = nullptr;
+    A.ncells = ncells;
+    A.bulk_ok = aligned16(stress_prev) && aligned16(stress_cur) && aligned16(tangent) &&
+                aligned16(eps_n0) && aligned16(eps_n1) && aligned16(alpha0) && aligned16(alpha1);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (nd == 10 && nq == 4)
+        return launch_mises_form<10, 4>(P, A, st);
+    if (nd == 4 && nq == 1)
+        return launch_mises_form<4, 1>(P, A, st);
+    if (nd == 4 && nq == 4)
+        return launch_mises_form<4, 4>(P, A, st);
+    return FCX_ERR_ARG;  // no fused specialisation: call fcx_gather_grad + fcx_mises_evaluate
 }
 
 int fcx_kelvin_evaluate(int constraint, const double *D0, const double *I2, double mu0,

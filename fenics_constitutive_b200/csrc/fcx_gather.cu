@@ -203,6 +203,9 @@ extern "C" int fcx_gather_grad(int gdim, size_t ncells, int nq, int nd, const in
     FCX_GATHER_CASE(3, 10, 4)  // P2 tetrahedron, q_degree 2 (BASELINE config 5)
     FCX_GATHER_CASE(3, 4, 1)   // P1 tetrahedron, q_degree 1 (reference tests/models/test_plasticity.py:16-17)
     FCX_GATHER_CASE(3, 10, 1)
+    FCX_GATHER_CASE(3, 4, 4)   // P1 tetrahedron, q_degree 2
+    FCX_GATHER_CASE(2, 3, 3)   // P1 triangle, q_degree 2
+    FCX_GATHER_CASE(1, 2, 2)   // P1 interval, q_degree 2
     FCX_GATHER_CASE(2, 6, 3)   // P2 triangle, q_degree 2
     FCX_GATHER_CASE(2, 3, 1)   // P1 triangle, q_degree 1
     FCX_GATHER_CASE(1, 3, 2)   // P2 interval, q_degree 2/3

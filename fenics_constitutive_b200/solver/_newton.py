@@ -1,0 +1,172 @@
+"""Newton solver for the device-resident ``IncrSmallStrainProblem`` -- stand-in
+for ``dolfinx.nls.petsc.NewtonSolver`` (third-party in the reference, used by
+every reference test, e.g. tests/models/test_plasticity.py:87-104).
+
+Same loop and defaults as dolfinx 0.9's NewtonSolver:
+    form(x); b = F(x)                      (with Dirichlet lifting, see below)
+    while not converged and it < max_it:
+        solve J dx = b;  x -= relaxation * dx;  form(x);  b = F(x);  it += 1
+    converged:  "residual":    |b| / |b_0| < rtol  or  |b| < atol
+                "incremental": |dx| / |dx_0| < rtol or |dx| < atol   (checked after the update)
+rtol = 1e-9, atol = 1e-10, max_it = 50, relaxation_parameter = 1.
+
+Dirichlet conditions follow dolfinx's NonlinearProblem.F/J: with z = g - x on
+the constrained dofs (0 elsewhere), b <- b + J z on the free dofs and b = x - g
+on the constrained ones; J gets identity rows/columns there.
+
+Linear solver: the Jacobian is applied matrix-free from the stored tangents
+(``problem.J_apply``).  "cg": Jacobi-preconditioned conjugate gradients on the
+free dofs (the consistent tangents of the built-in laws are symmetric);
+"dense": the operator is materialised column by column and solved with LU --
+the analogue of the reference tests' default PETSc LU -- for small problems;
+"auto" picks dense up to 3000 dofs.  With several ranks (torchrun), every dot
+product and norm is summed over ranks (NCCL all-reduce of one double).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ..partition import sum_over_ranks
+
+
+class NewtonSolver:
+    def __init__(self, comm_or_problem, problem=None):
+        # dolfinx signature NewtonSolver(comm, problem); the comm is ignored here
+        self.problem = problem if problem is not None else comm_or_problem
+        self.rtol = 1e-9
+        self.atol = 1e-10
+        self.max_it = 50
+        self.relaxation_parameter = 1.0
+        self.convergence_criterion = "residual"
+        self.error_on_nonconvergence = True
+        self.report = False
+        self.linear_solver = "auto"  # "cg" | "dense" | "auto"
+        self.cg_rtol = 1e-12
+        self.cg_max_it = 20000
+        self.reduce_over_ranks = False  # sum norms/dots over torch.distributed ranks
+        self.residual_history: list[float] = []
+        self.krylov_iterations: list[int] = []
+
+    # ------------------------------------------------------------ helpers
+    def _dot(self, a, b) -> float:
+        v = float((a * b).sum().item())
+        if self.reduce_over_ranks:
+            v = sum_over_ranks(v, a.device)
+        return v
+
+    def _norm(self, a) -> float:
+        return float(np.sqrt(self._dot(a, a)))
+
+    def _solve_dense(self, apply, rhs, free_mask):
+        import torch
+
+        n = rhs.numel()
+        idx = torch.nonzero(free_mask, as_tuple=False).ravel()
+        m = idx.numel()
+        A = torch.empty((m, m), dtype=torch.float64, device=rhs.device)
+        e = torch.zeros(n, dtype=torch.float64, device=rhs.device)
+        y = torch.empty_like(e)
+        for k in range(m):
+            e[idx[k]] = 1.0
+            apply(e, y)
+            A[:, k] = y[idx]
+            e[idx[k]] = 0.0
+        sol = torch.linalg.solve(A, rhs[idx])
+        dx = torch.zeros_like(rhs)
+        dx[idx] = sol
+        return dx, 0
+
+    def _solve_cg(self, apply, rhs, free_mask, diag):
+        """Jacobi-preconditioned CG on the free dofs (projected operator P J P)."""
+        import torch
+
+        fm = free_mask.to(torch.float64)
+        minv = fm / torch.where(diag.abs() > 0, diag, torch.ones_like(diag))
+        x = torch.zeros_like(rhs)
+        r = rhs * fm
+        z = minv * r
+        p = z.clone()
+        Ap = torch.empty_like(rhs)
+        rz = self._dot(r, z)
+        r0 = self._norm(r)
+        if r0 == 0.0:
+            return x, 0
+        it = 0
+        for it in range(1, self.cg_max_it + 1):
+            apply(p, Ap)
+            Ap.mul_(fm)
+            alpha = rz / self._dot(p, Ap)
+            x.add_(p, alpha=alpha)
+            r.add_(Ap, alpha=-alpha)
+            if self._norm(r) <= self.cg_rtol * r0:
+                break
+            z = minv * r
+            rz_new = self._dot(r, z)
+            p.mul_(rz_new / rz).add_(z)
+            rz = rz_new
+        return x, it
+
+    # -------------------------------------------------------------- solve
+    def solve(self, u):
+        """Returns (number of Newton iterations, converged) like dolfinx."""
+        import torch
+
+        pb = self.problem
+        x = u.x.array
+        dev = x.device
+        n = x.numel()
+        dofs_np, vals_np = pb.bc_dofs_values()
+        bc_dofs = torch.as_tensor(dofs_np, dtype=torch.int64, device=dev)
+        bc_vals = torch.as_tensor(vals_np, dtype=torch.float64, device=dev)
+        free = torch.ones(n, dtype=torch.bool, device=dev)
+        free[bc_dofs] = False
+        b = torch.empty(n, dtype=torch.float64, device=dev)
+        z = torch.zeros(n, dtype=torch.float64, device=dev)
+        Jz = torch.empty(n, dtype=torch.float64, device=dev)
+
+        def residual():
+            pb.form(x)
+            pb.F(x, b)
+            # lifting: b_free += (J z)_free with z = g - x on the constrained dofs; b_bc = x - g
+            z.zero_()
+            z[bc_dofs] = bc_vals - x[bc_dofs]
+            if bc_dofs.numel() > 0 and float(z.abs().max().item()) > 0.0:
+                pb.J_apply(z, Jz)
+                b.add_(Jz)
+            b[bc_dofs] = x[bc_dofs] - bc_vals
+            return self._norm(b)
+
+        self.residual_history, self.krylov_iterations = [], []
+        r = residual()
+        r0 = r
+        self.residual_history.append(r)
+        dx0 = None
+        it = 0
+        converged = (r < self.atol) if self.convergence_criterion == "residual" else False
+        if self.convergence_criterion == "residual" and r0 > 0 and r / r0 < self.rtol:
+            converged = True
+        while not converged and it < self.max_it:
+            use_dense = self.linear_solver == "dense" or (self.linear_solver == "auto" and n <= 3000)
+            rhs = b.clone()
+            if use_dense:
+                dx, kit = self._solve_dense(pb.J_apply, rhs, free)
+            else:
+                dx, kit = self._solve_cg(pb.J_apply, rhs, free, pb.J_diag())
+            dx[bc_dofs] = b[bc_dofs]  # identity rows: dx_bc = x_bc - g
+            self.krylov_iterations.append(kit)
+            x.add_(dx, alpha=-self.relaxation_parameter)
+            it += 1
+            r = residual()
+            self.residual_history.append(r)
+            if self.convergence_criterion == "incremental":
+                dxn = self._norm(dx)
+                dx0 = dxn if dx0 is None else dx0
+                converged = dxn < self.atol or (dx0 > 0 and dxn / dx0 < self.rtol)
+            else:
+                converged = r < self.atol or (r0 > 0 and r / r0 < self.rtol)
+            if self.report:
+                print(f"Newton iteration {it}: r (abs) = {r:.6e} (tol = {self.atol:.1e}) "
+                      f"r (rel) = {r / r0 if r0 > 0 else 0.0:.6e} (tol = {self.rtol:.1e}) krylov its = {kit}")
+        if not converged and self.error_on_nonconvergence:
+            raise RuntimeError(f"Newton solver did not converge in {it} iterations (|r| = {r:.3e}).")
+        return it, converged

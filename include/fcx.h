@@ -135,6 +135,49 @@ int fcx_gather_grad(int gdim, size_t ncells, int nq, int nd, const int *dofmap,
                     const double *u, const double *u_prev, const double *dphi_ref,
                     const double *Jinv, double *grad_del_u, void *stream);
 
+/* Fused form() pipeline for VonMises3D on affine P1/P2 tetrahedra -- one launch
+ * for what LawOnSubMesh.evaluate does per Newton iteration (reference
+ * solver/_lawonsubmesh.py:72-95 with an IdentityMap): gather grad_del_u
+ * (_incrementalunknowns.py:40-49), history trial reset history_1 <- history_0
+ * (_history.py:64-79), sigma_local <- stress.previous (_lawonsubmesh.py:58-61),
+ * law.evaluate (:86-94), results -> stress.current / tangent (:63-70).
+ * The committed arrays (stress_prev, eps_n0, alpha0) are only read, the trial
+ * arrays (stress_cur, eps_n1, alpha1, tangent) only written; a pair may alias
+ * (in-place).  grad_out: optional [ncells*nq][3][3] copy of grad_del_u.
+ * (nd, nq) in {(10,4), (4,1), (4,4)}; FCX_ERR_ARG otherwise (use
+ * fcx_gather_grad + fcx_mises_evaluate). */
+int fcx_mises_form(const double *params_host, size_t ncells, int nq, int nd, const int *dofmap,
+                   const double *u, const double *u_prev, const double *dphi_ref,
+                   const double *Jinv, const double *stress_prev, double *stress_cur,
+                   double *tangent, const double *eps_n0, double *eps_n1, const double *alpha0,
+                   double *alpha1, double *grad_out, unsigned char *plastic_flag, int *status,
+                   void *stream);
+
+/* Residual and Jacobian action of IncrSmallStrainProblem on the device
+ * (reference solver/_solver.py:87-101: R_form = inner(eps(v), sigma) dx,
+ * dR_form = inner(eps(du), C eps(v)) dx, eps = ufl_mandel_strain,
+ * solver/utils.py:10-62).  Affine simplex cells; tables as for fcx_gather_grad
+ * plus weights [nq] (reference-cell quadrature weights) and detJ [ncells]
+ * (|det dx/dX|).  Each call writes ELEMENT vectors fe [ncells][nd][gdim]:
+ *   fcx_internal_force   fe = sum_q w|J| B_q^T stress_q          (stress [ncells*nq][sdim])
+ *   fcx_tangent_apply    fe = sum_q w|J| B_q^T C_q^T B_q p_e     (p [nnodes][gdim], tangent [ncells*nq][sdim][sdim])
+ *   fcx_tangent_diag     fe = diagonal of the element matrix
+ * fcx_gather_sum then forms out[node][j] = beta*out + alpha * sum over the
+ * node's (cell, local index) adjacency (adj_ptr [nnodes+1] int64, adj_idx
+ * int32 = cell*nd + a) in a fixed order -- deterministic, no atomics. */
+int fcx_internal_force(int gdim, int sdim, size_t ncells, int nq, int nd, const double *dphi_ref,
+                       const double *weights, const double *Jinv, const double *detJ,
+                       const double *stress, double *fe, void *stream);
+int fcx_tangent_apply(int gdim, int sdim, size_t ncells, int nq, int nd, const int *dofmap,
+                      const double *p, const double *dphi_ref, const double *weights,
+                      const double *Jinv, const double *detJ, const double *tangent, double *fe,
+                      void *stream);
+int fcx_tangent_diag(int gdim, int sdim, size_t ncells, int nq, int nd, const double *dphi_ref,
+                     const double *weights, const double *Jinv, const double *detJ,
+                     const double *tangent, double *fe, void *stream);
+int fcx_gather_sum(int gdim, size_t nnodes, const long long *adj_ptr, const int *adj_idx,
+                   const double *fe, double *out, double alpha, double beta, void *stream);
+
 /* -------------------------------------------------------------------- host */
 
 int fcx_elastic_evaluate_host(int constraint, const double *D, size_t n,

@@ -1,0 +1,288 @@
+"""GPU tests of the device-resident solver stand-in:
+fused form() kernel, residual / Jacobian-action kernels, sub-mesh maps and the
+Newton driver, against the CPU oracle (oracle/fem.py + oracle/models.py) and the
+closed-form answers of the reference's solver tests."""
+import numpy as np
+import pytest
+
+from fenics_constitutive_b200.models import (
+    LinearElasticityModel, SpringKelvinModel, SpringMaxwellModel, VonMises3D)
+from fenics_constitutive_b200.models import StressStrainConstraint as C
+from fenics_constitutive_b200 import solver as S
+from oracle import fem as F
+from oracle import models as om
+from _util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+E, NU = 42.0, 0.3
+MISES = {"p_ka": 175000.0, "p_mu": 80769.0, "p_y0": 1200.0, "p_y00": 2500.0, "p_w": 200.0}
+VISCO = {"E0": 42.0, "E1": 10.0, "tau": 10.0, "nu": 0.2}
+
+left = lambda x: np.isclose(x[0], 0.0)    # noqa: E731
+right = lambda x: np.isclose(x[0], 1.0)   # noqa: E731
+y0b = lambda x: np.isclose(x[1], 0.0)     # noqa: E731
+z0b = lambda x: np.isclose(x[2], 0.0)     # noqa: E731
+
+
+def oracle_for(problem):
+    V, T = problem.V, problem.tables
+    return F.FemOracle(V.mesh.gdim, V.dofmap, T.dphi_ref, T.weights, T.Jinv, T.detJ, V.num_nodes)
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+MESHES = [
+    ("tet_p2_q2", lambda: S.create_box((0, 0, 0), (1.0, 0.7, 1.3), 3, 2, 2), 2, 2, C.FULL),
+    ("tet_p1_q1", lambda: S.create_unit_cube(3, 3, 2), 1, 1, C.FULL),
+    ("tet_p1_q2", lambda: S.create_unit_cube(2, 2, 2), 1, 2, C.FULL),
+    ("tri_p2_q2", lambda: S.create_rectangle((0, 0), (2.0, 1.0), 5, 3), 2, 2, C.PLANE_STRAIN),
+    ("tri_p1_q1", lambda: S.create_unit_square(4, 3), 1, 1, C.PLANE_STRESS),
+    ("int_p2_q2", lambda: S.create_unit_interval(9), 2, 2, C.UNIAXIAL_STRAIN),
+    ("int_p1_q1", lambda: S.create_unit_interval(5), 1, 1, C.UNIAXIAL_STRESS),
+]
+
+
+@pytest.mark.parametrize("name,mk,degree,qd,cons", MESHES, ids=[m[0] for m in MESHES])
+def test_residual_and_jacobian_kernels_vs_oracle(name, mk, degree, qd, cons):
+    import torch
+
+    mesh = mk()
+    V = S.FunctionSpace(mesh, degree)
+    u = S.Function(V)
+    pb = S.IncrSmallStrainProblem(LinearElasticityModel({"E": E, "nu": NU}, cons), u, [], qd)
+    fem = oracle_for(pb)
+    rng = np.random.default_rng(5)
+    s = cons.stress_strain_dim
+    stress = rng.standard_normal(pb.nqp * s)
+    tangent = rng.standard_normal(pb.nqp * s * s)  # deliberately non-symmetric: checks the C^T convention
+    p = rng.standard_normal(V.num_dofs)
+    pb.stress.current.x.array.copy_(torch.from_numpy(stress))
+    pb.tangent.x.array.copy_(torch.from_numpy(tangent))
+    b = np_(pb.F())
+    ref = fem.internal_force(stress)
+    assert np.abs(b - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+    K = fem.tangent_matrix(tangent)
+    y = np_(pb.J_apply(torch.from_numpy(p).to(pb.device)))
+    assert np.abs(y - K @ p).max() <= 1e-12 * np.abs(K @ p).max()
+    d = np_(pb.J_diag())
+    assert np.abs(d - K.diagonal()).max() <= 1e-12 * np.abs(K.diagonal()).max()
+    # gather against the oracle as well
+    uu = rng.standard_normal(V.num_dofs) * 1e-3
+    up = rng.standard_normal(V.num_dofs) * 1e-3
+    u.x.array.copy_(torch.from_numpy(uu))
+    pb.incr_disp.previous.x.array.copy_(torch.from_numpy(up))
+    ctx = pb._law_on_submeshs[0]
+    pb.incr_disp.evaluate_local_incremental_gradient(ctx.gather_op, ctx.displacement_gradient_fn)
+    g = np_(ctx.displacement_gradient_fn.x.array)
+    gref = fem.grad(uu, up)
+    assert np.abs(g - gref).max() <= 1e-13 * np.abs(gref).max()
+
+
+@pytest.mark.parametrize("degree,qd,n,scale", [(2, 2, (5, 4, 3), 2e-4), (1, 1, (6, 5, 5), 4e-4), (1, 2, (3, 3, 3), 7e-4)])
+def test_fused_form_equals_unfused_and_oracle(degree, qd, n, scale):
+    """fcx_mises_form == gather + trial reset + evaluate, bit for bit, and both match the oracle.
+    Two consecutive increments so that the second starts from non-zero sigma/eps_n/alpha."""
+    import torch
+
+    mesh = S.create_unit_cube(*n)
+    V = S.FunctionSpace(mesh, degree)
+    rng = np.random.default_rng(11)
+    incs = [rng.standard_normal(V.num_dofs) * scale for _ in range(2)]  # mixed elastic/plastic
+    results = []
+    for fused in (True, False):
+        u = S.Function(V)
+        law = VonMises3D(MISES)
+        law.record_plastic_flag = True
+        pb = S.IncrSmallStrainProblem(law, u, [], qd)
+        assert pb.fused
+        pb.fused = fused
+        out = []
+        for inc in incs:
+            u.x.array.add_(torch.from_numpy(inc).to(pb.device))
+            pb.form(u.x.array)
+            out.append([np_(pb.stress_1.x.array).copy(), np_(pb.tangent.x.array).copy(),
+                        np_(pb._history_1[0]["eps_n"].x.array).copy(), np_(pb._history_1[0]["alpha"].x.array).copy(),
+                        np_(law.plastic_flag).copy(), np_(pb._del_grad_u[0].x.array).copy()])
+            pb.update()
+        results.append(out)
+    for a, b in zip(results[0], results[1]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    # oracle
+    pbf = S.IncrSmallStrainProblem(VonMises3D(MISES), S.Function(V), [], qd)
+    fem = oracle_for(pbf)
+    opb = F.OracleProblem(om.VonMises3D(MISES), fem, lambda: (np.zeros(0, dtype=int), np.zeros(0)))
+    for k, inc in enumerate(incs):
+        opb.u += inc
+        opb.form()
+        sg, tg, ep, al, fl, _ = results[0][k]
+        assert rel_err(sg, opb.stress_1, 6) <= 1e-10
+        assert rel_err(tg, opb.tangent, 36) <= 1e-10
+        assert rel_err(ep, opb.history_1[0]["eps_n"], 6) <= 1e-10
+        assert rel_err(al, opb.history_1[0]["alpha"], 1) <= 1e-10
+        assert 0.01 < fl.mean() < 0.99
+        opb.update()
+
+
+def gpu_bcs(V, specs):
+    return [S.dirichletbc(val, S.locate_dofs_geometrical(V, marker), V if comp is None else V.sub(comp))
+            for marker, comp, val in specs]
+
+
+def test_uniaxial_stress_1d_elastic():
+    """reference tests/models/test_elasticity.py:26-87"""
+    mesh = S.create_unit_interval(10)
+    V = S.functionspace(mesh, ("CG", 1))
+    u = S.Function(V)
+    law = LinearElasticityModel(parameters={"E": E, "nu": NU}, constraint=C.UNIAXIAL_STRESS)
+    displacement = S.Constant(mesh, 0.01)
+    bcs = gpu_bcs(V, [(left, None, S.Constant(mesh, 0.0)), (right, None, displacement)])
+    problem = S.IncrSmallStrainProblem(law, u, bcs, 1)
+    solver = S.NewtonSolver(None, problem)
+    n, converged = solver.solve(u)
+    assert converged
+    assert np.abs(problem.stress_1.numpy() - E * 0.01).max() < 1e-12
+    problem.update()
+    assert np.abs(problem.stress_0.numpy() - E * 0.01).max() < 1e-12
+    assert problem._u0.numpy().max() == pytest.approx(displacement.value, abs=1e-15)
+    displacement.value = 0.02
+    solver.solve(u)
+    assert np.abs(problem.stress_1.numpy() - E * 0.02).max() < 1e-12
+
+
+def test_two_law_bar():
+    """reference tests/models/test_elasticity.py:90-154: two materials on disjoint cell sets
+    (SubSpaceMap): homogeneous stress, strain ratio = inverse stiffness ratio."""
+    mesh = S.create_unit_interval(10)
+    V = S.functionspace(mesh, ("CG", 1))
+    u = S.Function(V)
+    laws = [
+        (LinearElasticityModel({"E": E, "nu": NU}, C.UNIAXIAL_STRESS), np.arange(0, 5, dtype=np.int32)),
+        (LinearElasticityModel({"E": 2 * E, "nu": NU}, C.UNIAXIAL_STRESS), np.arange(5, 10, dtype=np.int32)),
+    ]
+    bcs = gpu_bcs(V, [(left, None, S.Constant(mesh, 0.0)), (right, None, S.Constant(mesh, 0.01))])
+    problem = S.IncrSmallStrainProblem(laws, u, bcs, 1)
+    solver = S.NewtonSolver(None, problem)
+    n, converged = solver.solve(u)
+    problem.update()
+    sig = problem.stress_0.numpy()
+    assert np.abs(sig - sig[0]).max() < 1e-13
+    g = [f.numpy() for f in problem._del_grad_u]
+    assert np.allclose(g[0], g[0][0]) and np.allclose(g[1], g[1][0])
+    assert g[0][0] / g[1][0] == pytest.approx(2.0, rel=1e-12)
+    # series springs: sigma = eps_total / (0.5/E + 0.5/(2E))
+    assert sig[0] == pytest.approx(0.01 / (0.5 / E + 0.25 / E), rel=1e-12)
+
+
+def test_plane_stress_and_plane_strain_2d():
+    """reference tests/models/test_elasticity.py:239-333"""
+    mesh = S.create_unit_square(3, 2)
+    V = S.functionspace(mesh, ("CG", 2, (2,)))
+    for cons in (C.PLANE_STRESS, C.PLANE_STRAIN):
+        u = S.Function(V)
+        bcs = gpu_bcs(V, [(left, 0, S.Constant(mesh, 0.0)), (right, 0, S.Constant(mesh, 0.01)),
+                          (y0b, 1, S.Constant(mesh, 0.0))])
+        problem = S.IncrSmallStrainProblem(LinearElasticityModel({"E": E, "nu": NU}, cons), u, bcs, 2)
+        S.NewtonSolver(None, problem).solve(u)
+        s = problem.stress_1.numpy().reshape(-1, 4)
+        if cons == C.PLANE_STRESS:
+            assert np.abs(s[:, 0] - E * 0.01).max() < 1e-12 and np.abs(s[:, 1:]).max() < 1e-12
+        else:
+            assert np.abs(s[:, 0] - E / (1 - NU**2) * 0.01).max() < 1e-12   # free in y, eps_zz = 0
+            assert np.abs(s[:, 2] - NU * s[:, 0]).max() < 1e-12             # sigma_zz != 0
+            assert np.abs(s[:, 1]).max() < 1e-12
+
+
+def run_mises_uniaxial(n_steps, mesh_n, degree, qd, linear_solver="auto"):
+    mesh = S.create_unit_cube(*mesh_n)
+    V = S.functionspace(mesh, ("CG", degree, (3,)))
+    u = S.Function(V)
+    law = VonMises3D(MISES)
+    scalar_x = S.Constant(mesh, 0.0)
+    zero = S.Constant(mesh, 0.0)
+    bcs = gpu_bcs(V, [(left, 0, zero), (right, 0, scalar_x), (y0b, 1, zero), (z0b, 2, zero)])
+    problem = S.IncrSmallStrainProblem(law, u, bcs, q_degree=qd)
+    solver = S.NewtonSolver(None, problem)
+    solver.linear_solver = linear_solver
+    # oracle twin
+    fem = oracle_for(problem)
+    opb = F.OracleProblem(om.VonMises3D(MISES), fem, problem.bc_dofs_values)
+    displacement, load = [0.0], [0.0]
+    worst = 0.0
+    for t in np.linspace(0, 1, n_steps + 1)[1:]:
+        scalar_x.value = t * 0.05
+        niter, converged = solver.solve(u)
+        assert converged
+        problem.update()
+        on, ook = opb.solve()
+        opb.update()
+        assert ook
+        worst = max(worst, rel_err(problem.stress_0.numpy(), opb.stress_0, 6),
+                    np.abs(u.numpy() - opb.u).max() / np.abs(opb.u).max())
+        displacement.append(scalar_x.value)
+        load.append(problem.stress_0.numpy()[::6][0])
+    return np.array(displacement), np.array(load), worst, problem, opb
+
+
+def test_mises_uniaxial_stress_3d_100_steps():
+    """reference tests/models/test_plasticity.py:13-137 on the device stand-in (fused form kernel,
+    one cube = 6 P1 tets, q_degree 1), and step-by-step against the CPU oracle."""
+    displacement, load, worst, problem, opb = run_mises_uniaxial(100, (1, 1, 1), 1, 1)
+    assert problem.fused
+    tol = 1e-8
+    assert np.max(load) - MISES["p_y00"] <= tol
+    ind = load + tol < MISES["p_y0"]
+    ka, mu = MISES["p_ka"], MISES["p_mu"]
+    v = (3 * ka - 2 * mu) / (2 * (3 * ka + mu))
+    trace = displacement[ind][1] - 2 * v * displacement[ind][1]
+    dev = displacement[ind][1] - trace / 3
+    slope = (ka * trace + 2 * mu * dev) / displacement[ind][1]
+    assert np.all(np.abs(np.ediff1d(load[ind]) / np.ediff1d(displacement[ind]) - slope) < 1e-7)
+    assert worst < 1e-9
+    assert rel_err(problem._history_0[0]["alpha"].numpy(), opb.history_0[0]["alpha"], 1) < 1e-9
+
+
+def test_mises_p2_mesh_cg_vs_oracle():
+    """P2 tets, q_degree 2, matrix-free PCG linear solver vs the oracle's sparse LU."""
+    displacement, load, worst, problem, opb = run_mises_uniaxial(6, (2, 2, 2), 2, 2, linear_solver="cg")
+    assert problem.fused and load[-1] > 1500.0
+    # both Newton loops stop at rtol 1e-9 from different linear solvers: iterates agree to ~1e-8
+    assert worst < 1e-7
+
+
+@pytest.mark.parametrize("cls,ocls", [(SpringKelvinModel, om.SpringKelvinModel), (SpringMaxwellModel, om.SpringMaxwellModel)])
+def test_relaxation_3d_visco(cls, ocls):
+    """reference tests/models/test_viscoelasticity.py:128-288 (3D relaxation under a step strain with
+    free lateral faces): sigma_xx(0+) and sigma_xx(inf) closed forms, and oracle parity."""
+    mesh = S.create_unit_cube(1, 1, 1)
+    V = S.functionspace(mesh, ("CG", 1, (3,)))
+    u = S.Function(V)
+    zero = S.Constant(mesh, 0.0)
+    eps = 0.001
+    bcs = gpu_bcs(V, [(left, 0, zero), (right, 0, S.Constant(mesh, eps)), (y0b, 1, zero), (z0b, 2, zero)])
+    problem = S.IncrSmallStrainProblem(cls(VISCO, C.FULL), u, bcs, 1, del_t=1e-8)
+    solver = S.NewtonSolver(None, problem)
+    opb = F.OracleProblem(ocls(VISCO, C.FULL), oracle_for(problem), problem.bc_dofs_values, del_t=1e-8)
+    solver.solve(u)
+    problem.update()
+    opb.solve()
+    opb.update()
+    s0 = problem.stress_0.numpy()[0]
+    problem._del_t = 2.0
+    opb.dt = 2.0
+    for _ in range(100):
+        solver.solve(u)
+        problem.update()
+        opb.solve()
+        opb.update()
+    s_inf = problem.stress_0.numpy()[0]
+    E0, E1 = VISCO["E0"], VISCO["E1"]
+    if cls is SpringKelvinModel:
+        assert abs(s0 - E0 * eps) < 1e-8 and abs(s_inf - E0 * E1 / (E0 + E1) * eps) < 1e-8
+    else:
+        assert abs(s0 - (E0 + E1) * eps) < 1e-8 and abs(s_inf - E0 * eps) < 1e-8
+    assert rel_err(problem.stress_0.numpy(), opb.stress_0, 6) < 1e-9
+    assert problem._time == pytest.approx(1e-8 + 200.0)

@@ -1,0 +1,165 @@
+"""CPU tests (no GPU): the solver-side oracle (oracle/fem.py) against the closed-form
+answers of the reference's own solver tests, restated on the dolfinx-free mesh
+layer.  These pin the oracle that tests/test_solver_gpu.py compares the device
+stand-in against.
+
+Restated reference tests:
+  tests/models/test_elasticity.py:26-87     uniaxial stress, sigma = E eps, two load levels
+  tests/models/test_elasticity.py:157-199   uniaxial strain
+  tests/models/test_elasticity.py:300-333   plane stress: sigma_zz = 0, sigma_xx = E eps (free lateral)
+  tests/models/test_elasticity.py:335-402   3D vs the pure-dolfinx linear problem (here: patch test)
+  tests/models/test_plasticity.py:13-137    VonMises3D uniaxial stress, 100 steps
+  tests/models/test_viscoelasticity.py:26-125  1D relaxation, Kelvin and Maxwell
+"""
+import numpy as np
+import pytest
+
+from fenics_constitutive_b200.models import StressStrainConstraint as C
+from fenics_constitutive_b200.solver import mesh as M
+from oracle import fem as F
+from oracle import models as om
+
+E, NU = 42.0, 0.3  # reference tests/models/test_elasticity.py:22-23
+MISES = {"p_ka": 175000.0, "p_mu": 80769.0, "p_y0": 1200.0, "p_y00": 2500.0, "p_w": 200.0}
+VISCO = {"E0": 42.0, "E1": 10.0, "tau": 10.0, "nu": 0.2}
+
+
+def make(mesh, degree, q_degree):
+    V = M.FunctionSpace(mesh, degree)
+    T = M.ElementTables(V, q_degree)
+    fem = F.FemOracle(mesh.gdim, V.dofmap, T.dphi_ref, T.weights, T.Jinv, T.detJ, V.num_nodes)
+    return V, T, fem
+
+
+def bcs_of(V, specs):
+    """specs: list of (marker, component or None, value-holder list[float])."""
+    def get():
+        dofs, vals = [], []
+        for marker, comp, val in specs:
+            nodes = M.locate_dofs_geometrical(V, marker)
+            if comp is None:
+                d = (nodes[:, None] * V.block_size + np.arange(V.block_size)[None]).ravel()
+                v = np.tile(np.asarray(val[0], dtype=float).ravel(), nodes.size)
+            else:
+                d = nodes * V.block_size + comp
+                v = np.full(nodes.size, float(val[0]))
+            dofs.append(d)
+            vals.append(v)
+        return np.concatenate(dofs), np.concatenate(vals)
+    return get
+
+
+left = lambda x: np.isclose(x[0], 0.0)   # noqa: E731
+right = lambda x: np.isclose(x[0], 1.0)  # noqa: E731
+
+
+def test_uniaxial_stress_1d():
+    V, T, fem = make(M.create_unit_interval(10), 1, 1)
+    disp = [0.01]
+    pb = F.OracleProblem(om.LinearElasticityModel({"E": E, "nu": NU}, C.UNIAXIAL_STRESS), fem,
+                         bcs_of(V, [(left, 0, [0.0]), (right, 0, disp)]))
+    n, ok = pb.solve()
+    assert ok
+    assert np.abs(pb.stress_1 - E * 0.01).max() < 1e-12
+    pb.update()
+    assert np.abs(pb.stress_0 - E * 0.01).max() < 1e-12
+    assert pb.u_prev.max() == pytest.approx(0.01, abs=1e-15)
+    disp[0] = 0.02
+    pb.solve()
+    assert np.abs(pb.stress_1 - E * 0.02).max() < 1e-12
+
+
+def test_uniaxial_strain_1d():
+    V, T, fem = make(M.create_unit_interval(7), 2, 2)
+    pb = F.OracleProblem(om.LinearElasticityModel({"E": E, "nu": NU}, C.UNIAXIAL_STRAIN), fem,
+                         bcs_of(V, [(left, 0, [0.0]), (right, 0, [0.01])]))
+    pb.solve()
+    assert np.abs(pb.stress_1 - E * (1 - NU) / ((1 + NU) * (1 - 2 * NU)) * 0.01).max() < 1e-12
+
+
+def test_plane_stress_2d():
+    V, T, fem = make(M.create_unit_square(3, 2), 1, 1)
+    bottom = lambda x: np.isclose(x[1], 0.0)  # noqa: E731
+    pb = F.OracleProblem(om.LinearElasticityModel({"E": E, "nu": NU}, C.PLANE_STRESS), fem,
+                         bcs_of(V, [(left, 0, [0.0]), (right, 0, [0.01]), (bottom, 1, [0.0])]))
+    pb.solve()
+    s = pb.stress_1.reshape(-1, 4)
+    assert np.abs(s[:, 0] - E * 0.01).max() < 1e-12   # uniaxial stress state in the plane
+    assert np.abs(s[:, 1:]).max() < 1e-12             # sigma_yy = sigma_zz = sigma_xy = 0
+
+
+def test_3d_patch_test_affine_field():
+    """An affine displacement prescribed on the whole boundary is reproduced exactly in the
+    interior (P1 and P2), with the uniform stress D eps -- the content of the reference's
+    comparison with a pure-dolfinx LinearProblem."""
+    A = np.array([[0.01, 0.002, -0.003], [0.0, -0.004, 0.001], [0.005, 0.0, 0.002]])
+    for degree, qd in ((1, 1), (2, 2)):
+        V, T, fem = make(M.create_unit_cube(2, 2, 2), degree, qd)
+        boundary = lambda x: np.any(np.isclose(x, 0.0) | np.isclose(x, 1.0), axis=0)  # noqa: E731
+        nodes = M.locate_dofs_geometrical(V, boundary)
+        ub = V.node_coords[nodes] @ A.T
+
+        def get(nodes=nodes, ub=ub, V=V):
+            return (nodes[:, None] * 3 + np.arange(3)[None]).ravel(), ub.ravel()
+
+        pb = F.OracleProblem(om.LinearElasticityModel({"E": E, "nu": NU}, C.FULL), fem, get)
+        pb.solve()
+        assert np.abs(pb.u.reshape(-1, 3) - V.node_coords @ A.T).max() < 1e-13
+        grad = A.T  # nabla_grad: grad[i][j] = du_j/dx_i
+        eps = F.mandel_strain(grad[None], 3)[0]
+        D = om.get_elastic_tangent(E, NU, C.FULL)
+        assert np.abs(pb.stress_1.reshape(-1, 6) - eps @ D).max() < 1e-12
+
+
+def test_mises_uniaxial_stress_3d():
+    """reference tests/models/test_plasticity.py:13-137 (VonMises3D branch)."""
+    V, T, fem = make(M.create_unit_cube(1, 1, 1), 1, 1)
+    disp = [0.0]
+    y0b = lambda x: np.isclose(x[1], 0.0)  # noqa: E731
+    z0b = lambda x: np.isclose(x[2], 0.0)  # noqa: E731
+    pb = F.OracleProblem(om.VonMises3D(MISES), fem,
+                         bcs_of(V, [(left, 0, [0.0]), (right, 0, disp), (y0b, 1, [0.0]), (z0b, 2, [0.0])]))
+    nT, max_disp = 100, 0.05
+    displacement, load = [0.0], [0.0]
+    for t in np.linspace(0, 1, nT + 1)[1:]:
+        disp[0] = t * max_disp
+        n, ok = pb.solve()
+        assert ok
+        pb.update()
+        displacement.append(disp[0])
+        load.append(pb.stress_0[::6][0])
+    displacement, load = np.array(displacement), np.array(load)
+    tol = 1e-8
+    assert np.max(load) - MISES["p_y00"] <= tol
+    ind = load + tol < MISES["p_y0"]
+    ka, mu = MISES["p_ka"], MISES["p_mu"]
+    v = (3 * ka - 2 * mu) / (2 * (3 * ka + mu))
+    trace = displacement[ind][1] - 2 * v * displacement[ind][1]
+    dev = displacement[ind][1] - trace / 3
+    slope = (ka * trace + 2 * mu * dev) / displacement[ind][1]
+    assert np.all(np.abs(np.ediff1d(load[ind]) / np.ediff1d(displacement[ind]) - slope) < 1e-7)
+    assert load[-1] > 2400.0  # well into the saturated regime
+
+
+@pytest.mark.parametrize("name", ["kelvin", "maxwell"])
+def test_relaxation_1d(name):
+    """reference tests/models/test_viscoelasticity.py:26-125: step strain, first increment
+    dt = 1e-8, then dt = 2 up to t = 200."""
+    V, T, fem = make(M.create_unit_interval(2), 1, 1)
+    cls = om.SpringKelvinModel if name == "kelvin" else om.SpringMaxwellModel
+    eps = 0.001
+    pb = F.OracleProblem(cls(VISCO, C.UNIAXIAL_STRESS), fem,
+                         bcs_of(V, [(left, 0, [0.0]), (right, 0, [eps])]), del_t=1e-8)
+    pb.solve()
+    pb.update()
+    E0, E1 = VISCO["E0"], VISCO["E1"]
+    s0 = pb.stress_0[0]
+    pb.dt = 2.0
+    for _ in range(100):
+        pb.solve()
+        pb.update()
+    s_inf = pb.stress_0[0]
+    if name == "kelvin":
+        assert abs(s0 - E0 * eps) < 1e-8 and abs(s_inf - E0 * E1 / (E0 + E1) * eps) < 1e-8
+    else:
+        assert abs(s0 - (E0 + E1) * eps) < 1e-8 and abs(s_inf - E0 * eps) < 1e-8
