@@ -331,6 +331,52 @@ __global__ void strain_kernel(const double *__restrict__ grad, double *__restric
     }
 }
 
+
+// 3D -> 1D/2D adapters (fc/models/utils.py:211-412: UniaxialStrainFrom3D, PlaneStrainFrom3D):
+// embed the low-dimensional grad_del_u / stress into persistent 3D scratch arrays (only the
+// mapped components are overwritten, :285-292 / :365-386), and extract the mapped components
+// of the 3D stress / tangent afterwards (:293-297 / :388-412).
+template <int G, int S>
+__global__ void embed3d_kernel(const double *__restrict__ grad, const double *__restrict__ stress,
+                               double *__restrict__ grad3, double *__restrict__ stress3,
+                               unsigned long long n)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+         q += stride) {
+        if (G == 1) {
+            grad3[q * 9] = grad[q];      // :285-287
+            stress3[q * 6] = stress[q];  // :289-292
+        } else {
+            grad3[q * 9 + 0] = grad[q * 4 + 0];  // :375-376
+            grad3[q * 9 + 1] = grad[q * 4 + 1];
+            grad3[q * 9 + 3] = grad[q * 4 + 2];
+            grad3[q * 9 + 4] = grad[q * 4 + 3];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                stress3[q * 6 + k] = stress[q * 4 + k];  // :384-386
+        }
+    }
+}
+
+template <int G, int S>
+__global__ void extract3d_kernel(const double *__restrict__ stress3,
+                                 const double *__restrict__ tangent3, double *__restrict__ stress,
+                                 double *__restrict__ tangent, unsigned long long n)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+         q += stride) {
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            stress[q * S + i] = stress3[q * 6 + i];  // :293-297 / :388-391
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                tangent[q * S * S + i * S + j] = tangent3[q * 36 + i * 6 + j];  // :299-302 / :393-412
+        }
+    }
+}
+
 // Diagnostic: the simplest possible streaming kernel with the Mises kernel's
 // read:write byte mix (per pair of QPs: 22 double2 read, 49 double2 written),
 // perfectly coalesced, no shared memory, no arithmetic to speak of.  Its
@@ -516,6 +562,21 @@ int fcx_mises_evaluate(const double *params, size_t n, const double *grad, doubl
     return launch_tile<MisesModel<false>>(P, io, tangent, n, al, plastic_flag, status, st);
 }
 
+int fcx_mises_linear_hardening_evaluate(const double *params, size_t n, const double *grad,
+                                        double *stress, double *tangent, double *history,
+                                        unsigned char *plastic_flag, void *stream)
+{
+    if (n == 0)
+        return FCX_OK;
+    if (!params || !grad || !stress || !tangent || !history)
+        return FCX_ERR_NULL;
+    MisesLinParams P{params[0], params[1], params[2], params[3]};
+    SegPtrs<3> io{{const_cast<double *>(grad), stress, history}};
+    const bool al = aligned16(grad) && aligned16(stress) && aligned16(tangent) && aligned16(history);
+    return launch_tile<MisesLinModel>(P, io, tangent, n, al, plastic_flag, nullptr,
+                                      static_cast<cudaStream_t>(stream));
+}
+
 int fcx_mises_form(const double *params, size_t ncells, int nq, int nd, const int *dofmap,
                    const double *u, const double *u_prev, const double *dphi_ref,
                    const double *Jinv, const double *stress_prev, double *stress_cur,
@@ -606,6 +667,50 @@ int fcx_maxwell_evaluate(int constraint, const double *D0, const double *D1, dou
         return maxwell_dispatch<6, 3>(D0, D1, mu1, tau, del_t, n, grad, stress, tangent, ev, et, st);
     default: return FCX_ERR_CONSTRAINT;
     }
+}
+
+int fcx_embed_3d(int constraint, size_t n, const double *grad, const double *stress, double *grad3d,
+                 double *stress3d, void *stream)
+{
+    if (constraint != FCX_UNIAXIAL_STRAIN && constraint != FCX_PLANE_STRAIN)
+        return FCX_ERR_CONSTRAINT;
+    if (n == 0)
+        return FCX_OK;
+    if (!grad || !stress || !grad3d || !stress3d)
+        return FCX_ERR_NULL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long grid = (n + 255) / 256;
+    const unsigned long long cap = (unsigned long long)sm_count() * 8;
+    if (grid > cap)
+        grid = cap;
+    if (constraint == FCX_UNIAXIAL_STRAIN)
+        embed3d_kernel<1, 1><<<(unsigned)grid, 256, 0, st>>>(grad, stress, grad3d, stress3d, n);
+    else
+        embed3d_kernel<2, 4><<<(unsigned)grid, 256, 0, st>>>(grad, stress, grad3d, stress3d, n);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "embed3d_kernel launch");
+}
+
+int fcx_extract_from_3d(int constraint, size_t n, const double *stress3d, const double *tangent3d,
+                        double *stress, double *tangent, void *stream)
+{
+    if (constraint != FCX_UNIAXIAL_STRAIN && constraint != FCX_PLANE_STRAIN)
+        return FCX_ERR_CONSTRAINT;
+    if (n == 0)
+        return FCX_OK;
+    if (!stress3d || !tangent3d || !stress || !tangent)
+        return FCX_ERR_NULL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long grid = (n + 255) / 256;
+    const unsigned long long cap = (unsigned long long)sm_count() * 8;
+    if (grid > cap)
+        grid = cap;
+    if (constraint == FCX_UNIAXIAL_STRAIN)
+        extract3d_kernel<1, 1><<<(unsigned)grid, 256, 0, st>>>(stress3d, tangent3d, stress, tangent, n);
+    else
+        extract3d_kernel<2, 4><<<(unsigned)grid, 256, 0, st>>>(stress3d, tangent3d, stress, tangent, n);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "extract3d_kernel launch");
 }
 
 int fcx_strain_from_grad_u(int constraint, size_t n, const double *grad, double *strain,

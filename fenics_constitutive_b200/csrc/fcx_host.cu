@@ -217,6 +217,25 @@ int fcx_mises_evaluate_host(const double *params, size_t n, const double *grad, 
     });
 }
 
+int fcx_mises_linear_hardening_evaluate_host(const double *params, size_t n, const double *grad,
+                                             double *stress, double *tangent, double *history,
+                                             unsigned char *plastic_flag)
+{
+    if (n == 0)
+        return FCX_OK;
+    if (!params || !grad || !stress || !tangent || !history)
+        return FCX_ERR_NULL;
+    const size_t d = sizeof(double);
+    const HostArr arr[5] = {{grad, nullptr, d * 9}, {stress, stress, d * 6},
+                            {nullptr, tangent, d * 36}, {history, history, d * 7},
+                            {nullptr, plastic_flag, 1}};
+    return run_pipeline(arr, 5, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
+        return fcx_mises_linear_hardening_evaluate(
+            params, cnt, (const double *)dev[0], (double *)dev[1], (double *)dev[2],
+            (double *)dev[3], plastic_flag ? (unsigned char *)dev[4] : nullptr, st);
+    });
+}
+
 int fcx_kelvin_evaluate_host(int constraint, const double *D0, const double *I2, double mu0,
                              double lam0, double mu1, double tau, double del_t, size_t n,
                              const double *grad, double *stress, double *tangent, double *ev,

@@ -534,4 +534,122 @@ struct MisesModel {
     }
 };
 
+// ===========================================================================
+// comfe-rs MisesPlasticity3D (linear isotropic hardening, closed-form radial
+// return) -- comfe-rs/src/mises_plasticity.rs:58-126, exported by the reference
+// as MisesPlasticityLinearHardening3D (fc/models/rust_models.py:144-161).
+//   segments: 0 grad [9] (read)  1 stress [6]  2 history [7] = [alpha, plastic_strain[6]]
+//   (ONE history array per QP, comfe-rs/src/mises_plasticity.rs:43-51)
+// Mandel strain uses Rust's correctly rounded FRAC_1_SQRT_2 (mandel.rs:147).
+// The tangent kappa*1(x)1 + 2mu*theta*P_dev + 2mu*theta_bar*n n^T has the same
+// four-coefficient + direction structure as VonMises3D's, so the tangent
+// record / cooperative store of MisesModel is reused.
+// ===========================================================================
+struct MisesLinParams {
+    double mu, kappa, y_0, h;
+};
+
+struct MisesLinModel {
+    using Params = MisesLinParams;
+    static constexpr int REC = MisesModel<false>::REC;
+    static constexpr __host__ __device__ int nseg() { return 3; }
+    static constexpr __host__ __device__ int w(int k) { return k == 0 ? 9 : (k == 1 ? 6 : 7); }
+    static constexpr __host__ __device__ int off(int k) { return k == 0 ? 0 : (k == 1 ? 9 : 15); }
+    static constexpr __host__ __device__ int wsum() { return 22; }
+    static constexpr __host__ __device__ bool wr(int k) { return k >= 1; }
+    static constexpr __host__ __device__ bool soa(int) { return false; }
+    static constexpr __host__ __device__ int sdim() { return 6; }
+    static constexpr __host__ __device__ int const_tangent_qps() { return 0; }
+    static constexpr __host__ __device__ int aux_doubles(int tile) { return REC * tile; }
+    static constexpr __host__ __device__ int min_ctas(int tile) { return 512 / tile; }
+    static constexpr __host__ __device__ bool has_flag() { return true; }
+
+    __device__ static void init_aux(const Params &, double *, int, int) {}
+
+    template <class V>
+    __device__ static __forceinline__ void qp(const Params &P, const V &v, double *aux, int t,
+                                              bool &plastic, bool &)
+    {
+        double g[9], sig[6], hist[7];
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            g[i] = v.template ld<0>(i);
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            sig[i] = v.template ld<1>(i);
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            hist[i] = v.template ld<2>(i);
+        const double f = 0.70710678118654752440;  // f64::consts::FRAC_1_SQRT_2
+        const double e[6] = {g[0], g[4], g[8], f * (g[1] + g[3]), f * (g[2] + g[6]), f * (g[5] + g[7])};
+        const double alpha = hist[0];
+        const double p_0 = ((sig[0] + sig[1]) + sig[2]) / 3.0;   // vol_dev (mandel.rs:53-60)
+        const double eps_trace = (e[0] + e[1]) + e[2];           // trace_dev (mandel.rs:62-68)
+        const double ev = eps_trace / 3.0;
+        const double p_1 = p_0 + P.kappa * eps_trace;            // :86
+        const double two_mu = 2. * P.mu;
+        double s_tr[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double s0 = (k < 3) ? sig[k] + (-p_0) : sig[k];
+            const double ed = (k < 3) ? e[k] + (-ev) : e[k];
+            s_tr[k] = s0 + two_mu * ed;  // :88
+        }
+        const double tv = ((s_tr[0] + s_tr[1]) + s_tr[2]) / 3.0;  // mises_norm (mandel.rs:19-34)
+        double nsq = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double d = (k < 3) ? s_tr[k] + (-tv) : s_tr[k];
+            nsq += d * d;
+        }
+        const double s_tr_eq = sqrt(3.0 * (0.5 * nsq));  // :89
+        const double sigma_y = P.y_0 + P.h * alpha;      // :91
+        double theta = 1.0, theta_bar = 0.0, nn[6];
+        plastic = !(s_tr_eq < sigma_y);  // :94
+        if (plastic) {
+            const double del_alpha = (s_tr_eq - sigma_y) / (3. * P.mu + P.h);  // :104
+            const double del_gamma = sqrt(3. / 2.) * del_alpha;                // :105
+            theta = 1. - (3. * P.mu * del_alpha) / s_tr_eq;                    // :106
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                nn[k] = s_tr[k] / s_tr_eq;       // :110
+                hist[1 + k] += del_gamma * nn[k];  // :111
+            }
+            hist[0] += del_alpha;                                                // :112
+            theta_bar = 1.0 / (1.0 + (P.h / (3.0 * P.mu))) - (1.0 - theta);      // :117
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                nn[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            sig[k] = ((k < 3) ? p_1 : 0.0) + (plastic ? theta * s_tr[k] : s_tr[k]);  // :96 / :114
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            v.template st<1>(i, sig[i]);
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            v.template st<2>(i, hist[i]);
+        // kappa*1(x)1 + (2mu theta)*P_dev + (2mu theta_bar)*n n^T   (:98-100, :118-120)
+        const double c = two_mu * theta;
+        const double third = (1.0 * (1.0 / 3.0)) * -1.0;  // consts.rs:106-115
+        double *rec = aux + t * REC;
+        rec[0] = P.kappa + c * (1.0 + third);
+        rec[1] = P.kappa + c * (0.0 + third);
+        rec[2] = c;
+        rec[3] = two_mu * theta_bar;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            rec[4 + k] = nn[k];
+    }
+
+    __device__ static __forceinline__ void store_tangent(const Params &, const double *aux,
+                                                         double *tang, int cnt, int tid,
+                                                         int nthreads, bool vec_ok)
+    {
+        MisesModel<false>::store_tangent(MisesParams{}, aux, tang, cnt, tid, nthreads, vec_ok);
+    }
+};
+
 }  // namespace fcx

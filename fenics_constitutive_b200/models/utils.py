@@ -15,13 +15,15 @@ import numpy as np
 
 from .. import _buffers as B
 from .._lib import check, lib
-from .interfaces import StressStrainConstraint
+from .interfaces import IncrSmallStrainModel, StressStrainConstraint
 
 __all__ = [
     "lame_parameters",
     "get_elastic_tangent",
     "get_identity",
     "strain_from_grad_u",
+    "UniaxialStrainFrom3D",
+    "PlaneStrainFrom3D",
 ]
 
 _C = StressStrainConstraint
@@ -100,3 +102,88 @@ def strain_from_grad_u(grad_u, constraint: StressStrainConstraint):
         "strain_from_grad_u",
     )
     return out.cpu().numpy() if host else out
+
+
+class _From3D(IncrSmallStrainModel):
+    """Shared body of the 3D -> 1D/2D adapters (reference models/utils.py:211-412): the mapped
+    components of grad_del_u / stress are written into persistent 3D scratch arrays, the FULL
+    model is evaluated on them, and the mapped components of the 3D stress / tangent are
+    copied back.  Host numpy arrays take numpy slicing (as in the reference); CUDA tensors
+    take the fcx_embed_3d / fcx_extract_from_3d kernels and never leave HBM."""
+
+    _constraint: StressStrainConstraint
+
+    def __init__(self, model) -> None:
+        assert model.constraint == _C.FULL
+        self.model = model
+        self.stress_3d = None
+        self.tangent_3d = None
+        self.grad_del_u_3d = None
+
+    @property
+    def constraint(self) -> StressStrainConstraint:
+        return self._constraint
+
+    @property
+    def history_dim(self):
+        return self.model.history_dim
+
+    def update(self) -> None:
+        self.model.update()
+
+    def _scratch(self, n: int, like):
+        if isinstance(like, np.ndarray):
+            make = lambda m: np.zeros(m)  # noqa: E731
+        else:
+            import torch
+
+            make = lambda m: torch.zeros(m, dtype=torch.float64, device=like.device)  # noqa: E731
+        if self.tangent_3d is None:
+            self.tangent_3d = make(36 * n)
+        if self.stress_3d is None:
+            self.stress_3d = make(6 * n)
+        if self.grad_del_u_3d is None:
+            self.grad_del_u_3d = make(9 * n)
+
+    def evaluate(self, time, del_t, grad_del_u, mandel_stress, tangent, history) -> None:
+        g, s = self.geometric_dim, self.stress_strain_dim
+        bg = B.as_buf(grad_del_u, "grad_del_u")
+        n = bg.size // (g * g)
+        self._scratch(n, grad_del_u)
+        if bg.kind == B.HOST:
+            g3, s3, t3 = self.grad_del_u_3d.reshape(-1, 9), self.stress_3d.reshape(-1, 6), self.tangent_3d.reshape(-1, 36)
+            if g == 1:
+                g3[:, 0] = grad_del_u          # :285-287
+                s3[:, 0] = mandel_stress       # :289-292
+            else:
+                g2 = grad_del_u.reshape(-1, 4)
+                g3[:, 0:2] = g2[:, 0:2]        # :375-376
+                g3[:, 3:5] = g2[:, 2:4]
+                s3[:, 0:4] = mandel_stress.reshape(-1, 4)  # :384-386
+            self.model.evaluate(time, del_t, self.grad_del_u_3d, self.stress_3d, self.tangent_3d, history)
+            tangent.reshape(-1, s, s)[:] = t3.reshape(-1, 6, 6)[:, :s, :s]   # :299-302 / :393-412
+            mandel_stress.reshape(-1, s)[:] = s3[:, :s]                     # :293-297 / :388-391
+            return
+        L = lib()
+        bs = B.as_buf(mandel_stress, "stress", writable=True)
+        bt = B.as_buf(tangent, "tangent", writable=True)
+        b3 = [B.as_buf(a, "scratch", writable=True) for a in (self.grad_del_u_3d, self.stress_3d, self.tangent_3d)]
+        B.common_kind([bg, bs, bt] + b3)
+        check(L.fcx_set_device(bg.device_index))
+        stream = B.current_stream_ptr(bg.device_index)
+        check(L.fcx_embed_3d(self._constraint.value, n, bg.ptr, bs.ptr, b3[0].ptr, b3[1].ptr, stream), "fcx_embed_3d")
+        self.model.evaluate(time, del_t, self.grad_del_u_3d, self.stress_3d, self.tangent_3d, history)
+        check(L.fcx_extract_from_3d(self._constraint.value, n, b3[1].ptr, b3[2].ptr, bs.ptr, bt.ptr, stream),
+              "fcx_extract_from_3d")
+
+
+class UniaxialStrainFrom3D(_From3D):
+    """reference models/utils.py:211-297"""
+
+    _constraint = _C.UNIAXIAL_STRAIN
+
+
+class PlaneStrainFrom3D(_From3D):
+    """reference models/utils.py:300-412"""
+
+    _constraint = _C.PLANE_STRAIN

@@ -43,6 +43,7 @@ class NewtonSolver:
         self.linear_solver = "auto"  # "cg" | "dense" | "auto"
         self.cg_rtol = 1e-12
         self.cg_max_it = 20000
+        self.cg_check_every = 10  # host convergence checks (one sync each)
         self.reduce_over_ranks = False  # sum norms/dots over torch.distributed ranks
         self.residual_history: list[float] = []
         self.krylov_iterations: list[int] = []
@@ -76,8 +77,19 @@ class NewtonSolver:
         dx[idx] = sol
         return dx, 0
 
+    def _rsum(self, t):
+        """Sum of a 0-dim device tensor over ranks (no host synchronisation)."""
+        if self.reduce_over_ranks:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
     def _solve_cg(self, apply, rhs, free_mask, diag):
-        """Jacobi-preconditioned CG on the free dofs (projected operator P J P)."""
+        """Jacobi-preconditioned CG on the free dofs (projected operator P J P).  All
+        scalars stay on the device; the host looks at the residual norm only every
+        ``cg_check_every`` iterations, so an iteration is a fixed sequence of enqueued
+        kernels (two element kernels of problem.J_apply + a handful of vector ops)."""
         import torch
 
         fm = free_mask.to(torch.float64)
@@ -87,22 +99,25 @@ class NewtonSolver:
         z = minv * r
         p = z.clone()
         Ap = torch.empty_like(rhs)
-        rz = self._dot(r, z)
-        r0 = self._norm(r)
+        rz = self._rsum(torch.dot(r, z))
+        r0 = float(torch.sqrt(self._rsum(torch.dot(r, r))).item())
         if r0 == 0.0:
             return x, 0
+        tol2 = (self.cg_rtol * r0) ** 2
         it = 0
-        for it in range(1, self.cg_max_it + 1):
+        while it < self.cg_max_it:
             apply(p, Ap)
             Ap.mul_(fm)
-            alpha = rz / self._dot(p, Ap)
-            x.add_(p, alpha=alpha)
-            r.add_(Ap, alpha=-alpha)
-            if self._norm(r) <= self.cg_rtol * r0:
+            pAp = self._rsum(torch.dot(p, Ap))
+            alpha = torch.where(pAp > 0, rz / pAp, torch.zeros_like(rz))  # exact convergence: stay at x
+            x.addcmul_(p, alpha)
+            r.addcmul_(Ap, -alpha)
+            it += 1
+            if it % self.cg_check_every == 0 and float(self._rsum(torch.dot(r, r)).item()) <= tol2:
                 break
-            z = minv * r
-            rz_new = self._dot(r, z)
-            p.mul_(rz_new / rz).add_(z)
+            torch.mul(minv, r, out=z)
+            rz_new = self._rsum(torch.dot(r, z))
+            p.mul_(torch.where(rz > 0, rz_new / rz, torch.zeros_like(rz))).add_(z)
             rz = rz_new
         return x, it
 

@@ -102,6 +102,16 @@ int fcx_mises_evaluate(const double *params_host, size_t n, const double *grad_d
                        int eps_layout, unsigned char *plastic_flag, int *status,
                        void *stream);
 
+/* MisesPlasticityLinearHardening3D.evaluate -- the reference's Rust model
+ * comfe-rs/src/mises_plasticity.rs:58-126 behind models/rust_models.py:144-161
+ * (batch driver comfe-rs/src/interfaces.rs:354-456).  params = {mu, kappa, y_0, h}
+ * (HOST).  history: ONE array [n][7] = [alpha, plastic_strain[6]] per QP
+ * (key "history", bindings/src/lib.rs:90-100).  plastic_flag: optional u8[n]. */
+int fcx_mises_linear_hardening_evaluate(const double *params_host, size_t n,
+                                        const double *grad_del_u, double *stress,
+                                        double *tangent, double *history,
+                                        unsigned char *plastic_flag, void *stream);
+
 /* SpringKelvinModel.evaluate -- reference models/spring_kelvin_model.py:43-88.
  * D0 (s*s), I2 (s): HOST pointers to the constants of __init__ (:24-41);
  * mu0, lam0, mu1, tau as built there.  history: strain_visco [n][s], strain [n][s]. */
@@ -120,6 +130,18 @@ int fcx_maxwell_evaluate(int constraint, const double *D0_host, const double *D1
 /* strain_from_grad_u -- reference models/utils.py:132-208.  strain [n][s]. */
 int fcx_strain_from_grad_u(int constraint, size_t n, const double *grad_del_u,
                            double *strain, void *stream);
+
+/* 3D -> 1D/2D adapters, reference models/utils.py:211-412 (UniaxialStrainFrom3D,
+ * PlaneStrainFrom3D).  constraint = FCX_UNIAXIAL_STRAIN or FCX_PLANE_STRAIN.
+ * fcx_embed_3d writes the mapped components of grad_del_u [n][g][g] / stress [n][s]
+ * into the persistent 3D scratch arrays grad3d [n][9] / stress3d [n][6] (other
+ * components keep their values, as in the reference :285-292, :365-386);
+ * fcx_extract_from_3d copies stress3d[:, :s] and the leading s x s block of
+ * tangent3d [n][36] back (:293-302, :388-412). */
+int fcx_embed_3d(int constraint, size_t n, const double *grad_del_u, const double *stress,
+                 double *grad3d, double *stress3d, void *stream);
+int fcx_extract_from_3d(int constraint, size_t n, const double *stress3d, const double *tangent3d,
+                        double *stress, double *tangent, void *stream);
 
 /* Companion gather: IncrementalDisplacement.evaluate_local_incremental_gradient,
  * reference solver/_incrementalunknowns.py:19-27,40-49:
@@ -187,6 +209,11 @@ int fcx_elastic_evaluate_host(int constraint, const double *D, size_t n,
 int fcx_mises_evaluate_host(const double *params, size_t n, const double *grad_del_u,
                             double *stress, double *tangent, double *eps_n, double *alpha,
                             unsigned char *plastic_flag);
+
+int fcx_mises_linear_hardening_evaluate_host(const double *params, size_t n,
+                                             const double *grad_del_u, double *stress,
+                                             double *tangent, double *history,
+                                             unsigned char *plastic_flag);
 
 int fcx_kelvin_evaluate_host(int constraint, const double *D0, const double *I2, double mu0,
                              double lam0, double mu1, double tau, double del_t, size_t n,

@@ -114,6 +114,29 @@ class RustLinearElasticity3D(_Base):
         )
 
 
+class RustMisesPlasticityLinearHardening3D(_Base):
+    """comfe-rs MisesPlasticity3D (comfe-rs/src/mises_plasticity.rs:58-126); history is the single
+    key "history" [n][7] = [alpha, plastic_strain[6]] (bindings/src/lib.rs:90-100,131-136)."""
+
+    def __init__(self, parameters):
+        get = lambda k: float(np.asarray(parameters[k]).reshape(-1)[0])  # noqa: E731
+        self.params = np.array([get("mu"), get("kappa"), get("y_0"), get("h")], dtype=np.float64)
+        self.constraint = 5
+        self.plastic_flag = None
+
+    @property
+    def history_dim(self):
+        return {"history": 7}
+
+    def evaluate(self, t, del_t, grad_del_u, stress, tangent, history):
+        n = self._check_sizes(grad_del_u, stress, tangent)
+        self.plastic_flag = np.zeros(n, dtype=np.uint8)
+        lib().oracle_rs_mises_linear_hardening(
+            _p(self.params), n, _p(grad_del_u), _p(stress), _p(tangent), _p(history["history"]),
+            self.plastic_flag.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),
+        )
+
+
 class VonMises3D(_Base):
     def __init__(self, param):
         self.constraint = 5
