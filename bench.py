@@ -246,8 +246,18 @@ def run_native(args):
     # ---- end-to-end leg: public API, pinned host arrays, H2D + D2H in the timed region ----
     ne = args.e2e_qps
     Ke = args.e2e_steps
-    pin = lambda m: torch.empty(m, dtype=torch.float64).pin_memory()  # noqa: E731
+    reg_s = None
+    if args.e2e_memory == "pinned":
+        pin = lambda m: torch.empty(m, dtype=torch.float64).pin_memory()  # noqa: E731
+    else:  # ordinary (pageable) numpy memory, as dolfinx hands it over
+        pin = lambda m: torch.from_numpy(np.zeros(m))  # noqa: E731
     h_grad, h_st, h_ep, h_al, h_tg = pin(ne * 9), pin(ne * 6), pin(ne * 6), pin(ne), pin(ne * 36)
+    if args.e2e_memory == "registered":  # pageable arrays page-locked once with fcx_host_register
+        t0 = time.perf_counter()
+        for a in (h_grad, h_st, h_ep, h_al, h_tg):
+            rc = L.fcx_host_register(a.data_ptr(), a.numel() * 8)
+            assert rc == 0, f"fcx_host_register rc={rc}"
+        reg_s = time.perf_counter() - t0
     rng = np.random.default_rng(99 + rank)
     h_grad.numpy()[:] = rng.standard_normal(ne * 9) * synthetic.MISES_GRAD_STD
     law_h = VonMises3D(synthetic.MISES_PARAMS)
@@ -290,10 +300,14 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": H2D_PER_QP * ne,
                     "d2h_bytes_per_step": D2H_PER_QP * ne, "qps_per_gpu": ne, "steps": Ke,
                     "plastic_fraction": round(e2e_plastic, 4),
-                    "api": "VonMises3D.evaluate(numpy pinned host arrays) -> fcx_mises_evaluate_host"},
+                    "host_memory": args.e2e_memory, "register_s": reg_s,
+                    "api": f"VonMises3D.evaluate(numpy {args.e2e_memory} host arrays) -> fcx_mises_evaluate_host"},
             "gpu_launches": launches, "clocks": clocks, "host_cpus": os.cpu_count(),
         }
         print(json.dumps(line), flush=True)
+    if args.e2e_memory == "registered":
+        for a in (h_grad, h_st, h_ep, h_al, h_tg):
+            L.fcx_host_unregister(a.data_ptr())
     if world > 1:
         dist.destroy_process_group()
 
@@ -307,6 +321,8 @@ def main():
     ap.add_argument("--qps", type=int, default=N_QP, help="QPs per GPU (default: the 16M workload)")
     ap.add_argument("--e2e-qps", type=int, default=N_QP)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-memory", choices=["pinned", "pageable", "registered"], default="pinned",
+                    help="host memory of the e2e leg's arrays (default: page-locked)")
     ap.add_argument("--cpu-sample", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

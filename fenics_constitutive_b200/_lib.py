@@ -35,8 +35,11 @@ SIGNATURES = {
     "fcx_gather_grad": (_ci, [_ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _vp]),
     "fcx_mises_linear_hardening_evaluate": (_ci, [_dp, _sz, _dp, _dp, _dp, _dp, _vp, _vp]),
     "fcx_mises_linear_hardening_evaluate_host": (_ci, [_dp, _sz, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_drucker_prager_evaluate": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp, _dp, _vp, _vp, _vp]),
+    "fcx_drucker_prager_evaluate_host": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp, _dp, _vp]),
     "fcx_mises_form": (_ci, [_dp, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
                              _dp, _vp, _vp, _vp]),
+    "fcx_fe_stride": (_ci, [_ci]),
     "fcx_internal_force": (_ci, [_ci, _ci, _sz, _ci, _ci, _dp, _dp, _dp, _dp, _dp, _dp, _vp]),
     "fcx_tangent_apply": (_ci, [_ci, _ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp]),
     "fcx_tangent_diag": (_ci, [_ci, _ci, _sz, _ci, _ci, _dp, _dp, _dp, _dp, _dp, _dp, _vp]),
@@ -47,6 +50,8 @@ SIGNATURES = {
     "fcx_maxwell_evaluate_host": (_ci, [_ci, _dp, _dp, _cd, _cd, _cd, _sz, _dp, _dp, _dp, _dp, _dp]),
     "fcx_host_register": (_ci, [_vp, _sz]),
     "fcx_host_unregister": (_ci, [_vp]),
+    "fcx_host_staging": (_ci, [_ci]),
+    "fcx_host_threads": (_ci, [_ci]),
     "fcx_host_chunk_qps": (_sz, [_sz]),
     "fcx_host_release": (None, []),
     "fcx_launch_count": (ctypes.c_ulonglong, []),

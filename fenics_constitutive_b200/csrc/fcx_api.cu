@@ -59,6 +59,7 @@ static int g_mises_variant = 1;
 static int g_mises_tile = 64;  // QPs per tile of the output-staged kernel (64 or 128)
 // Hand tiles out through an atomic ticket counter (all tile kernels).
 static int g_dynamic_tiles = 1;
+static int g_fem_variant = 1;
 static int g_hints = 8;  // bit1: evict_first on bulk loads, bit2: on bulk stores,
                          // bit3: constant tangents written by bulk stores from shared memory
 
@@ -96,6 +97,13 @@ static unsigned long long *ticket_for(cudaStream_t stream)
         return nullptr;
     return ptr;  // nullptr -> static tile stride
 }
+
+unsigned long long *tile_ticket(cudaStream_t stream)
+{
+    return g_dynamic_tiles ? ticket_for(stream) : nullptr;
+}
+int tuned_ctas_per_sm() { return g_ctas_per_sm; }
+int fem_variant() { return g_fem_variant; }
 
 template <class M, int TILE>
 static int launch_tile_t(const typename M::Params &prm, const SegPtrs<M::nseg()> &io,
@@ -440,6 +448,11 @@ int fcx_tune(const char *key, int value)
         g_ctas_per_sm = value;
         return old;
     }
+    if (key && strcmp(key, "fem_variant") == 0) {
+        const int old = g_fem_variant;
+        g_fem_variant = value;
+        return old;
+    }
     if (key && strcmp(key, "tile") == 0) {
         if (value != 64 && value != 128 && value != 256)
             return FCX_ERR_ARG;
@@ -575,6 +588,29 @@ int fcx_mises_linear_hardening_evaluate(const double *params, size_t n, const do
     const bool al = aligned16(grad) && aligned16(stress) && aligned16(tangent) && aligned16(history);
     return launch_tile<MisesLinModel>(P, io, tangent, n, al, plastic_flag, nullptr,
                                       static_cast<cudaStream_t>(stream));
+}
+
+int fcx_drucker_prager_evaluate(int hyperbolic, const double *params, size_t n, const double *grad,
+                                double *stress, double *tangent, double *history,
+                                unsigned char *plastic_flag, int *status, void *stream)
+{
+    if (n == 0)
+        return FCX_OK;
+    if (!params || !grad || !stress || !tangent || !history)
+        return FCX_ERR_NULL;
+    DruckerPragerParams P;
+    P.mu = params[0];
+    P.kappa = params[1];
+    P.a = params[2];
+    P.b = params[3];
+    P.d2 = hyperbolic ? params[4] * params[4] : 0.0;  // d.powi(2)
+    P.b_flow = hyperbolic ? params[5] : params[4];
+    SegPtrs<3> io{{const_cast<double *>(grad), stress, history}};
+    const bool al = aligned16(grad) && aligned16(stress) && aligned16(tangent) && aligned16(history);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (hyperbolic)
+        return launch_tile<DruckerPragerModel<true>>(P, io, tangent, n, al, plastic_flag, status, st);
+    return launch_tile<DruckerPragerModel<false>>(P, io, tangent, n, al, plastic_flag, status, st);
 }
 
 int fcx_mises_form(const double *params, size_t ncells, int nq, int nd, const int *dofmap,

@@ -13,37 +13,35 @@
 //     fe[a][j]      = sum_q w_q |detJ|  b_aj(q) . sigma_q
 //     (K p)e[a][j]  = sum_q w_q |detJ|  b_aj(q) . (C_q^T eps_q(p))
 //     diag(K)e[a][j]= sum_q w_q |detJ|  b_aj(q) . (C_q^T b_aj(q))
-// One thread owns one affine simplex cell and writes its element vector
-// [ND][G]; the global vector is then formed by a deterministic gather-sum over
-// the node -> (cell, local index) adjacency (no atomics: results do not depend
-// on scheduling, cf. reference tests/solver/test_solver_mpi.py:93-121).
+// Each cell's element vector goes to fe [ncells][ND][FS] (FS = 4 for G = 3: one
+// 32-byte sector per (cell, node) slot, else G); the global vector is then
+// formed by a deterministic gather-sum over the node -> (cell, local index)
+// adjacency (no atomics: results do not depend on scheduling, cf. reference
+// tests/solver/test_solver_mpi.py:93-121).
+//
+// Two implementations of the element kernels (fcx_tune "fem_variant"):
+//   1 (default) qp_cell_kernel: one thread per QUADRATURE POINT of a tile of
+//     whole cells; the tile's tangent (or stress) block, Jinv, detJ and dofmap
+//     rows are contiguous ranges and arrive by 1-D bulk async copies (TMA) one
+//     tile ahead; the NQ per-QP contributions of a cell are summed through
+//     shared memory in a fixed order and leave as one coalesced stream.
+//   0 cell_kernel: one thread per cell, plain strided loads (the first version;
+//     kept for A/B measurements -- L1-bound at 12 % occupancy, profiles/r1k).
 #include <cuda_runtime.h>
 
 #include "../../include/fcx.h"
+#include "fcx_fem.cuh"
 #include "fcx_internal.h"
-#include "fcx_models.cuh"
+#include "fcx_ptx.cuh"
 
 namespace fcx {
 
 constexpr int ASM_THREADS = 128;
 
-// physical basis gradients of local function a at QP q:  gphi[i] = sum_k Jinv[k][i] * dphi_ref[q][a][k]
-template <int G>
-__device__ __forceinline__ void phys_grad(const double *K, const double *dref, double *gphi)
-{
-#pragma unroll
-    for (int i = 0; i < G; ++i) {
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < G; ++k)
-            acc += K[k * G + i] * dref[k];
-        gphi[i] = acc;
-    }
-}
-
-// b_aj . t  for all j:  out[j] = sum_k mandel_strain(grad = gphi (x) e_j)[k] * t[k]
+// Mandel strain of grad = gphi (x) e_j dotted with t, all j (generic form used by
+// the per-cell kernel; the QP-parallel kernel uses bt_dot of fcx_fem.cuh).
 template <int S, int G>
-__device__ __forceinline__ void bt_dot(const double *gphi, const double *t, double *out)
+__device__ __forceinline__ void bt_dot_dense(const double *gphi, const double *t, double *out)
 {
 #pragma unroll
     for (int j = 0; j < G; ++j) {
@@ -184,19 +182,20 @@ __global__ void __launch_bounds__(ASM_THREADS)
                         out[j] = s;
                     }
                 } else {
-                    bt_dot<S, G>(gphi, t, out);
+                    bt_dot_dense<S, G>(gphi, t, out);
                 }
 #pragma unroll
                 for (int j = 0; j < G; ++j)
                     acc[a][j] += wdet * out[j];
             }
         }
-        double *dst = fe + c * (ND * G);
+        constexpr int FS = FeStride<G>::v;
+        double *dst = fe + c * (ND * FS);
 #pragma unroll
         for (int a = 0; a < ND; ++a)
 #pragma unroll
-            for (int j = 0; j < G; ++j)
-                dst[a * G + j] = acc[a][j];
+            for (int j = 0; j < FS; ++j)
+                dst[a * FS + j] = (j < G) ? acc[a][j < G ? j : 0] : 0.0;
     }
 }
 
@@ -217,10 +216,17 @@ __global__ void __launch_bounds__(256)
             acc[j] = 0.0;
         const long long e0 = adj_ptr[v], e1 = adj_ptr[v + 1];
         for (long long e = e0; e < e1; ++e) {
-            const double *src = fe + (size_t)adj_idx[e] * G;
+            const double *src = fe + (size_t)adj_idx[e] * FeStride<G>::v;
+            if (G == 3) {  // one 32-byte sector: 16-byte + 8-byte load
+                const double2 xy = *reinterpret_cast<const double2 *>(src);
+                acc[0] += xy.x;
+                acc[1 % G] += xy.y;
+                acc[2 % G] += src[2];
+            } else {
 #pragma unroll
-            for (int j = 0; j < G; ++j)
-                acc[j] += src[j];
+                for (int j = 0; j < G; ++j)
+                    acc[j] += src[j];
+            }
         }
 #pragma unroll
         for (int j = 0; j < G; ++j) {
@@ -230,12 +236,292 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// QP-parallel element kernel (fem_variant 1)
+// ---------------------------------------------------------------------------
+struct CellArgs {
+    const int *dofmap;       // [ncells][ND]            (MODE 1)
+    const double *p;         // [nnodes][G]             (MODE 1)
+    const double *dphi_ref;  // [NQ][ND][G]
+    const double *weights;   // [NQ]
+    const double *Jinv;      // [ncells][G][G]
+    const double *detJ;      // [ncells]
+    const double *qarr;      // MODE 0: stress [nqp][S]; MODE 1/2: tangent [nqp][S][S]
+    double *fe;              // [ncells][ND][FS]
+    unsigned long long ncells;
+    unsigned long long *ticket;
+    int bulk_ok;             // Jinv, detJ, dofmap, qarr 16-byte aligned
+};
+
+template <int G, int S, int ND, int NQ, int MODE>
+struct CellCfg {
+    static constexpr int TILE = fem_tile<NQ>();
+    static constexpr int CPT = TILE / NQ;                    // cells per tile (a multiple of 16)
+    static constexpr int SEGW = (MODE == 0) ? S : S * S;     // staged doubles per QP
+    static constexpr int NDG = ND * G;
+    static constexpr int PST = NDG | 1;                      // odd stride: conflict-free partials
+    static constexpr int DOF_DBL = (CPT * ND + 1) / 2;       // dofmap rows, in doubles
+    // NQ = 4 in 3-D: the four QP threads of a cell are four consecutive lanes; their
+    // contributions are reduce-scattered with shuffles and written straight to fe
+    // (no partial-sum stage: 21 KB instead of 37 KB of shared memory per CTA).
+    static constexpr bool SHFL = (NQ == 4 && G == 3);
+    static constexpr size_t smem_doubles = (size_t)TILE * SEGW + CPT * G * G + CPT + DOF_DBL +
+                                           (SHFL ? 0 : (size_t)TILE * PST) + NQ * ND * G + NQ + 2;
+    static constexpr size_t smem_bytes = sizeof(double) * smem_doubles;
+};
+
+template <int G, int S, int ND, int NQ, int MODE>
+__global__ void __launch_bounds__(fem_tile<NQ>())
+    qp_cell_kernel(const __grid_constant__ CellArgs A)
+{
+    using Cfg = CellCfg<G, S, ND, NQ, MODE>;
+    constexpr int TILE = Cfg::TILE, CPT = Cfg::CPT, SEGW = Cfg::SEGW, PST = Cfg::PST;
+    constexpr int FS = FeStride<G>::v;
+    static_assert(CPT % 16 == 0, "tile ranges must be 16-byte multiples");
+    extern __shared__ __align__(128) double smem[];
+    double *s_stage = smem;                              // [TILE][SEGW]   (bulk, barrier 1)
+    double *s_jinv = s_stage + TILE * SEGW;              // [CPT][G*G]     (bulk, barrier 0)
+    double *s_det = s_jinv + CPT * G * G;                // [CPT]          (bulk, barrier 0)
+    int *s_dof = reinterpret_cast<int *>(s_det + CPT);   // [CPT][ND]      (bulk, barrier 0; MODE 1)
+    double *s_part = s_det + CPT + Cfg::DOF_DBL;         // [TILE][PST]    (not with SHFL)
+    double *s_tab = s_part + (Cfg::SHFL ? 0 : TILE * PST);  // [NQ][ND][G]
+    double *s_wq = s_tab + NQ * ND * G;                  // [NQ]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_wq + NQ);  // [2]
+    __shared__ unsigned long long s_next[2];  // slot = iteration parity (SHFL: one CTA barrier per tile)
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NQ * ND * G; i += TILE)
+        s_tab[i] = A.dphi_ref[i];
+    if (tid < NQ)
+        s_wq[tid] = A.weights[tid];
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const unsigned long long ntiles = (A.ncells + CPT - 1) / CPT;
+    auto is_bulk = [&](unsigned long long t) { return A.bulk_ok && (t + 1) * CPT <= A.ncells; };
+    auto issue = [&](unsigned long long t) {  // thread 0: all ranges of tile t, one tile ahead
+        const unsigned long long c0 = t * CPT, q0 = t * TILE;
+        constexpr uint32_t small_bytes =
+            (uint32_t)(sizeof(double) * (CPT * G * G + CPT) + (MODE == 1 ? sizeof(int) * CPT * ND : 0));
+        mbar_arrive_expect_tx(&bar[0], small_bytes);
+        bulk_g2s(s_jinv, A.Jinv + c0 * (G * G), (uint32_t)(sizeof(double) * CPT * G * G), &bar[0]);
+        bulk_g2s(s_det, A.detJ + c0, (uint32_t)(sizeof(double) * CPT), &bar[0]);
+        if (MODE == 1)
+            bulk_g2s(s_dof, A.dofmap + c0 * ND, (uint32_t)(sizeof(int) * CPT * ND), &bar[0]);
+        mbar_arrive_expect_tx(&bar[1], (uint32_t)(sizeof(double) * TILE * SEGW));
+        bulk_g2s(s_stage, A.qarr + q0 * SEGW, (uint32_t)(sizeof(double) * TILE * SEGW), &bar[1]);
+    };
+
+    uint32_t parity = 0;
+    int it = 0;
+    unsigned long long tile = blockIdx.x;
+    bool bulk = tile < ntiles && is_bulk(tile);
+    if (tid == 0 && bulk)
+        issue(tile);
+    while (tile < ntiles) {
+        const unsigned long long c0 = tile * CPT, q0 = tile * TILE;
+        const int ncell = (A.ncells - c0 < (unsigned long long)CPT) ? (int)(A.ncells - c0) : CPT;
+        const int cnt = ncell * NQ;
+        if (tid == 0)
+            s_next[it] = (A.ticket != nullptr) ? gridDim.x + atomicAdd(A.ticket, 1ULL) : tile + gridDim.x;
+        if (bulk) {
+            mbar_wait(&bar[0], parity);
+        } else {  // ragged last tile / unaligned views: cooperative plain loads into the same stage
+            for (int i = tid; i < ncell * G * G; i += TILE)
+                s_jinv[i] = A.Jinv[c0 * (G * G) + i];
+            for (int i = tid; i < ncell; i += TILE)
+                s_det[i] = A.detJ[c0 + i];
+            if (MODE == 1)
+                for (int i = tid; i < ncell * ND; i += TILE)
+                    s_dof[i] = A.dofmap[c0 * ND + i];
+            for (int i = tid; i < cnt * SEGW; i += TILE)
+                s_stage[i] = A.qarr[q0 * SEGW + i];
+            __syncthreads();
+        }
+
+        const bool active = tid < cnt;
+        const int lc = tid / NQ, q = tid - lc * NQ;
+        double K[G * G], e[S];
+        double wdet = 0.0;
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+            e[i] = 0.0;
+        if (active || Cfg::SHFL) {
+#pragma unroll
+            for (int i = 0; i < G * G; ++i)
+                K[i] = s_jinv[lc * (G * G) + i];
+            wdet = s_wq[q] * s_det[lc];
+            if (MODE == 1 && NQ == 4 && Cfg::SHFL) {  // Mandel strain of nabla_grad(p) at this QP
+                double g[G * G];
+                grad_of_increment_quad<G, ND>(s_tab + q * ND * G, K, s_dof + lc * ND, A.p, nullptr, active, q, g);
+                mandel_strain<S, G>(g, e);
+            } else if (MODE == 1 && active) {
+                double g[G * G];
+                grad_of_increment<G, ND>(s_tab + q * ND * G, K, s_dof + lc * ND, A.p, nullptr, g);
+                mandel_strain<S, G>(g, e);
+            }
+        }
+        if (bulk) {
+            mbar_wait(&bar[1], parity);
+            parity ^= 1;
+        }
+        if (active || Cfg::SHFL) {  // SHFL: idle lanes of a ragged tile take part in the shuffles with zeros
+            double row[SEGW];
+            const double *src = s_stage + tid * SEGW;
+            // (idle lanes read in-bounds stage garbage; a cell's 4 lanes are all idle or all
+            //  active, so garbage is only ever exchanged among idle lanes and never stored)
+            if (SEGW % 2 == 0) {
+#pragma unroll
+                for (int i = 0; i < SEGW; i += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(src + i);
+                    row[i] = v.x;
+                    row[i + 1 < SEGW ? i + 1 : i] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < SEGW; ++i)
+                    row[i] = src[i];
+            }
+            double t[S], ts[S];
+            if (MODE == 0) {
+#pragma unroll
+                for (int k = 0; k < S; ++k)
+                    t[k] = row[k];
+            } else if (MODE == 1) {  // tau = C^T eps
+#pragma unroll
+                for (int k = 0; k < S; ++k)
+                    t[k] = 0.0;
+#pragma unroll
+                for (int m = 0; m < S; ++m)
+#pragma unroll
+                    for (int k = 0; k < S; ++k)
+                        t[k] = fma(row[(m * S + k) % SEGW], e[m], t[k]);
+            }
+            if (MODE != 2)
+                prescale_shear<S, G>(t, ts);
+            double *part = s_part + tid * PST;
+            double *fe_cell = A.fe + (c0 + lc) * (ND * FS);
+#pragma unroll
+            for (int a = 0; a < ND; ++a) {
+                double gphi[G], out[G];
+                phys_grad<G>(K, s_tab + (q * ND + a) * G, gphi);
+                if (MODE == 2) {  // b_aj . (C^T b_aj) for each j
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        double g[G * G], b[S];
+#pragma unroll
+                        for (int i = 0; i < G * G; ++i)
+                            g[i] = 0.0;
+#pragma unroll
+                        for (int i = 0; i < G; ++i)
+                            g[i * G + j] = gphi[i];
+                        mandel_strain<S, G>(g, b);
+                        double acc = 0.0;
+#pragma unroll
+                        for (int m = 0; m < S; ++m)
+#pragma unroll
+                            for (int k = 0; k < S; ++k)
+                                acc += b[k] * (row[(m * S + k) % SEGW] * b[m]);
+                        out[j] = acc;
+                    }
+                } else {
+                    bt_dot<S, G>(gphi, ts, out);
+                }
+                if (Cfg::SHFL) {
+                    // reduce-scatter over the cell's 4 lanes: lane q ends with component j = q
+                    // of node a summed over the 4 QPs, (q0 + q2) + (q1 + q3); lane 3 = the pad.
+                    const double v0 = wdet * out[0], v1 = wdet * out[1 % G], v2 = wdet * out[2 % G];
+                    const bool hi = (q & 2) != 0, od = (q & 1) != 0;
+                    const double ka = (hi ? v2 : v0) + __shfl_xor_sync(0xffffffffu, hi ? v0 : v2, 2);
+                    const double kb = (hi ? 0.0 : v1) + __shfl_xor_sync(0xffffffffu, hi ? v1 : 0.0, 2);
+                    const double r = (od ? kb : ka) + __shfl_xor_sync(0xffffffffu, od ? ka : kb, 1);
+                    if (active)
+                        fe_cell[a * FS + q] = r;  // 4 lanes = one 32-byte sector
+                } else {
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+                        part[a * G + j] = wdet * out[j];
+                }
+            }
+        }
+        __syncthreads();  // partials complete; every staged range has been consumed
+        const unsigned long long next = s_next[it];
+        it ^= 1;
+        const bool next_bulk = next < ntiles && is_bulk(next);
+        if (tid == 0 && next_bulk)
+            issue(next);  // overlaps the reduction below and the next tile's gathers
+
+        // fe[c][a][j] = sum_q part[c*NQ + q][a*G + j], fixed order; dense coalesced stream
+        double *dst = A.fe + c0 * (ND * FS);
+        for (int idx = tid; !Cfg::SHFL && idx < ncell * ND * FS; idx += TILE) {
+            const int cell = idx / (ND * FS), r = idx - cell * (ND * FS);
+            const int a = r / FS, j = r - a * FS;
+            double acc = 0.0;
+            if (j < G) {
+#pragma unroll
+                for (int qq = 0; qq < NQ; ++qq)
+                    acc += s_part[(cell * NQ + qq) * PST + a * G + j];
+            }
+            dst[idx] = acc;
+        }
+        if (!Cfg::SHFL)
+            __syncthreads();  // partials consumed before the next tile overwrites them
+        tile = next;
+        bulk = next_bulk;
+    }
+}
+
+template <int G, int S, int ND, int NQ, int MODE>
+static int launch_qp_cell(const CellArgs &A0, cudaStream_t st)
+{
+    using Cfg = CellCfg<G, S, ND, NQ, MODE>;
+    auto kern = qp_cell_kernel<G, S, ND, NQ, MODE>;
+    static int occ = -1;
+    if (occ < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)Cfg::smem_bytes);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaFuncSetAttribute(qp_cell)");
+        int o = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, Cfg::TILE, Cfg::smem_bytes);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaOccupancy(qp_cell)");
+        occ = o > 0 ? o : 1;
+    }
+    CellArgs A = A0;
+    const unsigned long long ntiles = (A.ncells + Cfg::CPT - 1) / Cfg::CPT;
+    const int per_sm = tuned_ctas_per_sm() > 0 ? tuned_ctas_per_sm() : occ;
+    unsigned long long grid = (unsigned long long)sm_count() * per_sm;
+    if (grid > ntiles)
+        grid = ntiles;
+    A.ticket = (ntiles > grid) ? tile_ticket(st) : nullptr;
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    A.bulk_ok = al16(A.Jinv) && al16(A.detJ) && al16(A.qarr) && (MODE != 1 || al16(A.dofmap));
+    kern<<<(unsigned)grid, Cfg::TILE, Cfg::smem_bytes, st>>>(A);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "qp_cell_kernel launch");
+}
+
 template <int G, int S, int ND, int NQ>
 static int launch_cell(int mode, size_t ncells, const int *dofmap, const double *p,
                        const double *dphi, const double *w, const double *Jinv,
                        const double *detJ, const double *qvec, const double *tangent, double *fe,
                        cudaStream_t st)
 {
+    if (fem_variant() != 0) {
+        CellArgs A{dofmap, p, dphi, w, Jinv, detJ, mode == 0 ? qvec : tangent, fe,
+                   (unsigned long long)ncells, nullptr, 0};
+        switch (mode) {
+        case 0: return launch_qp_cell<G, S, ND, NQ, 0>(A, st);
+        case 1: return launch_qp_cell<G, S, ND, NQ, 1>(A, st);
+        default: return launch_qp_cell<G, S, ND, NQ, 2>(A, st);
+        }
+    }
     unsigned long long grid = (ncells + ASM_THREADS - 1) / ASM_THREADS;
     const unsigned long long cap = (unsigned long long)sm_count() * 16;
     if (grid > cap)
@@ -285,6 +571,8 @@ static int dispatch_cell(int mode, int gdim, int sdim, size_t ncells, int nq, in
 using namespace fcx;
 
 extern "C" {
+
+int fcx_fe_stride(int gdim) { return gdim == 3 ? 4 : (gdim == 1 || gdim == 2 ? gdim : FCX_ERR_ARG); }
 
 int fcx_internal_force(int gdim, int sdim, size_t ncells, int nq, int nd, const double *dphi_ref,
                        const double *weights, const double *Jinv, const double *detJ,

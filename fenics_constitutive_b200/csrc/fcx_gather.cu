@@ -9,111 +9,150 @@
 // For an affine cell with reference gradients dphi_ref[q][a][k] = dphi_a/dX_k and
 // Jinv[k][i] = dX_k/dx_i:
 //     T[k][j]     = sum_a dphi_ref[q][a][k] * du[a][j]
-//     grad[i][j]  = sum_k Jinv[k][i] * T[k][j]
-// One thread owns one cell: it gathers the cell's nd nodal increments once
-// (L2-resident, shared with neighbouring cells), keeps them in registers for
-// all nq quadrature points, and stages its nq*g*g results in shared memory so
-// the CTA writes the [cells][nq][g][g] block as one dense coalesced stream.
+//     grad[i][j]  = sum_k Jinv[k][i] * T[k][j]              (grad_at_qp, fcx_fem.cuh)
+// One thread owns one QUADRATURE POINT of a tile of whole cells (64 or 96 QPs).
+// The tile's dofmap rows and Jinv blocks are contiguous ranges and arrive by 1-D
+// bulk async copies (TMA) one tile ahead; the nodal increments are gathered
+// straight from L1/L2 (the NQ threads of a cell hit the same sectors; two load
+// instructions per 3-D node, load_node) and accumulated on the fly (9
+// accumulators, no per-cell register array, so the kernel runs at high
+// occupancy); the tile's [TILE][g][g] result block is staged in shared memory
+// (double-buffered) and leaves as one bulk async store.
 #include <cuda_runtime.h>
 
 #include "../../include/fcx.h"
+#include "fcx_fem.cuh"
 #include "fcx_internal.h"
 #include "fcx_ptx.cuh"
 
 namespace fcx {
 
-constexpr int GATHER_CELLS = 128;  // cells (= threads) per CTA
+struct GatherArgs {
+    const int *dofmap;
+    const double *u;
+    const double *u_prev;  // or nullptr
+    const double *dphi_ref;
+    const double *Jinv;
+    double *grad;
+    unsigned long long ncells;
+    unsigned long long *ticket;
+    int bulk_ok;  // dofmap, Jinv, grad 16-byte aligned
+};
 
 template <int G, int ND, int NQ>
-__global__ void __launch_bounds__(GATHER_CELLS)
-    gather_kernel(const int *__restrict__ dofmap, const double *__restrict__ u,
-                  const double *__restrict__ u_prev, const double *__restrict__ dphi_ref,
-                  const double *__restrict__ Jinv, double *__restrict__ grad,
-                  const unsigned long long ncells, const int vec_ok)
+struct GatherCfg {
+    static constexpr int TILE = fem_tile<NQ>();
+    static constexpr int CPT = TILE / NQ;
+    static constexpr int GG = G * G;
+    static constexpr int DOF_DBL = (CPT * ND + 1) / 2;
+    static constexpr size_t smem_bytes =
+        sizeof(double) * (2 * (size_t)TILE * GG + CPT * GG + DOF_DBL + NQ * ND * G + 1);
+};
+
+template <int G, int ND, int NQ>
+__global__ void __launch_bounds__(fem_tile<NQ>())
+    gather_kernel(const __grid_constant__ GatherArgs A)
 {
-    constexpr int OUT = NQ * G * G;          // doubles per cell
-    constexpr int OUTP = OUT | 1;            // odd stride: conflict-free staging
-    extern __shared__ __align__(16) double sm[];
-    double *tab = sm;                        // [NQ][ND][G]
-    double *stage = sm + ((NQ * ND * G + 1) & ~1);  // [GATHER_CELLS][OUTP]
+    using Cfg = GatherCfg<G, ND, NQ>;
+    constexpr int TILE = Cfg::TILE, CPT = Cfg::CPT, GG = Cfg::GG;
+    static_assert(CPT % 16 == 0, "tile ranges must be 16-byte multiples");
+    extern __shared__ __align__(128) double smem[];
+    double *s_out = smem;                                   // [2][TILE][GG]
+    double *s_jinv = s_out + 2 * TILE * GG;                 // [CPT][GG]
+    int *s_dof = reinterpret_cast<int *>(s_jinv + CPT * GG);  // [CPT][ND]
+    double *s_tab = s_jinv + CPT * GG + Cfg::DOF_DBL;       // [NQ][ND][G]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_tab + NQ * ND * G);
+    __shared__ unsigned long long s_next[2];  // slot = iteration parity (one CTA barrier per tile)
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < NQ * ND * G; i += GATHER_CELLS)
-        tab[i] = dphi_ref[i];
+    for (int i = tid; i < NQ * ND * G; i += TILE)
+        s_tab[i] = A.dphi_ref[i];
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
     __syncthreads();
 
-    const unsigned long long ngroups = (ncells + GATHER_CELLS - 1) / GATHER_CELLS;
-    for (unsigned long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        const unsigned long long c0 = grp * GATHER_CELLS;
-        const unsigned long long c = c0 + tid;
-        const int cnt = (ncells - c0 < (unsigned long long)GATHER_CELLS) ? (int)(ncells - c0)
-                                                                         : GATHER_CELLS;
-        if (tid < cnt) {
-            double du[ND][G];
+    const unsigned long long ntiles = (A.ncells + CPT - 1) / CPT;
+    auto is_bulk = [&](unsigned long long t) { return A.bulk_ok && (t + 1) * CPT <= A.ncells; };
+    auto issue = [&](unsigned long long t) {
+        const unsigned long long c0 = t * CPT;
+        mbar_arrive_expect_tx(bar, (uint32_t)(sizeof(double) * CPT * GG + sizeof(int) * CPT * ND));
+        bulk_g2s(s_jinv, A.Jinv + c0 * GG, (uint32_t)(sizeof(double) * CPT * GG), bar);
+        bulk_g2s(s_dof, A.dofmap + c0 * ND, (uint32_t)(sizeof(int) * CPT * ND), bar);
+    };
+
+    uint32_t parity = 0;
+    int buf = 0, it = 0;
+    unsigned long long tile = blockIdx.x;
+    bool bulk = tile < ntiles && is_bulk(tile);
+    if (tid == 0 && bulk)
+        issue(tile);
+    while (tile < ntiles) {
+        const unsigned long long c0 = tile * CPT, q0 = tile * TILE;
+        const int ncell = (A.ncells - c0 < (unsigned long long)CPT) ? (int)(A.ncells - c0) : CPT;
+        const int cnt = ncell * NQ;
+        if (tid == 0)
+            s_next[it] = (A.ticket != nullptr) ? gridDim.x + atomicAdd(A.ticket, 1ULL) : tile + gridDim.x;
+        if (bulk) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        } else {  // ragged last tile / unaligned views
+            for (int i = tid; i < ncell * GG; i += TILE)
+                s_jinv[i] = A.Jinv[c0 * GG + i];
+            for (int i = tid; i < ncell * ND; i += TILE)
+                s_dof[i] = A.dofmap[c0 * ND + i];
+            __syncthreads();
+        }
+        {
+            const bool active = tid < cnt;
+            const int lc = tid / NQ, q = tid - lc * NQ;
+            double K[GG], g[GG];
 #pragma unroll
-            for (int a = 0; a < ND; ++a) {
-                const size_t node = (size_t)dofmap[c * ND + a];
+            for (int i = 0; i < GG; ++i)
+                K[i] = s_jinv[lc * GG + i];  // (idle lanes: in-bounds stage garbage, never stored)
+            if (NQ == 4) {
+                grad_of_increment_quad<G, ND>(s_tab + q * ND * G, K, s_dof + lc * ND, A.u, A.u_prev, active, q, g);
+            } else if (active) {
+                grad_of_increment<G, ND>(s_tab + q * ND * G, K, s_dof + lc * ND, A.u, A.u_prev, g);
+            }
+            if (active) {
+                if (bulk) {
+                    double *o = s_out + (buf * TILE + tid) * GG;
 #pragma unroll
-                for (int j = 0; j < G; ++j) {
-                    double v = u[node * G + j];
-                    if (u_prev != nullptr)
-                        v -= u_prev[node * G + j];
-                    du[a][j] = v;
+                    for (int i = 0; i < GG; ++i)
+                        o[i] = g[i];
+                } else {
+                    double *o = A.grad + (q0 + tid) * GG;
+#pragma unroll
+                    for (int i = 0; i < GG; ++i)
+                        o[i] = g[i];
                 }
             }
-            double K[G][G];
-#pragma unroll
-            for (int k = 0; k < G; ++k)
-#pragma unroll
-                for (int i = 0; i < G; ++i)
-                    K[k][i] = Jinv[c * (G * G) + k * G + i];
-            double *out = stage + tid * OUTP;
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                double T[G][G];
-#pragma unroll
-                for (int k = 0; k < G; ++k)
-#pragma unroll
-                    for (int j = 0; j < G; ++j)
-                        T[k][j] = 0.0;
-#pragma unroll
-                for (int a = 0; a < ND; ++a)
-#pragma unroll
-                    for (int k = 0; k < G; ++k) {
-                        const double d = tab[(q * ND + a) * G + k];
-#pragma unroll
-                        for (int j = 0; j < G; ++j)
-                            T[k][j] += d * du[a][j];
-                    }
-#pragma unroll
-                for (int i = 0; i < G; ++i)
-#pragma unroll
-                    for (int j = 0; j < G; ++j) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int k = 0; k < G; ++k)
-                            acc += K[k][i] * T[k][j];
-                        out[q * G * G + i * G + j] = acc;
-                    }
-            }
         }
-        __syncthreads();
-        double *dst = grad + c0 * OUT;
-        const int total = cnt * OUT;
-        if (vec_ok && (OUT % 2 == 0)) {
-            for (int p = tid; p < total / 2; p += GATHER_CELLS) {
-                const int e = 2 * p;
-                const int cell = e / OUT, r = e - cell * OUT;
-                st_stream_v2(dst + e, stage[cell * OUTP + r], stage[cell * OUTP + r + 1]);
+        if (bulk)
+            fence_proxy_async_smem();
+        __syncthreads();  // results staged; dofmap / Jinv stage consumed
+        const unsigned long long next = s_next[it];
+        it ^= 1;
+        const bool next_bulk = next < ntiles && is_bulk(next);
+        if (tid == 0) {
+            if (bulk) {
+                bulk_s2g(A.grad + q0 * GG, s_out + buf * TILE * GG, (uint32_t)(sizeof(double) * TILE * GG));
+                bulk_commit();
+                bulk_wait_read_1();  // the store issued one tile ago has left the other buffer
             }
-        } else {
-            for (int e = tid; e < total; e += GATHER_CELLS) {
-                const int cell = e / OUT, r = e - cell * OUT;
-                dst[e] = stage[cell * OUTP + r];
-            }
+            if (next_bulk)
+                issue(next);
         }
-        __syncthreads();
+        if (!bulk)
+            __syncthreads();  // plain-path stage reuse
+        buf ^= bulk ? 1 : 0;
+        tile = next;
+        bulk = next_bulk;
     }
+    if (tid == 0)
+        bulk_wait_read_all();
 }
 
 // Generic fallback for element/quadrature combinations without a compiled
@@ -156,28 +195,30 @@ template <int G, int ND, int NQ>
 static int launch_gather(size_t ncells, const int *dofmap, const double *u, const double *u_prev,
                          const double *dphi, const double *Jinv, double *grad, cudaStream_t st)
 {
-    constexpr int OUT = NQ * G * G;
-    constexpr int OUTP = OUT | 1;
-    constexpr size_t smem = sizeof(double) * (((NQ * ND * G + 1) & ~1) + GATHER_CELLS * OUTP);
+    using Cfg = GatherCfg<G, ND, NQ>;
     auto kern = gather_kernel<G, ND, NQ>;
     static int occ = -1;
     if (occ < 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)Cfg::smem_bytes);
         if (e != cudaSuccess)
             return note_cuda_error(e, "cudaFuncSetAttribute(gather)");
         int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, GATHER_CELLS, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, Cfg::TILE, Cfg::smem_bytes);
         if (e != cudaSuccess)
             return note_cuda_error(e, "cudaOccupancy(gather)");
         occ = o > 0 ? o : 1;
     }
-    const unsigned long long ngroups = (ncells + GATHER_CELLS - 1) / GATHER_CELLS;
-    unsigned long long grid = (unsigned long long)sm_count() * occ;
-    if (grid > ngroups)
-        grid = ngroups;
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(grad) & 15u) == 0;
-    kern<<<(unsigned)grid, GATHER_CELLS, smem, st>>>(dofmap, u, u_prev, dphi, Jinv, grad,
-                                                     (unsigned long long)ncells, vec_ok ? 1 : 0);
+    const unsigned long long ntiles = (ncells + Cfg::CPT - 1) / Cfg::CPT;
+    const int per_sm = tuned_ctas_per_sm() > 0 ? tuned_ctas_per_sm() : occ;
+    unsigned long long grid = (unsigned long long)sm_count() * per_sm;
+    if (grid > ntiles)
+        grid = ntiles;
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    GatherArgs A{dofmap, u, u_prev, dphi, Jinv, grad, (unsigned long long)ncells,
+                 (ntiles > grid) ? tile_ticket(st) : nullptr,
+                 (al16(dofmap) && al16(Jinv) && al16(grad)) ? 1 : 0};
+    kern<<<(unsigned)grid, Cfg::TILE, Cfg::smem_bytes, st>>>(A);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return note_cuda_error(cudaGetLastError(), "gather_kernel launch");
 }

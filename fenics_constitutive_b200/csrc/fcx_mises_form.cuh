@@ -18,6 +18,7 @@
 // form grad_del_u in registers; sigma/eps_n/alpha/tangent leave through shared
 // memory with bulk async stores.
 #pragma once
+#include "fcx_fem.cuh"
 #include "fcx_models.cuh"
 
 namespace fcx {
@@ -98,51 +99,22 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
         // ---- grad_del_u of this thread's QP, in registers (overlaps the loads) ----
         double g[9];
         const bool active = tid < cnt;
-        if (active) {
-            const unsigned long long c = q0 / NQ + tid / NQ;
+        {
+            // idle lanes of the ragged last tile clamp to the last cell (they only take part in
+            // the quad shuffles; nothing of theirs is stored)
+            unsigned long long c = q0 / NQ + tid / NQ;
+            c = c < A.ncells ? c : A.ncells - 1;
             const int q = tid % NQ;
-            double T[3][3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    T[k][j] = 0.0;
-            const int *dm = A.dofmap + c * ND;
-            const double *tab = s_tab + q * ND * 3;
-#pragma unroll
-            for (int a = 0; a < ND; ++a) {
-                const size_t node = (size_t)dm[a];
-                double du[3];
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    double v = A.u[node * 3 + j];
-                    if (A.u_prev != nullptr)
-                        v -= A.u_prev[node * 3 + j];
-                    du[j] = v;
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const double d = tab[a * 3 + k];
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        T[k][j] += d * du[j];  // same summation order as gather_kernel
-                }
-            }
             double K[9];
 #pragma unroll
             for (int i = 0; i < 9; ++i)
                 K[i] = A.Jinv[c * 9 + i];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        acc += K[k * 3 + i] * T[k][j];
-                    g[i * 3 + j] = acc;
-                }
-            if (A.grad_out != nullptr) {
+            // same device functions as gather_kernel: fused == gather + evaluate, bit for bit
+            if (NQ == 4)
+                grad_of_increment_quad<3, ND>(s_tab + q * ND * 3, K, A.dofmap + c * ND, A.u, A.u_prev, active, q, g);
+            else if (active)
+                grad_of_increment<3, ND>(s_tab + q * ND * 3, K, A.dofmap + c * ND, A.u, A.u_prev, g);
+            if (active && A.grad_out != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 9; ++i)
                     A.grad_out[(q0 + tid) * 9 + i] = g[i];

@@ -652,4 +652,299 @@ struct MisesLinModel {
     }
 };
 
+// ===========================================================================
+// comfe-rs Drucker-Prager models behind the generic implicit return mapping
+//   comfe-rs/src/plasticity/general.rs:105-266           (8x8 Newton on [sigma, del_lambda, kappa])
+//   comfe-rs/src/plasticity/drucker_prager_classic.rs:75-108      f = sqrt(J2) + b I1 - a
+//   comfe-rs/src/plasticity/drucker_prager_hyperbolic.rs:64-102   f = sqrt(J2 + d^2) + b I1 - a
+// exported by the reference as DruckerPrager3D / DruckerPragerHyperbolic3D
+// (fc/models/rust_models.py:96-141).  Same segments as MisesLinModel:
+//   0 grad [9] (read)  1 stress [6]  2 history [7] = [alpha, plastic_strain[6]]
+//
+// The reference solves the dense 8x8 system with LU every Newton iteration.
+// For both models that system has closed structure: with s = dev(sigma),
+// c1 = df/dJ2, c2 = d2f/dJ2^2,
+//   dg/dsigma   = c1 P_dev + c2 s s^T                      (:98 / :87)
+//   A := I + dl C dg/dsigma = I + alpha P_dev - beta s s^T,  alpha = 2 mu dl c1, beta = -2 mu dl c2
+//   A^-1 x      = x_vol + x_dev/(1+alpha) + beta (s.x) / ((1+alpha) den) s,   den = 1 + alpha - beta |s|^2
+// (Sherman-Morrison), the del_lambda column is C g = 3 kappa b_flow 1 + 2 mu c1 s and
+// the kappa row/column decouples (df/dkappa = dg/dkappa = dk/dkappa = 0, the
+// struct defaults).  So each Newton step -- THE SAME step, iterate for iterate,
+// stop rule for stop rule (:219-227) -- costs O(6) instead of an 8x8 LU, the
+// consistent tangent inverse(dres)[0:6,0:6] C (:255-262) is
+//   3 kappa P_vol + 2mu/(1+alpha) P_dev + 2 mu gamma s s^T - y2 w^T / (c.y2)
+// and fits a 12-double record (6 coefficients + s) that the CTA expands into
+// the dense [TILE][36] block exactly like the Mises kernels do.
+// Quirk reproduced, not fixed: res_kappa = alpha_1 - alpha_0 - k has no
+// del_lambda factor (:208) while its Jacobian row has (:60-67), so alpha grows
+// by sqrt(2/3)|g| per plastic step.
+// ===========================================================================
+struct DruckerPragerParams {
+    double mu, kappa, a, b, d2, b_flow;
+};
+
+template <bool HYP>
+struct DruckerPragerModel {
+    using Params = DruckerPragerParams;
+    static constexpr int REC = 13;  // 12 used; odd stride -> conflict-free 64-bit smem access
+    static constexpr __host__ __device__ int nseg() { return 3; }
+    static constexpr __host__ __device__ int w(int k) { return k == 0 ? 9 : (k == 1 ? 6 : 7); }
+    static constexpr __host__ __device__ int off(int k) { return k == 0 ? 0 : (k == 1 ? 9 : 15); }
+    static constexpr __host__ __device__ int wsum() { return 22; }
+    static constexpr __host__ __device__ bool wr(int k) { return k >= 1; }
+    static constexpr __host__ __device__ bool soa(int) { return false; }
+    static constexpr __host__ __device__ int sdim() { return 6; }
+    static constexpr __host__ __device__ int const_tangent_qps() { return 0; }
+    static constexpr __host__ __device__ int aux_doubles(int tile) { return REC * tile; }
+    static constexpr __host__ __device__ int min_ctas(int tile) { return 384 / tile; }
+    static constexpr __host__ __device__ bool has_flag() { return true; }
+
+    __device__ static void init_aux(const Params &, double *, int, int) {}
+
+    struct State {
+        double s[6], nsq, f, c1, c2, gn;
+        bool apex;
+    };
+
+    // set_model_state (classic :75-108, hyperbolic :64-102)
+    __device__ static __forceinline__ void state(const Params &P, const double *sg, double bfe, State &S)
+    {
+        const double i_1 = (sg[0] + sg[1]) + sg[2];
+        const double m = i_1 / 3.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            S.s[k] = (k < 3) ? sg[k] + (-m) : sg[k];
+        double nsq = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            nsq += S.s[k] * S.s[k];
+        S.nsq = nsq;
+        const double j_2 = 0.5 * nsq;
+        if (HYP) {
+            const double x = j_2 + P.d2;
+            const double r = sqrt(x);
+            S.apex = false;
+            S.f = r + P.b * i_1 - P.a;
+            S.c1 = 0.5 * (1.0 / r);
+            S.c2 = -0.25 / (x * r);  // -1/4 (J2 + d^2)^(-3/2)
+        } else {
+            const double r = sqrt(j_2);
+            S.apex = !(i_1 < P.a / P.b);  // assert!, :86
+            S.f = r + P.b * i_1 - P.a;
+            S.c1 = 0.5 / r;
+            S.c2 = -0.25 / (j_2 * r);
+        }
+        double gsq = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double gk = ((k < 3) ? bfe : 0.0) + S.c1 * S.s[k];
+            gsq += gk * gk;
+        }
+        S.gn = sqrt(gsq);
+    }
+
+    __device__ static __forceinline__ double norm6(const double *x)
+    {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            acc += x[k] * x[k];
+        return sqrt(acc);
+    }
+
+    template <class V>
+    __device__ static __forceinline__ void qp(const Params &P, const V &v, double *aux, int t,
+                                              bool &plastic, bool &failed)
+    {
+        double g[9], sig0[6], hist[7];
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            g[i] = v.template ld<0>(i);
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            sig0[i] = v.template ld<1>(i);
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            hist[i] = v.template ld<2>(i);
+        const double fr = 0.70710678118654752440;  // f64::consts::FRAC_1_SQRT_2 (mandel.rs:147)
+        const double e[6] = {g[0], g[4], g[8], fr * (g[1] + g[3]), fr * (g[2] + g[6]), fr * (g[5] + g[7])};
+        const double two_mu = 2.0 * P.mu, k3 = 3.0 * P.kappa;
+        const double bfe = (P.b == P.b_flow) ? P.b : P.b_flow;  // associated / non-associated flow
+        const double c23 = sqrt23();
+        // sigma_tr = C de + sigma_0   (general.rs:126)
+        const double etr = (e[0] + e[1]) + e[2];
+        double sol[6], sigtr[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double ev = (k < 3) ? etr / 3.0 : 0.0;
+            sigtr[k] = (two_mu * (e[k] - ev) + k3 * ev) + sig0[k];
+            sol[k] = sigtr[k];
+        }
+        State S;
+        state(P, sigtr, bfe, S);
+        failed = S.apex;
+        plastic = !(S.f <= 0.0);  // :133
+        double *rec = aux + t * REC;
+        rec[0] = P.kappa + two_mu * (2.0 / 3.0);  // elastic tangent 3 kappa P_vol + 2 mu P_dev
+        rec[1] = P.kappa - two_mu / 3.0;          // (also what a failed point reports)
+        rec[2] = two_mu;
+#pragma unroll
+        for (int k = 3; k < 12; ++k)
+            rec[k] = 0.0;
+        if (!plastic || failed) {
+            if (!failed) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+                    v.template st<1>(i, sigtr[i]);
+            }
+            return;
+        }
+        const double alpha_0 = hist[0];
+        double dl = 0.0, al = alpha_0;
+        double rs[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, rf = S.f, rk = 0.0;
+        const double atol = 1e-8, rtol = 1e-8;
+        double opa = 1.0, den = 1.0, beta = 0.0;
+        for (int it = 0;; ++it) {
+            // ---- one Newton step with the matrix of the current iterate (:176-190) ----
+            const double alpha = two_mu * dl * S.c1;
+            beta = -(two_mu * dl * S.c2);
+            opa = 1.0 + alpha;
+            den = opa - beta * S.nsq;
+            const double tr = ((rs[0] + rs[1]) + rs[2]) / 3.0;
+            double sdot = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                sdot += S.s[k] * rs[k];
+            const double cf = beta * sdot / (opa * den);
+            const double h = two_mu * S.c1 / den, q1 = k3 * bfe;
+            double y1[6], y2[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const double vol = (k < 3) ? tr : 0.0;
+                y1[k] = vol + (rs[k] - vol) / opa + cf * S.s[k];
+                y2[k] = ((k < 3) ? q1 : 0.0) + h * S.s[k];
+            }
+            double sy1 = 0.0, sy2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                sy1 += S.s[k] * y1[k];
+                sy2 += S.s[k] * y2[k];
+            }
+            const double cy1 = P.b * ((y1[0] + y1[1]) + y1[2]) + S.c1 * sy1;
+            const double cy2 = P.b * ((y2[0] + y2[1]) + y2[2]) + S.c1 * sy2;
+            const double dlam = (cy1 - rf) / cy2;
+            double dsig[6], sds = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                dsig[k] = y1[k] - y2[k] * dlam;
+                sds += S.s[k] * dsig[k];
+            }
+            const double kk = c23 * S.gn;
+            const double dkc = (c23 / S.gn) * S.c1 * (S.c1 + S.c2 * S.nsq);  // dk/dsigma = dkc s
+            const double dkap = rk + dl * (dkc * sds) + kk * dlam;
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                sol[k] -= dsig[k];
+            dl -= dlam;
+            al -= dkap;
+            // ---- new state and residual (:200-217) ----
+            state(P, sol, bfe, S);
+            if (S.apex || !(cy2 != 0.0)) {
+                failed = true;
+                break;
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const double cg = ((k < 3) ? k3 * bfe : 0.0) + two_mu * S.c1 * S.s[k];
+                rs[k] = sol[k] - sigtr[k] + dl * cg;
+            }
+            rk = al - alpha_0 - c23 * S.gn;
+            rf = S.f;
+            const bool conv_res = norm6(rs) < atol && fabs(rk) < atol && fabs(rf) < atol;
+            const bool conv_inc = norm6(dsig) < atol + rtol * norm6(sol) &&
+                                  fabs(dkap) < atol + rtol * fabs(al) &&
+                                  fabs(dlam) < atol + rtol * fabs(dl);
+            if (conv_res || conv_inc)
+                break;
+            if (it > 25) {  // maxit, :167,:228
+                failed = true;
+                break;
+            }
+        }
+        if (failed)
+            return;  // the Rust code panics; nothing is written for this point
+        // ---- commit: stress, alpha, plastic strain += de - C^-1 (sigma_1 - sigma_0)  (:249-252) ----
+        double x[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            x[k] = sol[k] - sig0[k];
+        const double xv = ((x[0] + x[1]) + x[2]) / 3.0;
+        hist[0] = al;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double vol = (k < 3) ? xv : 0.0;
+            hist[1 + k] += e[k] - ((x[k] - vol) / two_mu + vol / k3);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            v.template st<1>(i, sol[i]);
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            v.template st<2>(i, hist[i]);
+        // ---- consistent tangent at the converged state (:255-262) ----
+        {
+            const double alpha = two_mu * dl * S.c1;
+            beta = -(two_mu * dl * S.c2);
+            opa = 1.0 + alpha;
+            den = opa - beta * S.nsq;
+            const double m1 = two_mu / opa, m2 = two_mu * (beta / (opa * den));
+            const double h = two_mu * S.c1 / den, q1 = k3 * bfe, q2 = k3 * P.b;
+            const double D = P.b * (3.0 * q1) + S.c1 * (h * S.nsq);
+            const double A0 = P.kappa - q1 * q2 / D;
+            rec[0] = A0 + m1 * (2.0 / 3.0);
+            rec[1] = A0 - m1 / 3.0;
+            rec[2] = m1;
+            rec[3] = m2 - h * h / D;
+            rec[4] = -(q1 * h) / D;
+            rec[5] = -(h * q2) / D;
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                rec[6 + k] = S.s[k];
+        }
+    }
+
+    // M_ij = [vol block] + m1 delta_ij + A3 s_i s_j + A4 1_i s_j + A5 s_i 1_j
+    __device__ static __forceinline__ double entry(const double *rec, int i, int j)
+    {
+        const bool vi = i < 3, vj = j < 3, diag = (i == j);
+        const double base = (vi && vj) ? (diag ? rec[0] : rec[1]) : (diag ? rec[2] : 0.0);
+        const double si = rec[6 + i], sj = rec[6 + j];
+        return base + rec[3] * (si * sj) + (vi ? rec[4] * sj : 0.0) + (vj ? rec[5] * si : 0.0);
+    }
+
+    __device__ static __forceinline__ void store_tangent(const Params &, const double *aux,
+                                                         double *tang, int cnt, int tid,
+                                                         int nthreads, bool vec_ok)
+    {
+        if (vec_ok) {
+            const int npairs = cnt * 18;
+            for (int p = tid; p < npairs; p += nthreads) {
+                const int q = p / 18;
+                const int pr = p - q * 18;
+                const int i = pr / 3;
+                const int j = 2 * (pr - 3 * i);
+                const double *rec = aux + q * REC;
+                st_stream_v2(tang + 2 * (size_t)p, entry(rec, i, j), entry(rec, i, j + 1));
+            }
+        } else {
+            for (int p = tid; p < cnt * 36; p += nthreads) {
+                const int q = p / 36;
+                const int ij = p - q * 36;
+                const int i = ij / 6, j = ij - 6 * i;
+                tang[p] = entry(aux + q * REC, i, j);
+            }
+        }
+    }
+};
+
 }  // namespace fcx

@@ -7,7 +7,8 @@ from .interfaces import *  # noqa: F401,F403
 from .interfaces import IncrSmallStrainModel, StressStrainConstraint
 from .linear_elasticity_model import LinearElasticityModel
 from .mises_plasticity_isotropic_hardening import VonMises3D
-from .rust_models import LinearElasticity3D, MisesPlasticityLinearHardening3D
+from .rust_models import (DruckerPrager3D, DruckerPragerHyperbolic3D, LinearElasticity3D,
+                          MisesPlasticityLinearHardening3D)
 from .spring_kelvin_model import SpringKelvinModel
 from .spring_maxwell_model import SpringMaxwellModel
 from .utils import *  # noqa: F401,F403

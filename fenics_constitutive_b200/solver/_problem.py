@@ -212,7 +212,8 @@ class IncrSmallStrainProblem:
         ptr, idx = node_adjacency(self.V.dofmap, self.V.num_nodes)
         self._adj_ptr = torch.as_tensor(ptr, dtype=torch.int64, device=dev)
         self._adj_idx = torch.as_tensor(idx, dtype=torch.int32, device=dev)
-        self._fe = torch.empty(self.num_cells * T.nd * self.gdim, dtype=torch.float64, device=dev)
+        # element vectors [ncells][nd][fs]; 3-D slots are padded to one 32-byte sector (include/fcx.h)
+        self._fe = torch.empty(self.num_cells * T.nd * lib().fcx_fe_stride(self.gdim), dtype=torch.float64, device=dev)
 
         self.stress = IncrementalStress(self.nqp * self.sdim, dev)
         self.tangent = QuadratureFunction(self.nqp * self.sdim**2, dev)

@@ -112,6 +112,19 @@ int fcx_mises_linear_hardening_evaluate(const double *params_host, size_t n,
                                         double *tangent, double *history,
                                         unsigned char *plastic_flag, void *stream);
 
+/* DruckerPrager3D / DruckerPragerHyperbolic3D.evaluate -- the reference's Rust models
+ * comfe-rs/src/plasticity/{general.rs:105-266, drucker_prager_classic.rs:75-108,
+ * drucker_prager_hyperbolic.rs:64-102} behind models/rust_models.py:96-141.
+ * hyperbolic = 0: params = {mu, kappa, a, b, b_flow}; 1: {mu, kappa, a, b, d, b_flow} (HOST).
+ * history: ONE array [n][7] = [alpha, plastic_strain[6]].  plastic_flag: optional u8[n].
+ * status: as for fcx_mises_evaluate -- counts the points where the Rust code would panic
+ * (Newton not converged after 25 iterations, or the classic model's apex assert); such
+ * points are left unchanged. */
+int fcx_drucker_prager_evaluate(int hyperbolic, const double *params_host, size_t n,
+                                const double *grad_del_u, double *stress, double *tangent,
+                                double *history, unsigned char *plastic_flag, int *status,
+                                void *stream);
+
 /* SpringKelvinModel.evaluate -- reference models/spring_kelvin_model.py:43-88.
  * D0 (s*s), I2 (s): HOST pointers to the constants of __init__ (:24-41);
  * mu0, lam0, mu1, tau as built there.  history: strain_visco [n][s], strain [n][s]. */
@@ -180,13 +193,16 @@ int fcx_mises_form(const double *params_host, size_t ncells, int nq, int nd, con
  * dR_form = inner(eps(du), C eps(v)) dx, eps = ufl_mandel_strain,
  * solver/utils.py:10-62).  Affine simplex cells; tables as for fcx_gather_grad
  * plus weights [nq] (reference-cell quadrature weights) and detJ [ncells]
- * (|det dx/dX|).  Each call writes ELEMENT vectors fe [ncells][nd][gdim]:
+ * (|det dx/dX|).  Each call writes ELEMENT vectors fe [ncells][nd][fs] with
+ * fs = fcx_fe_stride(gdim) doubles per (cell, local node) slot (3-D slots are
+ * padded to 4 doubles = one 32-byte sector; the pad entry is written as 0):
  *   fcx_internal_force   fe = sum_q w|J| B_q^T stress_q          (stress [ncells*nq][sdim])
  *   fcx_tangent_apply    fe = sum_q w|J| B_q^T C_q^T B_q p_e     (p [nnodes][gdim], tangent [ncells*nq][sdim][sdim])
  *   fcx_tangent_diag     fe = diagonal of the element matrix
  * fcx_gather_sum then forms out[node][j] = beta*out + alpha * sum over the
  * node's (cell, local index) adjacency (adj_ptr [nnodes+1] int64, adj_idx
  * int32 = cell*nd + a) in a fixed order -- deterministic, no atomics. */
+int fcx_fe_stride(int gdim);
 int fcx_internal_force(int gdim, int sdim, size_t ncells, int nq, int nd, const double *dphi_ref,
                        const double *weights, const double *Jinv, const double *detJ,
                        const double *stress, double *fe, void *stream);
@@ -215,6 +231,10 @@ int fcx_mises_linear_hardening_evaluate_host(const double *params, size_t n,
                                              double *tangent, double *history,
                                              unsigned char *plastic_flag);
 
+int fcx_drucker_prager_evaluate_host(int hyperbolic, const double *params, size_t n,
+                                     const double *grad_del_u, double *stress, double *tangent,
+                                     double *history, unsigned char *plastic_flag);
+
 int fcx_kelvin_evaluate_host(int constraint, const double *D0, const double *I2, double mu0,
                              double lam0, double mu1, double tau, double del_t, size_t n,
                              const double *grad_del_u, double *stress, double *tangent,
@@ -231,7 +251,14 @@ int fcx_maxwell_evaluate_host(int constraint, const double *D0, const double *D1
  * arrays are created). */
 int fcx_host_register(void *ptr, size_t bytes);
 int fcx_host_unregister(void *ptr);
-/* QPs per pipeline chunk of the *_host entry points (default 1<<19); 0 = query. */
+/* Pageable caller arrays (ordinary numpy memory) are staged through pinned ring
+ * slots by a pool of host threads, both ways, overlapped with the DMA (memcpy
+ * only -- no arithmetic on the CPU).  fcx_host_staging(0/1) switches that off/on
+ * (off = let the driver stage; -1 = query), fcx_host_threads(n) sets the pool
+ * size (0 = query; default min(12, cores - 2)).  Both return the old value. */
+int fcx_host_staging(int on);
+int fcx_host_threads(int n);
+/* QPs per pipeline chunk of the *_host entry points (default 1<<18); 0 = query. */
 size_t fcx_host_chunk_qps(size_t new_value);
 /* Release the streams / staging buffers cached by the *_host entry points. */
 void fcx_host_release(void);

@@ -56,6 +56,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_rs_linear_elasticity3d.restype = ci
         L.oracle_rs_mises_linear_hardening.argtypes = [dp, sz, dp, dp, dp, dp, u8p]
         L.oracle_rs_mises_linear_hardening.restype = ci
+        L.oracle_rs_drucker_prager.argtypes = [ci, dp, sz, dp, dp, dp, dp, u8p, ci]
+        L.oracle_rs_drucker_prager.restype = ci
         L.oracle_mises_evaluate.argtypes = [dp, sz, dp, dp, dp, dp, dp, u8p, ci]
         L.oracle_mises_evaluate.restype = ci
         L.oracle_kelvin_evaluate.argtypes = [ci, dp, dp, cd, cd, cd, cd, cd, sz, dp, dp, dp, dp, dp, ci]

@@ -137,6 +137,48 @@ class RustMisesPlasticityLinearHardening3D(_Base):
         )
 
 
+class _RustDruckerPrager(_Base):
+    """comfe-rs IsotropicPlasticityModel3D<DruckerPrager...> (comfe-rs/src/plasticity/general.rs:105-266)."""
+
+    _keys: tuple = ()
+    _hyperbolic = 0
+
+    def __init__(self, parameters):
+        get = lambda k: float(np.asarray(parameters[k]).reshape(-1)[0])  # noqa: E731
+        self.params = np.array([get(k) for k in self._keys], dtype=np.float64)
+        self.constraint = 5
+        self.plastic_flag = None
+        self.nthreads = 1
+
+    @property
+    def history_dim(self):
+        return {"history": 7}
+
+    def evaluate(self, t, del_t, grad_del_u, stress, tangent, history):
+        n = self._check_sizes(grad_del_u, stress, tangent)
+        self.plastic_flag = np.zeros(n, dtype=np.uint8)
+        rc = lib().oracle_rs_drucker_prager(
+            self._hyperbolic, _p(self.params), n, _p(grad_del_u), _p(stress), _p(tangent), _p(history["history"]),
+            self.plastic_flag.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)), int(self.nthreads),
+        )
+        if rc > 0:  # the Rust code panics (general.rs:186,236; drucker_prager_classic.rs:86)
+            raise RuntimeError(f"Plasticity3D: Newton-Raphson did not converge ({rc} point(s))")
+
+
+class RustDruckerPrager3D(_RustDruckerPrager):
+    """drucker_prager_classic.rs:46-166; params mu, kappa, a, b, b_flow."""
+
+    _keys = ("mu", "kappa", "a", "b", "b_flow")
+    _hyperbolic = 0
+
+
+class RustDruckerPragerHyperbolic3D(_RustDruckerPrager):
+    """drucker_prager_hyperbolic.rs:48-164; params mu, kappa, a, b, d, b_flow."""
+
+    _keys = ("mu", "kappa", "a", "b", "d", "b_flow")
+    _hyperbolic = 1
+
+
 class VonMises3D(_Base):
     def __init__(self, param):
         self.constraint = 5

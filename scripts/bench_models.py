@@ -125,6 +125,40 @@ def main():
             report(f"{cls.__name__}_{c.name}", 8 * (g * g + 6 * s + s * s), ms)
             del grad, stress, ev, et, tangent
 
+    # --- comfe-rs models: linear-hardening Mises, Drucker-Prager classic / hyperbolic ---
+    from fenics_constitutive_b200.models import (DruckerPrager3D, DruckerPragerHyperbolic3D,
+                                                 MisesPlasticityLinearHardening3D)
+    import numpy as np
+
+    A = lambda v: np.array([v])  # noqa: E731
+    rs_cases = [
+        ("rs_mises_linear_hardening", MisesPlasticityLinearHardening3D,
+         {"mu": A(80769.0), "kappa": A(175000.0), "y_0": A(1200.0), "h": A(200.0)}, synthetic.MISES_GRAD_STD, None),
+        ("rs_drucker_prager", DruckerPrager3D,
+         {"mu": A(80769.0), "kappa": A(175000.0), "a": A(300.0), "b": A(0.05), "b_flow": A(0.05)}, 1.7e-3, 4e-4),
+        ("rs_drucker_prager_hyperbolic", DruckerPragerHyperbolic3D,
+         {"mu": A(80769.0), "kappa": A(175000.0), "a": A(300.0), "b": A(0.05), "d": A(40.0), "b_flow": A(0.02)},
+         1.7e-3, 4e-4),
+    ]
+    for name, cls, prm, shear, vol in rs_cases:
+        law = cls(prm)
+        law.record_plastic_flag = True
+        grad = rnd(n * 9, shear)
+        if vol is not None:  # deviator-dominated increments (stay away from the apex of the cone)
+            grad.view(n, 9)[:, [0, 4, 8]] = rnd(n * 3, vol).view(n, 3)
+        tangent = torch.empty(n * 36, dtype=torch.float64, device=dev)
+        z = lambda m: torch.zeros(m, dtype=torch.float64, device=dev)  # noqa: E731
+        states = [(z(n * 6), z(n * 7)) for _ in range(K + 3)]
+
+        def step(i):
+            st, hi = states[i]
+            law.evaluate(0.0, 1.0, grad, st, tangent, {"history": hi})
+
+        ms = time_steps(step, K)
+        frac = float(law.plastic_flag.double().mean().item())
+        report(name, 8 * (9 + 6 + 6 + 36 + 7 + 7) + 1, ms, {"plastic_fraction": frac})
+        del states, grad, tangent
+
     # --- companion gather: ~1M P2 tets (BASELINE config 5 mesh size), q_degree 2 ---
     from fenics_constitutive_b200 import gather as G
 

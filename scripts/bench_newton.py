@@ -39,6 +39,9 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--degree", type=int, default=2)
 ap.add_argument("--cg-rtol", type=float, default=1e-8)
 ap.add_argument("--max-disp", type=float, default=0.012)
+ap.add_argument("--newton-steps-only", type=int, default=0,
+                help="if > 0: stop each load step's CG after this many iterations (kernel timing runs)")
+ap.add_argument("--ab", action="store_true", help="also time the element kernels with fem_variant 0")
 args = ap.parse_args()
 
 rank, local_rank, world = env_rank_world()
@@ -70,6 +73,10 @@ solver = S.NewtonSolver(None, problem)
 solver.linear_solver = "cg"
 solver.cg_rtol = args.cg_rtol
 solver.reduce_over_ranks = world > 1
+if args.newton_steps_only > 0:
+    solver.cg_max_it = args.newton_steps_only
+    solver.max_it = 2
+    solver.error_on_nonconvergence = False
 setup_s = time.perf_counter() - t0
 
 
@@ -118,12 +125,24 @@ sxx = float(problem.stress_0.x.array[::6].mean().item())
 # ---- per-kernel timings on the final state ----
 p = torch.randn(V.num_dofs, dtype=torch.float64, device=dev)
 y = torch.empty_like(p)
-ms_form = time_kernel(lambda: orig_form(None))
-ms_F = time_kernel(lambda: problem.F())
-ms_J = time_kernel(lambda: problem.J_apply(p, y))
+from fenics_constitutive_b200._lib import lib  # noqa: E402
+
+ms_form = time_kernel(lambda: orig_form(None), 20)
+ms_F = time_kernel(lambda: problem.F(), 20)
+ms_J = time_kernel(lambda: problem.J_apply(p, y), 20)
+ms_D = time_kernel(lambda: problem.J_diag(y), 20)
+ms_gs = time_kernel(lambda: problem._gather_sum(y), 20)
+ab = None
+if args.ab:
+    lib().fcx_tune(b"fem_variant", 0)
+    ab = {"F": time_kernel(lambda: problem.F(), 20), "J_apply": time_kernel(lambda: problem.J_apply(p, y), 20),
+          "J_diag": time_kernel(lambda: problem.J_diag(y), 20)}
+    lib().fcx_tune(b"fem_variant", 1)
 nqp = problem.nqp
+fs = lib().fcx_fe_stride(3) * 8 * (10 if args.degree == 2 else 4)  # element-vector bytes per cell
 form_bytes = nqp * (104 + 392) + problem.num_cells * (40 + 72)  # state in/out + dofmap + Jinv (nodal values L2-resident)
-J_bytes = nqp * 288 + problem.num_cells * (40 + 72 + 8 + 2 * 240 + 40)
+# tangent + dofmap + Jinv + detJ + element vector written and read once + adjacency index + nodal result
+J_bytes = nqp * 288 + problem.num_cells * (40 + 72 + 8 + 2 * fs + 40) + V.num_dofs * 8
 if rank == 0:
     print(json.dumps({
         "bench": "full Newton solve, stand-in driver (not dolfinx/PETSc)", "n_gpus": world,
@@ -133,7 +152,8 @@ if rank == 0:
         "setup_s": round(setup_s, 2), "solve_s": round(solve_s, 3), "form_calls": form_calls,
         "qp_updates_per_s_whole_solve": world * nqp * form_calls / solve_s,
         "plastic_fraction_final": round(plastic_frac, 4), "mean_sigma_xx": sxx,
-        "kernel_ms": {"form_fused": ms_form, "F": ms_F, "J_apply": ms_J},
+        "kernel_ms": {"form_fused": ms_form, "F": ms_F, "J_apply": ms_J, "J_diag": ms_D, "gather_sum_alone": ms_gs},
+        "kernel_ms_fem_variant0": ab,
         "form_qp_per_s": nqp / (ms_form * 1e-3), "form_GBps": form_bytes / (ms_form * 1e-3) / 1e9,
         "J_apply_GBps": J_bytes / (ms_J * 1e-3) / 1e9,
     }), flush=True)

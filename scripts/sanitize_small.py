@@ -30,5 +30,39 @@ for n in (1, 128, 1000, 5 * 128 * 148 + 77):
         for cls in (SpringKelvinModel, SpringMaxwellModel):
             cls(synthetic.VISCO_PARAMS, cons).evaluate(
                 0.0, 2.0, gr, z(n * sd), tg, {"strain_visco": z(n * sd), "strain": z(n * sd)})
+from fenics_constitutive_b200.models import DruckerPrager3D, DruckerPragerHyperbolic3D  # noqa: E402
+import numpy as _np  # noqa: E402
+
+for cls, extra in ((DruckerPrager3D, {}), (DruckerPragerHyperbolic3D, {"d": _np.array([40.0])})):
+    prm = {"mu": _np.array([80769.0]), "kappa": _np.array([175000.0]), "a": _np.array([300.0]),
+           "b": _np.array([0.05]), "b_flow": _np.array([0.02]), **extra}
+    for n in (1, 1000, 3 * 128 * 148 + 5):
+        gr = torch.randn(n * 9, dtype=torch.float64, device=dev) * 1.7e-3
+        gr.view(n, 9)[:, [0, 4, 8]] *= 0.2
+        z = lambda m: torch.zeros(m, dtype=torch.float64, device=dev)  # noqa: E731
+        cls(prm).evaluate(0.0, 1.0, gr, z(n * 6), z(n * 36), {"history": z(n * 7)})
+
+# FEM kernels (gather, fused form, residual / Jacobian action / diagonal, gather-sum), one CTA
+# per SM so that every CTA walks several tiles (prefetch + ticket paths) and meets a ragged tile
+from fenics_constitutive_b200 import solver as S  # noqa: E402
+from fenics_constitutive_b200._lib import lib  # noqa: E402
+
+lib().fcx_tune(b"ctas_per_sm", 1)
+for mk, degree, qd in ((lambda: S.create_unit_cube(9, 9, 8), 2, 2), (lambda: S.create_unit_cube(13, 12, 11), 1, 1)):
+    V = S.FunctionSpace(mk(), degree)
+    u = S.Function(V)
+    pb = S.IncrSmallStrainProblem(VonMises3D(synthetic.MISES_PARAMS), u, [], qd)
+    u.x.array.copy_(torch.randn(V.num_dofs, dtype=torch.float64, device=dev) * 3e-4)
+    for fused in (True, False):
+        pb.fused = fused
+        pb.form(u.x.array)
+    p = torch.randn(V.num_dofs, dtype=torch.float64, device=dev)
+    for variant in (1, 0):
+        lib().fcx_tune(b"fem_variant", variant)
+        pb.F()
+        pb.J_apply(p)
+        pb.J_diag()
+lib().fcx_tune(b"fem_variant", 1)
+lib().fcx_tune(b"ctas_per_sm", 0)
 torch.cuda.synchronize()
 print("sanitize_small: done")

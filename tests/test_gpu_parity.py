@@ -396,3 +396,57 @@ def test_elastic_16m_linearity():
     assert torch.equal(tg.view(n, 36)[::997], D.reshape(1, 36).expand(len(range(0, n, 997)), 36))
     law.evaluate(0.0, 1.0, grad * 4.0, s2, tg, None)  # power of two: exact scaling
     assert torch.equal(s2, s1 * 4.0)
+
+
+# ------------------------------------------------------------------ host-memory kinds
+
+@pytest.mark.parametrize("kind", ["pageable_staged", "pageable_driver", "pinned", "registered", "mixed"])
+def test_host_path_memory_kinds(kind):
+    """The host entry points give bit-identical results for every kind of caller memory:
+    ordinary (pageable) numpy arrays staged by the library's host-thread pool or by the driver,
+    page-locked arrays, registered arrays, and a mix (per-array decision).  Chunk size lowered
+    so the ring slots wrap many times and the last chunk is ragged."""
+    from fenics_constitutive_b200._lib import lib
+
+    n = 300_007
+    grad, s0, e0, a0 = synthetic.mises_inputs_numpy(n, seed=77)
+    # device-path result as the yardstick
+    d = [dev(grad), dev(s0), torch.empty(n * 36, dtype=torch.float64, device="cuda"), dev(e0), dev(a0)]
+    law = VonMises3D(MISES)
+    law.record_plastic_flag = True
+    law.evaluate(0.0, 1.0, d[0], d[1], d[2], {"eps_n": d[3], "alpha": d[4]})
+    torch.cuda.synchronize()
+    want = [t.cpu().numpy() for t in d[1:]] + [law.plastic_flag.cpu().numpy()]
+
+    L = lib()
+
+    def pinned(a):
+        t = torch.from_numpy(a.copy()).pin_memory()
+        return t, t.numpy()
+
+    keep = []
+    arrs = [grad.copy(), s0.copy(), np.full(n * 36, np.nan), e0.copy(), a0.copy()]
+    if kind == "pinned":
+        for i, a in enumerate(arrs):
+            t, arrs[i] = pinned(a)
+            keep.append(t)
+    elif kind == "mixed":  # tangent and grad pinned, the in/out arrays pageable
+        for i in (0, 2):
+            t, arrs[i] = pinned(arrs[i])
+            keep.append(t)
+    elif kind == "registered":
+        for a in arrs:
+            assert L.fcx_host_register(a.ctypes.data, a.nbytes) == 0
+    old_stage = L.fcx_host_staging(0 if kind == "pageable_driver" else 1)
+    old_chunk = L.fcx_host_chunk_qps(40_000)
+    try:
+        law.evaluate(0.0, 1.0, arrs[0], arrs[1], arrs[2], {"eps_n": arrs[3], "alpha": arrs[4]})
+    finally:
+        L.fcx_host_staging(old_stage)
+        L.fcx_host_chunk_qps(old_chunk)
+        if kind == "registered":
+            for a in arrs:
+                L.fcx_host_unregister(a.ctypes.data)
+    for got, ref in zip(arrs[1:] + [law.plastic_flag], want):
+        assert np.array_equal(got, ref)
+    assert np.array_equal(arrs[0], grad)  # read-only input untouched

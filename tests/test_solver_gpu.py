@@ -81,6 +81,59 @@ def test_residual_and_jacobian_kernels_vs_oracle(name, mk, degree, qd, cons):
     assert np.abs(g - gref).max() <= 1e-13 * np.abs(gref).max()
 
 
+@pytest.mark.parametrize("name,mk,degree,qd,cons", [
+    ("tet_p2_q2", lambda: S.create_unit_cube(10, 9, 8), 2, 2, C.FULL),
+    ("tri_p2_q2", lambda: S.create_unit_square(53, 47), 2, 2, C.PLANE_STRAIN),
+    ("tet_p1_q1", lambda: S.create_unit_cube(13, 12, 11), 1, 1, C.FULL),
+], ids=["tet_p2_q2", "tri_p2_q2", "tet_p1_q1"])
+@pytest.mark.parametrize("ctas_per_sm", [1, 0])
+def test_fem_kernels_many_tiles_per_cta(name, mk, degree, qd, cons, ctas_per_sm):
+    """Persistent-CTA paths of the QP-parallel FEM kernels: with one CTA per SM every CTA walks
+    several tiles (bulk prefetch one tile ahead, atomic tile tickets, ragged last tile).  Both
+    element-kernel variants against the oracle, and against each other."""
+    import torch
+
+    from fenics_constitutive_b200._lib import lib
+
+    mesh = mk()
+    V = S.FunctionSpace(mesh, degree)
+    u = S.Function(V)
+    pb = S.IncrSmallStrainProblem(LinearElasticityModel({"E": E, "nu": NU}, cons), u, [], qd)
+    fem = oracle_for(pb)
+    rng = np.random.default_rng(17)
+    s = cons.stress_strain_dim
+    stress = rng.standard_normal(pb.nqp * s)
+    tangent = rng.standard_normal(pb.nqp * s * s)
+    p = rng.standard_normal(V.num_dofs)
+    uu = rng.standard_normal(V.num_dofs) * 1e-3
+    up = rng.standard_normal(V.num_dofs) * 1e-3
+    pb.stress.current.x.array.copy_(torch.from_numpy(stress))
+    pb.tangent.x.array.copy_(torch.from_numpy(tangent))
+    u.x.array.copy_(torch.from_numpy(uu))
+    pb.incr_disp.previous.x.array.copy_(torch.from_numpy(up))
+    pd = torch.from_numpy(p).to(pb.device)
+    L = lib()
+    old = L.fcx_tune(b"ctas_per_sm", ctas_per_sm)
+    try:
+        got = {}
+        for variant in (1, 0):
+            L.fcx_tune(b"fem_variant", variant)
+            got[variant] = (np_(pb.F()).copy(), np_(pb.J_apply(pd)).copy(), np_(pb.J_diag()).copy())
+        ctx = pb._law_on_submeshs[0]
+        pb.incr_disp.evaluate_local_incremental_gradient(ctx.gather_op, ctx.displacement_gradient_fn)
+        g = np_(ctx.displacement_gradient_fn.x.array)
+    finally:
+        L.fcx_tune(b"fem_variant", 1)
+        L.fcx_tune(b"ctas_per_sm", old)
+    K = fem.tangent_matrix(tangent)
+    refs = (fem.internal_force(stress), K @ p, K.diagonal())
+    for variant in (1, 0):
+        for x, r in zip(got[variant], refs):
+            assert np.abs(x - r).max() <= 1e-12 * np.abs(r).max(), f"variant {variant}"
+    gref = fem.grad(uu, up)
+    assert np.abs(g - gref).max() <= 1e-13 * np.abs(gref).max()
+
+
 @pytest.mark.parametrize("degree,qd,n,scale", [(2, 2, (5, 4, 3), 2e-4), (1, 1, (6, 5, 5), 4e-4), (1, 2, (3, 3, 3), 7e-4)])
 def test_fused_form_equals_unfused_and_oracle(degree, qd, n, scale):
     """fcx_mises_form == gather + trial reset + evaluate, bit for bit, and both match the oracle.
