@@ -356,11 +356,7 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
             for (int i = 0; i < G * G; ++i)
                 K[i] = s_jinv[lc * (G * G) + i];
             wdet = s_wq[q] * s_det[lc];
-            if (MODE == 1 && NQ == 4 && Cfg::SHFL) {  // Mandel strain of nabla_grad(p) at this QP
-                double g[G * G];
-                grad_of_increment_quad<G, ND>(s_tab + q * ND * G, K, s_dof + lc * ND, A.p, nullptr, active, q, g);
-                mandel_strain<S, G>(g, e);
-            } else if (MODE == 1 && active) {
+            if (MODE == 1 && active) {  // Mandel strain of nabla_grad(p) at this QP
                 double g[G * G];
                 grad_of_increment<G, ND>(s_tab + q * ND * G, K, s_dof + lc * ND, A.p, nullptr, g);
                 mandel_strain<S, G>(g, e);

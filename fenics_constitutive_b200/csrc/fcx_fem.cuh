@@ -71,9 +71,10 @@ __device__ __forceinline__ void grad_at_qp(const double *tabq, const double *K, 
 // G = 3: the 24-byte record is 8-byte aligned only, but one of its two halves is
 // always 16-byte aligned -- even nodes load (x, y) as a pair and z alone, odd
 // nodes x alone and (y, z) as a pair: two load instructions instead of three,
-// branch-free (the kernels' L1 request rate is what bounds the gathers; measured
-// alternatives -- one fetch per (cell, node) staged through shared memory -- were
-// slower, profiles/r1m).
+// branch-free.  Measured alternatives to every QP thread of a cell issuing its own
+// (L1-hitting) loads were SLOWER on B200: one fetch per (cell, node) staged through
+// shared memory (+27 % on the fused form() kernel, profiles/r1m) and a 4-lane
+// split of the fetches exchanged with shuffles (+23 %, profiles/r1o).
 template <int G>
 __device__ __forceinline__ void load_node(const double *__restrict__ base, size_t node, double *v)
 {
@@ -113,49 +114,6 @@ __device__ __forceinline__ void grad_of_increment(const double *tabq, const doub
             g);
     else
         grad_at_qp<G, ND>(tabq, K, [&](int a, double *v) { load_node<G>(u, (size_t)dm[a], v); }, g);
-}
-
-// NQ = 4: the four QP threads of a cell are four consecutive lanes (a "quad") and
-// all need the same ND nodal increments.  Instead of every lane loading all of
-// them (4x the L1 requests -- the measured bound of these kernels, profiles/r1n),
-// lane q fetches nodes q, q+4, q+8, ... and the quad exchanges them with shuffles.
-// Same values, same arithmetic as grad_of_increment.  EVERY lane of the warp must
-// call this (idle quads of a ragged tile pass valid = false and load nothing).
-template <int G, int ND>
-__device__ __forceinline__ void grad_of_increment_quad(const double *tabq, const double *K,
-                                                       const int *dm, const double *__restrict__ u,
-                                                       const double *__restrict__ u_prev, bool valid,
-                                                       int q, double *g)
-{
-    constexpr int NM = (ND + 3) / 4;  // nodes fetched per lane
-    double mine[NM][G];
-#pragma unroll
-    for (int m = 0; m < NM; ++m) {
-        const int a = q + 4 * m;
-#pragma unroll
-        for (int j = 0; j < G; ++j)
-            mine[m][j] = 0.0;
-        if (valid && a < ND) {
-            const size_t node = (size_t)dm[a];
-            load_node<G>(u, node, mine[m]);
-            if (u_prev != nullptr) {
-                double w[G];
-                load_node<G>(u_prev, node, w);
-#pragma unroll
-                for (int j = 0; j < G; ++j)
-                    mine[m][j] -= w[j];
-            }
-        }
-    }
-    const int quad_base = (threadIdx.x & 31) & ~3;
-    grad_at_qp<G, ND>(
-        tabq, K,
-        [&](int a, double *v) {
-#pragma unroll
-            for (int j = 0; j < G; ++j)
-                v[j] = __shfl_sync(0xffffffffu, mine[a >> 2][j], quad_base + (a & 3));
-        },
-        g);
 }
 
 // physical basis gradient of local function a at a QP:  gphi[i] = sum_k K[k][i] * dref[k]

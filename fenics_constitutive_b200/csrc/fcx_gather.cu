@@ -111,11 +111,8 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
 #pragma unroll
             for (int i = 0; i < GG; ++i)
                 K[i] = s_jinv[lc * GG + i];  // (idle lanes: in-bounds stage garbage, never stored)
-            if (NQ == 4) {
-                grad_of_increment_quad<G, ND>(s_tab + q * ND * G, K, s_dof + lc * ND, A.u, A.u_prev, active, q, g);
-            } else if (active) {
+            if (active)
                 grad_of_increment<G, ND>(s_tab + q * ND * G, K, s_dof + lc * ND, A.u, A.u_prev, g);
-            }
             if (active) {
                 if (bulk) {
                     double *o = s_out + (buf * TILE + tid) * GG;

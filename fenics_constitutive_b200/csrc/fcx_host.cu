@@ -224,7 +224,7 @@ static int ensure_pin(size_t need)
     }
     g_ctx.pin_cap = 0;
     for (int s = 0; s < NSLOT; ++s) {
-        cudaError_t e = cudaHostAlloc((void **)&g_ctx.pin[s], need, cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc((void **)&g_ctx.pin[s], need, cudaHostAllocMapped);
         if (e != cudaSuccess)
             return note_cuda_error(e, "cudaHostAlloc(ring slot)");
     }
@@ -232,11 +232,24 @@ static int ensure_pin(size_t need)
     return FCX_OK;
 }
 
-// Pipeline for callers with pageable arrays: host threads stage chunks through
-// pinned ring slots on both sides of the DMA (see the header comment).
+// Optional "packed wire" for the download side of a model (see MisesWire below): the
+// outputs it covers leave the GPU as a compact stream written by a pack kernel straight
+// into the pinned ring slot (zero-copy stores over PCIe) and are expanded into the
+// caller's arrays by the host-thread pool -- data movement only, no arithmetic.
+struct Packer {
+    size_t dev_bytes = 0;   // device scratch per slot
+    size_t wire_bytes = 0;  // pinned bytes per slot
+    // enqueue the pack kernels of one chunk after the model kernel
+    std::function<int(void **dev, void *scratch, void *wire, size_t cnt, cudaStream_t st)> enqueue;
+    // expand chunk [q0, q0 + cnt) from the wire into the caller's arrays (tasks on the pool)
+    std::function<void(size_t q0, size_t cnt, const void *wire, Group &g)> expand;
+};
+
+// Pipeline for callers with pageable arrays and/or a packed wire: host threads stage
+// chunks through pinned ring slots on both sides of the DMA (see the header comment).
 template <class Launch>
 static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageable, size_t n,
-                               Launch &&launch)
+                               Launch &&launch, const Packer *packer = nullptr)
 {
     size_t chunk = g_chunk_staged < g_chunk ? g_chunk_staged : g_chunk;  // fcx_host_chunk_qps caps both
     chunk = chunk < n ? chunk : n;
@@ -254,6 +267,13 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
             pin_out[a] = pin_total;
             pin_total += round256(arr[a].bpq * chunk);
         }
+    }
+    size_t scratch_off = 0, wire_off = 0;
+    if (packer) {
+        scratch_off = total;
+        total += round256(packer->dev_bytes);
+        wire_off = pin_total;
+        pin_total += round256(packer->wire_bytes);
     }
     int rc = ensure_ctx(total);
     if (rc != FCX_OK)
@@ -300,6 +320,8 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
                     if (arr[a].dst && pageable[a])
                         parallel_copy((char *)arr[a].dst + it.q0 * arr[a].bpq,
                                       g_ctx.pin[it.slot] + pin_out[a], it.cnt * arr[a].bpq, g);
+                if (packer)
+                    packer->expand(it.q0, it.cnt, g_ctx.pin[it.slot] + wire_off, g);
                 g.wait();
             }
             {
@@ -340,6 +362,8 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
         }
         if (rc == FCX_OK)
             rc = launch(dev, cnt, st, g_ctx.status);
+        if (rc == FCX_OK && packer)
+            rc = packer->enqueue(dev, g_ctx.buf[slot] + scratch_off, g_ctx.pin[slot] + wire_off, cnt, st);
         for (int a = 0; a < narr && rc == FCX_OK; ++a) {
             if (arr[a].dst) {
                 void *dst = pageable[a] ? (void *)(g_ctx.pin[slot] + pin_out[a])
@@ -384,21 +408,176 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
     return status[0] > 0 ? status[0] : FCX_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// Packed download wire of VonMises3D (fcx_mises_evaluate_host).
+//
+// 288 of the 392 bytes a Mises point sends back are its 6x6 tangent, and the
+// host-array path is bound by the PCIe link (49 GB/s each way on this pool,
+// profiles/r1j_pcie_probe.log).  But the tangent is bitwise symmetric
+// (ka*xioi + cpp*xpp + cnn*outer(xn, xn): products commute) and an ELASTIC point
+// has the same tangent as every other elastic point and leaves eps_n / alpha
+// untouched.  So per chunk the GPU sends
+//     stress (all points, plain DMA), one flag byte per point, and for the plastic
+//     points only a 28-double record [21 upper-triangle entries, eps_n[6], alpha],
+// compacted in point order (exclusive scan of the flags), written by the pack
+// kernel straight into the pinned ring slot; host threads mirror the triangle /
+// copy the constant elastic tangent (computed once on the GPU) into the caller's
+// arrays.  104 + 1 + 224 p bytes per point instead of 392 (p = plastic fraction).
+// Data movement only: every double the caller sees was computed on the GPU.
+// ---------------------------------------------------------------------------
+constexpr int WIRE_REC = 28;
+
+// pos[q] = number of plastic points before q in the chunk; *count = total.  One CTA.
+__global__ void __launch_bounds__(1024)
+    wire_scan_kernel(const unsigned char *__restrict__ flag, unsigned cnt, unsigned *__restrict__ pos,
+                     unsigned *__restrict__ count_out)
+{
+    __shared__ unsigned warp_sum[32];
+    __shared__ unsigned carry;
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned per = (cnt + 1023) / 1024;
+    const unsigned b = tid * per, e = (b + per < cnt) ? b + per : cnt;
+    unsigned mine = 0;
+    for (unsigned q = b; q < e; ++q)
+        mine += flag[q];
+    unsigned incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (unsigned)d)
+            incl += t;
+    }
+    if (lane == 31)
+        warp_sum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned w = warp_sum[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= (unsigned)d)
+                wi += t;
+        }
+        warp_sum[lane] = wi - w;  // exclusive
+        if (lane == 31)
+            carry = wi;
+    }
+    __syncthreads();
+    unsigned run = warp_sum[wid] + incl - mine;
+    for (unsigned q = b; q < e; ++q) {
+        pos[q] = run;
+        run += flag[q];
+    }
+    if (tid == 0)
+        *count_out = carry;
+}
+
+// rec[pos[q]] = [upper triangle of tangent[q] (row-major, i <= j), eps_n[q], alpha[q]] for plastic q
+__global__ void wire_pack_kernel(const unsigned char *__restrict__ flag, const unsigned *__restrict__ pos,
+                                 const double *__restrict__ tangent, const double *__restrict__ eps,
+                                 const double *__restrict__ alpha, unsigned cnt, double *__restrict__ rec)
+{
+    // k -> offset of the k-th upper-triangle entry in the row-major 6x6
+    const int tri[21] = {0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 14, 15, 16, 17, 21, 22, 23, 28, 29, 35};
+    const unsigned long long total = (unsigned long long)cnt * WIRE_REC;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const unsigned q = (unsigned)(i / WIRE_REC);
+        const int k = (int)(i - (unsigned long long)q * WIRE_REC);
+        if (!flag[q])
+            continue;
+        double v;
+        if (k < 21)
+            v = tangent[(size_t)q * 36 + tri[k]];
+        else if (k < 27)
+            v = eps[(size_t)q * 6 + (k - 21)];
+        else
+            v = alpha[q];
+        rec[(size_t)pos[q] * WIRE_REC + k] = v;
+    }
+}
+
+struct MisesWire {
+    // caller arrays
+    double *tangent, *eps, *alpha;
+    unsigned char *user_flag;  // or nullptr
+    double tmpl[36];           // elastic tangent, computed on the GPU
+    size_t chunk;
+    // wire layout inside the pinned slot
+    size_t off_count() const { return 0; }
+    size_t off_flag() const { return 256; }
+    size_t off_rec() const { return 256 + round256(chunk); }
+    size_t wire_bytes() const { return off_rec() + chunk * WIRE_REC * sizeof(double); }
+    size_t dev_bytes() const { return chunk * sizeof(unsigned); }
+};
+
+static void mises_wire_expand(const MisesWire &W, size_t q0, size_t cnt, const void *wire, Group &g)
+{
+    const char *base = (const char *)wire;
+    const unsigned char *flag = (const unsigned char *)(base + W.off_flag());
+    const double *rec = (const double *)(base + W.off_rec());
+    Pool &pool = Pool::get();
+    const int nt = pool_threads();
+    pool.ensure(nt);
+    size_t parts = cnt / 2048;
+    if (parts < 1)
+        parts = 1;
+    if (parts > (size_t)nt)
+        parts = nt;
+    const size_t per = (cnt + parts - 1) / parts;
+    size_t r = 0;  // records before the part
+    for (size_t a = 0; a < cnt; a += per) {
+        const size_t b = a + per < cnt ? a + per : cnt;
+        const size_t r0 = r;
+        for (size_t q = a; q < b; ++q)
+            r += flag[q];
+        g.add();
+        pool.submit([=, &W, &g] {
+            size_t rr = r0;
+            for (size_t q = a; q < b; ++q) {
+                double *T = W.tangent + (q0 + q) * 36;
+                if (flag[q]) {
+                    const double *R = rec + rr * WIRE_REC;
+                    int k = 0;
+                    for (int i = 0; i < 6; ++i)
+                        for (int j = i; j < 6; ++j, ++k) {
+                            T[i * 6 + j] = R[k];
+                            T[j * 6 + i] = R[k];
+                        }
+                    memcpy(W.eps + (q0 + q) * 6, R + 21, 6 * sizeof(double));
+                    W.alpha[q0 + q] = R[27];
+                    ++rr;
+                } else {
+                    memcpy(T, W.tmpl, sizeof W.tmpl);
+                }
+            }
+            if (W.user_flag)
+                memcpy(W.user_flag + q0 + a, flag + a, b - a);
+            g.done();
+        });
+    }
+}
+
+static int g_wire = 1;  // packed download wire for the Mises host path
+
 // launch(dev_ptrs, q_count, stream, status_dev) enqueues the kernel for one chunk.
 template <class Launch>
-static int run_pipeline(const HostArr *arr, int narr, size_t n, Launch &&launch)
+static int run_pipeline(const HostArr *arr, int narr, size_t n, Launch &&launch,
+                        const Packer *packer = nullptr)
 {
     if (n == 0)
         return FCX_OK;
     std::lock_guard<std::mutex> lock(g_mu);
-    if (g_staging && n >= 4096) {  // tiny calls: the driver's own staging is as good
+    if ((g_staging || packer) && n >= 4096) {  // tiny calls: the driver's own staging is as good
         bool pageable[MAXARR], any = false;
         for (int a = 0; a < narr; ++a) {
-            pageable[a] = is_pageable(arr[a].src ? arr[a].src : arr[a].dst);
+            const void *p = arr[a].src ? arr[a].src : arr[a].dst;
+            pageable[a] = g_staging && p != nullptr && is_pageable(p);
             any = any || pageable[a];
         }
-        if (any)
-            return run_pipeline_staged(arr, narr, pageable, n, launch);
+        if (any || packer)
+            return run_pipeline_staged(arr, narr, pageable, n, launch, packer);
     }
     size_t chunk = g_chunk < n ? g_chunk : n;
     chunk = (chunk + 127) & ~(size_t)127;  // whole tiles
@@ -475,6 +654,14 @@ int fcx_host_staging(int on)
     return old;
 }
 
+int fcx_host_wire(int on)
+{
+    const int old = g_wire;
+    if (on >= 0)
+        g_wire = on ? 1 : 0;
+    return old;
+}
+
 int fcx_host_threads(int n)
 {
     const int old = pool_threads();
@@ -548,6 +735,82 @@ int fcx_mises_evaluate_host(const double *params, size_t n, const double *grad, 
     if (!params || !grad || !stress || !tangent || !eps_n || !alpha)
         return FCX_ERR_NULL;
     const size_t d = sizeof(double);
+    if (g_wire && n >= 4096) {
+        // elastic tangent as the kernel produces it: one virgin point with a zero increment
+        // (elastic whenever y0 > 0; otherwise fall through to the plain path)
+        MisesWire W{};
+        {
+            std::lock_guard<std::mutex> lock(g_mu);
+            int rc = ensure_ctx(4096);
+            if (rc != FCX_OK)
+                return rc;
+            double *z = (double *)g_ctx.buf[0];
+            cudaStream_t st = g_ctx.stream[0];
+            cudaError_t e = cudaMemsetAsync(z, 0, (9 + 6 + 36 + 6 + 1) * d + 8, st);
+            if (e != cudaSuccess)
+                return note_cuda_error(e, "cudaMemsetAsync(template)");
+            unsigned char *fl = (unsigned char *)(z + 58);
+            rc = fcx_mises_evaluate(params, 1, z, z + 9, z + 15, z + 51, z + 57, FCX_LAYOUT_AOS, fl, nullptr, st);
+            if (rc != FCX_OK)
+                return rc;
+            double host[59];
+            e = cudaMemcpyAsync(host, z, sizeof host, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess)
+                e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess)
+                return note_cuda_error(e, "template download");
+            unsigned char f0;
+            memcpy(&f0, &host[58], 1);
+            memcpy(W.tmpl, host + 15, sizeof W.tmpl);
+            if (f0 != 0)
+                W.chunk = 0;  // degenerate parameters: the zero state yields
+            else
+                W.chunk = 1;
+        }
+        if (W.chunk != 0) {
+            size_t chunk = g_chunk_staged < g_chunk ? g_chunk_staged : g_chunk;
+            chunk = chunk < n ? chunk : n;
+            chunk = (chunk + 127) & ~(size_t)127;
+            W.chunk = chunk;
+            W.tangent = tangent;
+            W.eps = eps_n;
+            W.alpha = alpha;
+            W.user_flag = plastic_flag;
+            Packer P;
+            P.dev_bytes = W.dev_bytes();
+            P.wire_bytes = W.wire_bytes();
+            P.enqueue = [&W](void **dev, void *scratch, void *wire, size_t cnt, cudaStream_t st) {
+                char *wb = (char *)wire;
+                unsigned *pos = (unsigned *)scratch;
+                const unsigned char *fl = (const unsigned char *)dev[5];
+                wire_scan_kernel<<<1, 1024, 0, st>>>(fl, (unsigned)cnt, pos, (unsigned *)(wb + W.off_count()));
+                unsigned long long work = (unsigned long long)cnt * WIRE_REC;
+                unsigned grid = (unsigned)((work + 255) / 256);
+                const unsigned cap = (unsigned)sm_count() * 8;
+                if (grid > cap)
+                    grid = cap;
+                wire_pack_kernel<<<grid, 256, 0, st>>>(fl, pos, (const double *)dev[2], (const double *)dev[3],
+                                                       (const double *)dev[4], (unsigned)cnt,
+                                                       (double *)(wb + W.off_rec()));
+                g_launches.fetch_add(2, std::memory_order_relaxed);
+                cudaError_t e = cudaGetLastError();
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(wb + W.off_flag(), fl, cnt, cudaMemcpyDeviceToHost, st);
+                return note_cuda_error(e, "mises wire pack");
+            };
+            P.expand = [&W](size_t q0, size_t cnt, const void *wire, Group &g) {
+                mises_wire_expand(W, q0, cnt, wire, g);
+            };
+            // tangent, eps_n, alpha, flag: uploaded / kept on the device as before, downloaded by the wire
+            const HostArr arr[6] = {{grad, nullptr, d * 9}, {stress, stress, d * 6}, {nullptr, nullptr, d * 36},
+                                    {eps_n, nullptr, d * 6}, {alpha, nullptr, d},    {nullptr, nullptr, 1}};
+            return run_pipeline(arr, 6, n, [&](void **dev, size_t cnt, cudaStream_t st, int *status) {
+                return fcx_mises_evaluate(params, cnt, (const double *)dev[0], (double *)dev[1],
+                                          (double *)dev[2], (double *)dev[3], (double *)dev[4],
+                                          FCX_LAYOUT_AOS, (unsigned char *)dev[5], status, st);
+            }, &P);
+        }
+    }
     const HostArr arr[6] = {{grad, nullptr, d * 9}, {stress, stress, d * 6},
                             {nullptr, tangent, d * 36}, {eps_n, eps_n, d * 6},
                             {alpha, alpha, d}, {nullptr, plastic_flag, 1}};

@@ -100,8 +100,7 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
         double g[9];
         const bool active = tid < cnt;
         {
-            // idle lanes of the ragged last tile clamp to the last cell (they only take part in
-            // the quad shuffles; nothing of theirs is stored)
+            // idle lanes of the ragged last tile clamp to the last cell; nothing of theirs is stored
             unsigned long long c = q0 / NQ + tid / NQ;
             c = c < A.ncells ? c : A.ncells - 1;
             const int q = tid % NQ;
@@ -110,9 +109,7 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
             for (int i = 0; i < 9; ++i)
                 K[i] = A.Jinv[c * 9 + i];
             // same device functions as gather_kernel: fused == gather + evaluate, bit for bit
-            if (NQ == 4)
-                grad_of_increment_quad<3, ND>(s_tab + q * ND * 3, K, A.dofmap + c * ND, A.u, A.u_prev, active, q, g);
-            else if (active)
+            if (active)
                 grad_of_increment<3, ND>(s_tab + q * ND * 3, K, A.dofmap + c * ND, A.u, A.u_prev, g);
             if (active && A.grad_out != nullptr) {
 #pragma unroll

@@ -258,6 +258,12 @@ int fcx_host_unregister(void *ptr);
  * size (0 = query; default min(12, cores - 2)).  Both return the old value. */
 int fcx_host_staging(int on);
 int fcx_host_threads(int n);
+/* fcx_mises_evaluate_host sends its results over a packed wire (stress for every point, a flag
+ * byte, and for PLASTIC points only the 21 upper-triangle tangent entries + eps_n + alpha; the
+ * host threads mirror the triangle and copy the constant elastic tangent -- bit-identical
+ * arrays, 104 + 1 + 224 p bytes per point over PCIe instead of 392).  0 = plain D2H of every
+ * array, -1 = query; returns the old value. */
+int fcx_host_wire(int on);
 /* QPs per pipeline chunk of the *_host entry points (default 1<<18); 0 = query. */
 size_t fcx_host_chunk_qps(size_t new_value);
 /* Release the streams / staging buffers cached by the *_host entry points. */

@@ -400,12 +400,15 @@ def test_elastic_16m_linearity():
 
 # ------------------------------------------------------------------ host-memory kinds
 
+@pytest.mark.parametrize("wire", [1, 0], ids=["packed_wire", "plain_d2h"])
 @pytest.mark.parametrize("kind", ["pageable_staged", "pageable_driver", "pinned", "registered", "mixed"])
-def test_host_path_memory_kinds(kind):
+def test_host_path_memory_kinds(kind, wire):
     """The host entry points give bit-identical results for every kind of caller memory:
     ordinary (pageable) numpy arrays staged by the library's host-thread pool or by the driver,
     page-locked arrays, registered arrays, and a mix (per-array decision).  Chunk size lowered
-    so the ring slots wrap many times and the last chunk is ragged."""
+    so the ring slots wrap many times and the last chunk is ragged.  With and without the packed
+    download wire (plastic points only: upper triangle + eps_n + alpha; elastic tangents filled on
+    the host from the GPU-computed constant)."""
     from fenics_constitutive_b200._lib import lib
 
     n = 300_007
@@ -439,11 +442,13 @@ def test_host_path_memory_kinds(kind):
             assert L.fcx_host_register(a.ctypes.data, a.nbytes) == 0
     old_stage = L.fcx_host_staging(0 if kind == "pageable_driver" else 1)
     old_chunk = L.fcx_host_chunk_qps(40_000)
+    old_wire = L.fcx_host_wire(wire)
     try:
         law.evaluate(0.0, 1.0, arrs[0], arrs[1], arrs[2], {"eps_n": arrs[3], "alpha": arrs[4]})
     finally:
         L.fcx_host_staging(old_stage)
         L.fcx_host_chunk_qps(old_chunk)
+        L.fcx_host_wire(old_wire)
         if kind == "registered":
             for a in arrs:
                 L.fcx_host_unregister(a.ctypes.data)
