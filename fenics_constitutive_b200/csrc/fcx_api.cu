@@ -605,6 +605,7 @@ int fcx_drucker_prager_evaluate(int hyperbolic, const double *params, size_t n, 
     P.b = params[3];
     P.d2 = hyperbolic ? params[4] * params[4] : 0.0;  // d.powi(2)
     P.b_flow = hyperbolic ? params[5] : params[4];
+    P.apex = P.a / P.b;
     SegPtrs<3> io{{const_cast<double *>(grad), stress, history}};
     const bool al = aligned16(grad) && aligned16(stress) && aligned16(tangent) && aligned16(history);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

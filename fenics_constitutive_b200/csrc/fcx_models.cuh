@@ -681,6 +681,7 @@ struct MisesLinModel {
 // ===========================================================================
 struct DruckerPragerParams {
     double mu, kappa, a, b, d2, b_flow;
+    double apex;  // a / b
 };
 
 template <bool HYP>
@@ -720,20 +721,13 @@ struct DruckerPragerModel {
             nsq += S.s[k] * S.s[k];
         S.nsq = nsq;
         const double j_2 = 0.5 * nsq;
-        if (HYP) {
-            const double x = j_2 + P.d2;
-            const double r = sqrt(x);
-            S.apex = false;
-            S.f = r + P.b * i_1 - P.a;
-            S.c1 = 0.5 * (1.0 / r);
-            S.c2 = -0.25 / (x * r);  // -1/4 (J2 + d^2)^(-3/2)
-        } else {
-            const double r = sqrt(j_2);
-            S.apex = !(i_1 < P.a / P.b);  // assert!, :86
-            S.f = r + P.b * i_1 - P.a;
-            S.c1 = 0.5 / r;
-            S.c2 = -0.25 / (j_2 * r);
-        }
+        // one division per state: c1 = 1/(2r), c2 = -1/(4 r^3) with r = sqrt(J2 [+ d^2])
+        const double r = sqrt(HYP ? j_2 + P.d2 : j_2);
+        const double inv_r = 1.0 / r;
+        S.apex = HYP ? false : !(i_1 < P.apex);  // assert!(i_1 < a/b), classic :86
+        S.f = r + P.b * i_1 - P.a;
+        S.c1 = 0.5 * inv_r;
+        S.c2 = -0.25 * (inv_r * inv_r) * inv_r;
         double gsq = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
@@ -743,13 +737,13 @@ struct DruckerPragerModel {
         S.gn = sqrt(gsq);
     }
 
-    __device__ static __forceinline__ double norm6(const double *x)
+    __device__ static __forceinline__ double normsq6(const double *x)
     {
         double acc = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; ++k)
-            acc += x[k] * x[k];
-        return sqrt(acc);
+            acc = fma(x[k], x[k], acc);
+        return acc;
     }
 
     template <class V>
@@ -810,25 +804,26 @@ struct DruckerPragerModel {
             beta = -(two_mu * dl * S.c2);
             opa = 1.0 + alpha;
             den = opa - beta * S.nsq;
-            const double tr = ((rs[0] + rs[1]) + rs[2]) / 3.0;
+            const double tr = ((rs[0] + rs[1]) + rs[2]) * (1.0 / 3.0);
             double sdot = 0.0;
 #pragma unroll
             for (int k = 0; k < 6; ++k)
-                sdot += S.s[k] * rs[k];
-            const double cf = beta * sdot / (opa * den);
-            const double h = two_mu * S.c1 / den, q1 = k3 * bfe;
+                sdot = fma(S.s[k], rs[k], sdot);
+            const double inv_opa = 1.0 / opa, inv_den = 1.0 / den;
+            const double cf = beta * sdot * (inv_opa * inv_den);
+            const double h = two_mu * S.c1 * inv_den, q1 = k3 * bfe;
             double y1[6], y2[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 const double vol = (k < 3) ? tr : 0.0;
-                y1[k] = vol + (rs[k] - vol) / opa + cf * S.s[k];
-                y2[k] = ((k < 3) ? q1 : 0.0) + h * S.s[k];
+                y1[k] = fma(cf, S.s[k], fma(rs[k] - vol, inv_opa, vol));
+                y2[k] = fma(h, S.s[k], (k < 3) ? q1 : 0.0);
             }
             double sy1 = 0.0, sy2 = 0.0;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                sy1 += S.s[k] * y1[k];
-                sy2 += S.s[k] * y2[k];
+                sy1 = fma(S.s[k], y1[k], sy1);
+                sy2 = fma(S.s[k], y2[k], sy2);
             }
             const double cy1 = P.b * ((y1[0] + y1[1]) + y1[2]) + S.c1 * sy1;
             const double cy2 = P.b * ((y2[0] + y2[1]) + y2[2]) + S.c1 * sy2;
@@ -836,8 +831,8 @@ struct DruckerPragerModel {
             double dsig[6], sds = 0.0;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                dsig[k] = y1[k] - y2[k] * dlam;
-                sds += S.s[k] * dsig[k];
+                dsig[k] = fma(-y2[k], dlam, y1[k]);
+                sds = fma(S.s[k], dsig[k], sds);
             }
             const double kk = c23 * S.gn;
             const double dkc = (c23 / S.gn) * S.c1 * (S.c1 + S.c2 * S.nsq);  // dk/dsigma = dkc s
@@ -860,8 +855,10 @@ struct DruckerPragerModel {
             }
             rk = al - alpha_0 - c23 * S.gn;
             rf = S.f;
-            const bool conv_res = norm6(rs) < atol && fabs(rk) < atol && fabs(rf) < atol;
-            const bool conv_inc = norm6(dsig) < atol + rtol * norm6(sol) &&
+            // |x| < t  <=>  x.x < t^2 for t > 0: two of the three square roots go
+            const bool conv_res = normsq6(rs) < atol * atol && fabs(rk) < atol && fabs(rf) < atol;
+            const double tinc = atol + rtol * sqrt(normsq6(sol));
+            const bool conv_inc = normsq6(dsig) < tinc * tinc &&
                                   fabs(dkap) < atol + rtol * fabs(al) &&
                                   fabs(dlam) < atol + rtol * fabs(dl);
             if (conv_res || conv_inc)

@@ -255,7 +255,7 @@ int fcx_host_unregister(void *ptr);
  * slots by a pool of host threads, both ways, overlapped with the DMA (memcpy
  * only -- no arithmetic on the CPU).  fcx_host_staging(0/1) switches that off/on
  * (off = let the driver stage; -1 = query), fcx_host_threads(n) sets the pool
- * size (0 = query; default min(12, cores - 2)).  Both return the old value. */
+ * size (0 = query; default min(16, cores - 2)).  Both return the old value. */
 int fcx_host_staging(int on);
 int fcx_host_threads(int n);
 /* fcx_mises_evaluate_host sends its results over a packed wire (stress for every point, a flag

@@ -34,7 +34,7 @@ from fenics_constitutive_b200.models import VonMises3D  # noqa: E402
 from fenics_constitutive_b200.partition import env_rank_world, max_over_ranks  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=55, help="grid cubes per direction (6 n^3 tets)")
+ap.add_argument("--n", "--grid", dest="n", type=int, default=55, help="grid cubes per direction (6 n^3 tets); use --grid under torchrun (its parser treats --n as an abbreviation)")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--degree", type=int, default=2)
 ap.add_argument("--cg-rtol", type=float, default=1e-8)
