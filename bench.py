@@ -301,8 +301,14 @@ def run_native(args):
                          "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_qp": BYTES_PER_QP, "kernel_ms": kernel_ms},
             "cpu_baseline": cpu,
+            # d2h_bytes_per_step: the result arrays delivered into host memory (392 B/QP);
+            # d2h_wire_bytes_per_step: what actually crosses PCIe with the packed download wire
+            # (stress + flag byte for every point, 224 B only for plastic points; include/fcx.h fcx_host_wire)
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": H2D_PER_QP * ne,
-                    "d2h_bytes_per_step": D2H_PER_QP * ne, "qps_per_gpu": ne, "steps": Ke,
+                    "d2h_bytes_per_step": D2H_PER_QP * ne,
+                    "d2h_wire_bytes_per_step": (int(ne * (49 + 224 * e2e_plastic)) if L.fcx_host_wire(-1)
+                                                else D2H_PER_QP * ne),
+                    "qps_per_gpu": ne, "steps": Ke,
                     "plastic_fraction": round(e2e_plastic, 4),
                     "host_memory": args.e2e_memory, "register_s": reg_s,
                     "api": f"VonMises3D.evaluate(numpy {args.e2e_memory} host arrays) -> fcx_mises_evaluate_host"},

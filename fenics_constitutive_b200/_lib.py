@@ -38,12 +38,17 @@ SIGNATURES = {
     "fcx_drucker_prager_evaluate": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp, _dp, _vp, _vp, _vp]),
     "fcx_drucker_prager_evaluate_host": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp, _dp, _vp]),
     "fcx_mises_form": (_ci, [_dp, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
-                             _dp, _vp, _vp, _vp]),
+                             _dp, _dp, _vp, _vp, _vp]),
+    "fcx_tangent_apply_rec": (_ci, [_ci, _ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp]),
     "fcx_fe_stride": (_ci, [_ci]),
-    "fcx_internal_force": (_ci, [_ci, _ci, _sz, _ci, _ci, _dp, _dp, _dp, _dp, _dp, _dp, _vp]),
-    "fcx_tangent_apply": (_ci, [_ci, _ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp]),
-    "fcx_tangent_diag": (_ci, [_ci, _ci, _sz, _ci, _ci, _dp, _dp, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_internal_force": (_ci, [_ci, _ci, _sz, _ci, _ci, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp]),
+    "fcx_tangent_apply": (_ci, [_ci, _ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp]),
+    "fcx_tangent_diag": (_ci, [_ci, _ci, _sz, _ci, _ci, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp]),
     "fcx_gather_sum": (_ci, [_ci, _sz, _vp, _vp, _dp, _dp, _cd, _cd, _vp]),
+    "fcx_pcg_scratch_doubles": (_sz, []),
+    "fcx_pcg_pap": (_ci, [_sz, _dp, _dp, _dp, _dp, _vp, _dp, _vp]),
+    "fcx_pcg_update_xr": (_ci, [_sz, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _dp, _vp]),
+    "fcx_pcg_update_p": (_ci, [_sz, _dp, _dp, _dp, _dp, _dp, _vp]),
     "fcx_elastic_evaluate_host": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp]),
     "fcx_mises_evaluate_host": (_ci, [_dp, _sz, _dp, _dp, _dp, _dp, _dp, _vp]),
     "fcx_kelvin_evaluate_host": (_ci, [_ci, _dp, _dp, _cd, _cd, _cd, _cd, _cd, _sz, _dp, _dp, _dp, _dp, _dp]),

@@ -450,7 +450,8 @@ int fcx_tune(const char *key, int value)
     }
     if (key && strcmp(key, "fem_variant") == 0) {
         const int old = g_fem_variant;
-        g_fem_variant = value;
+        if (value >= 0)  // negative = query
+            g_fem_variant = value;
         return old;
     }
     if (key && strcmp(key, "tile") == 0) {
@@ -618,11 +619,13 @@ int fcx_mises_form(const double *params, size_t ncells, int nq, int nd, const in
                    const double *u, const double *u_prev, const double *dphi_ref,
                    const double *Jinv, const double *stress_prev, double *stress_cur,
                    double *tangent, const double *eps_n0, double *eps_n1, const double *alpha0,
-                   double *alpha1, double *grad_out, unsigned char *plastic_flag, int *status,
-                   void *stream)
+                   double *alpha1, double *grad_out, double *tangent_rec,
+                   unsigned char *plastic_flag, int *status, void *stream)
 {
     if (ncells == 0)
         return FCX_OK;
+    if (tangent_rec && !aligned16(tangent_rec))
+        return FCX_ERR_ARG;
     if (!params || !dofmap || !u || !dphi_ref || !Jinv || !stress_prev || !stress_cur || !tangent ||
         !eps_n0 || !eps_n1 || !alpha0 || !alpha1)
         return FCX_ERR_NULL;
@@ -641,6 +644,7 @@ int fcx_mises_form(const double *params, size_t ncells, int nq, int nd, const in
     A.eps1 = eps_n1;
     A.alpha1 = alpha1;
     A.grad_out = grad_out;
+    A.trec = tangent_rec;
     A.flag = plastic_flag;
     A.status = status;
     A.ticket = nullptr;

@@ -64,6 +64,8 @@ __device__ __forceinline__ void bt_dot_dense(const double *gphi, const double *t
 // MODE 0: internal force from a QP vector field (sigma)           -> fe
 // MODE 1: Jacobian action: p gathered, tau = C^T eps(p)           -> fe
 // MODE 2: Jacobian diagonal                                        -> fe
+// MODE 3 (qp_cell_kernel only): Jacobian action with VonMises3D tangent RECORDS
+//         [nqp][10] = {c0, c1, c2, c3, xn[6]}: tau = C eps(p) from 80 B instead of 288 B per QP
 template <int G, int S, int ND, int NQ, int MODE>
 __global__ void __launch_bounds__(ASM_THREADS)
     cell_kernel(const int *__restrict__ dofmap, const double *__restrict__ p,
@@ -216,7 +218,8 @@ __global__ void __launch_bounds__(256)
             acc[j] = 0.0;
         const long long e0 = adj_ptr[v], e1 = adj_ptr[v + 1];
         for (long long e = e0; e < e1; ++e) {
-            const double *src = fe + (size_t)adj_idx[e] * FeStride<G>::v;
+            // adj_idx == nullptr: fe is already in node-major slot order (contiguous per node)
+            const double *src = fe + (size_t)(adj_idx != nullptr ? adj_idx[e] : e) * FeStride<G>::v;
             if (G == 3) {  // one 32-byte sector: 16-byte + 8-byte load
                 const double2 xy = *reinterpret_cast<const double2 *>(src);
                 acc[0] += xy.x;
@@ -247,18 +250,20 @@ struct CellArgs {
     const double *weights;   // [NQ]
     const double *Jinv;      // [ncells][G][G]
     const double *detJ;      // [ncells]
-    const double *qarr;      // MODE 0: stress [nqp][S]; MODE 1/2: tangent [nqp][S][S]
-    double *fe;              // [ncells][ND][FS]
+    const double *qarr;      // MODE 0: stress [nqp][S]; MODE 1/2: tangent [nqp][S][S]; MODE 3: records [nqp][10]
+    double *fe;              // [ncells][ND][FS], or node-major slots [pos[c][a]][FS] if pos != nullptr
+    const int *pos;          // [ncells][ND] slot of (cell, local node) in the node-sorted adjacency, or nullptr
     unsigned long long ncells;
     unsigned long long *ticket;
-    int bulk_ok;             // Jinv, detJ, dofmap, qarr 16-byte aligned
+    int bulk_ok;             // Jinv, detJ, dofmap, pos, qarr 16-byte aligned
 };
 
 template <int G, int S, int ND, int NQ, int MODE>
 struct CellCfg {
     static constexpr int TILE = fem_tile<NQ>();
     static constexpr int CPT = TILE / NQ;                    // cells per tile (a multiple of 16)
-    static constexpr int SEGW = (MODE == 0) ? S : S * S;     // staged doubles per QP
+    static constexpr int SEGW = (MODE == 0) ? S : (MODE == 3 ? 10 : S * S);  // staged doubles per QP
+    static constexpr bool GATHER = (MODE == 1 || MODE == 3);  // needs the nodal values of p
     static constexpr int NDG = ND * G;
     static constexpr int PST = NDG | 1;                      // odd stride: conflict-free partials
     static constexpr int DOF_DBL = (CPT * ND + 1) / 2;       // dofmap rows, in doubles
@@ -266,7 +271,7 @@ struct CellCfg {
     // contributions are reduce-scattered with shuffles and written straight to fe
     // (no partial-sum stage: 21 KB instead of 37 KB of shared memory per CTA).
     static constexpr bool SHFL = (NQ == 4 && G == 3);
-    static constexpr size_t smem_doubles = (size_t)TILE * SEGW + CPT * G * G + CPT + DOF_DBL +
+    static constexpr size_t smem_doubles = (size_t)TILE * SEGW + CPT * G * G + CPT + 2 * DOF_DBL +
                                            (SHFL ? 0 : (size_t)TILE * PST) + NQ * ND * G + NQ + 2;
     static constexpr size_t smem_bytes = sizeof(double) * smem_doubles;
 };
@@ -284,7 +289,8 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
     double *s_jinv = s_stage + TILE * SEGW;              // [CPT][G*G]     (bulk, barrier 0)
     double *s_det = s_jinv + CPT * G * G;                // [CPT]          (bulk, barrier 0)
     int *s_dof = reinterpret_cast<int *>(s_det + CPT);   // [CPT][ND]      (bulk, barrier 0; MODE 1)
-    double *s_part = s_det + CPT + Cfg::DOF_DBL;         // [TILE][PST]    (not with SHFL)
+    int *s_pos = s_dof + 2 * Cfg::DOF_DBL;               // [CPT][ND]      (bulk, barrier 0; SHFL + A.pos)
+    double *s_part = s_det + CPT + 2 * Cfg::DOF_DBL;     // [TILE][PST]    (not with SHFL)
     double *s_tab = s_part + (Cfg::SHFL ? 0 : TILE * PST);  // [NQ][ND][G]
     double *s_wq = s_tab + NQ * ND * G;                  // [NQ]
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_wq + NQ);  // [2]
@@ -306,13 +312,17 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
     auto is_bulk = [&](unsigned long long t) { return A.bulk_ok && (t + 1) * CPT <= A.ncells; };
     auto issue = [&](unsigned long long t) {  // thread 0: all ranges of tile t, one tile ahead
         const unsigned long long c0 = t * CPT, q0 = t * TILE;
-        constexpr uint32_t small_bytes =
-            (uint32_t)(sizeof(double) * (CPT * G * G + CPT) + (MODE == 1 ? sizeof(int) * CPT * ND : 0));
+        const bool scatter = Cfg::SHFL && A.pos != nullptr;
+        const uint32_t small_bytes =
+            (uint32_t)(sizeof(double) * (CPT * G * G + CPT) +
+                       ((Cfg::GATHER ? 1 : 0) + (scatter ? 1 : 0)) * sizeof(int) * CPT * ND);
         mbar_arrive_expect_tx(&bar[0], small_bytes);
         bulk_g2s(s_jinv, A.Jinv + c0 * (G * G), (uint32_t)(sizeof(double) * CPT * G * G), &bar[0]);
         bulk_g2s(s_det, A.detJ + c0, (uint32_t)(sizeof(double) * CPT), &bar[0]);
-        if (MODE == 1)
+        if (Cfg::GATHER)
             bulk_g2s(s_dof, A.dofmap + c0 * ND, (uint32_t)(sizeof(int) * CPT * ND), &bar[0]);
+        if (scatter)
+            bulk_g2s(s_pos, A.pos + c0 * ND, (uint32_t)(sizeof(int) * CPT * ND), &bar[0]);
         mbar_arrive_expect_tx(&bar[1], (uint32_t)(sizeof(double) * TILE * SEGW));
         bulk_g2s(s_stage, A.qarr + q0 * SEGW, (uint32_t)(sizeof(double) * TILE * SEGW), &bar[1]);
     };
@@ -336,9 +346,12 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
                 s_jinv[i] = A.Jinv[c0 * (G * G) + i];
             for (int i = tid; i < ncell; i += TILE)
                 s_det[i] = A.detJ[c0 + i];
-            if (MODE == 1)
+            if (Cfg::GATHER)
                 for (int i = tid; i < ncell * ND; i += TILE)
                     s_dof[i] = A.dofmap[c0 * ND + i];
+            if (Cfg::SHFL && A.pos != nullptr)
+                for (int i = tid; i < ncell * ND; i += TILE)
+                    s_pos[i] = A.pos[c0 * ND + i];
             for (int i = tid; i < cnt * SEGW; i += TILE)
                 s_stage[i] = A.qarr[q0 * SEGW + i];
             __syncthreads();
@@ -356,7 +369,7 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
             for (int i = 0; i < G * G; ++i)
                 K[i] = s_jinv[lc * (G * G) + i];
             wdet = s_wq[q] * s_det[lc];
-            if (MODE == 1 && active) {  // Mandel strain of nabla_grad(p) at this QP
+            if (Cfg::GATHER && active) {  // Mandel strain of nabla_grad(p) at this QP
                 double g[G * G];
                 grad_of_increment<G, ND>(s_tab + q * ND * G, K, s_dof + lc * ND, A.p, nullptr, g);
                 mandel_strain<S, G>(g, e);
@@ -397,6 +410,17 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
 #pragma unroll
                     for (int k = 0; k < S; ++k)
                         t[k] = fma(row[(m * S + k) % SEGW], e[m], t[k]);
+            } else if (MODE == 3) {
+                // C = c0/c1 on the volumetric block, c2 on the shear diagonal, + c3 xn xn^T (symmetric)
+                const double c0 = row[0], c1 = row[1 % SEGW], c2 = row[2 % SEGW], c3 = row[3 % SEGW];
+                double ne = 0.0;
+#pragma unroll
+                for (int k = 0; k < S; ++k)
+                    ne = fma(row[(4 + k) % SEGW], e[k], ne);
+                const double tre = c1 * ((e[0] + e[1 % S]) + e[2 % S]), cn = c3 * ne, dd = c0 - c1;
+#pragma unroll
+                for (int k = 0; k < S; ++k)
+                    t[k] = fma(cn, row[(4 + k) % SEGW], (k < 3) ? fma(dd, e[k], tre) : c2 * e[k]);
             }
             if (MODE != 2)
                 prescale_shear<S, G>(t, ts);
@@ -436,8 +460,12 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
                     const double ka = (hi ? v2 : v0) + __shfl_xor_sync(0xffffffffu, hi ? v0 : v2, 2);
                     const double kb = (hi ? 0.0 : v1) + __shfl_xor_sync(0xffffffffu, hi ? v1 : 0.0, 2);
                     const double r = (od ? kb : ka) + __shfl_xor_sync(0xffffffffu, od ? ka : kb, 1);
-                    if (active)
-                        fe_cell[a * FS + q] = r;  // 4 lanes = one 32-byte sector
+                    if (active) {  // 4 lanes = one 32-byte sector
+                        if (A.pos != nullptr)
+                            A.fe[(size_t)s_pos[lc * ND + a] * FS + q] = r;
+                        else
+                            fe_cell[a * FS + q] = r;
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < G; ++j)
@@ -497,7 +525,10 @@ static int launch_qp_cell(const CellArgs &A0, cudaStream_t st)
         grid = ntiles;
     A.ticket = (ntiles > grid) ? tile_ticket(st) : nullptr;
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    A.bulk_ok = al16(A.Jinv) && al16(A.detJ) && al16(A.qarr) && (MODE != 1 || al16(A.dofmap));
+    A.bulk_ok = al16(A.Jinv) && al16(A.detJ) && al16(A.qarr) && (!Cfg::GATHER || al16(A.dofmap)) &&
+                (A.pos == nullptr || al16(A.pos));
+    if (!Cfg::SHFL && A.pos != nullptr)
+        return FCX_ERR_ARG;  // node-major slots are written by the shuffle path only (3-D, 4 QPs)
     kern<<<(unsigned)grid, Cfg::TILE, Cfg::smem_bytes, st>>>(A);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return note_cuda_error(cudaGetLastError(), "qp_cell_kernel launch");
@@ -507,17 +538,24 @@ template <int G, int S, int ND, int NQ>
 static int launch_cell(int mode, size_t ncells, const int *dofmap, const double *p,
                        const double *dphi, const double *w, const double *Jinv,
                        const double *detJ, const double *qvec, const double *tangent, double *fe,
-                       cudaStream_t st)
+                       const int *pos, cudaStream_t st)
 {
     if (fem_variant() != 0) {
-        CellArgs A{dofmap, p, dphi, w, Jinv, detJ, mode == 0 ? qvec : tangent, fe,
+        CellArgs A{dofmap, p, dphi, w, Jinv, detJ, mode == 0 ? qvec : tangent, fe, pos,
                    (unsigned long long)ncells, nullptr, 0};
         switch (mode) {
         case 0: return launch_qp_cell<G, S, ND, NQ, 0>(A, st);
         case 1: return launch_qp_cell<G, S, ND, NQ, 1>(A, st);
+        case 3:
+            if constexpr (G == 3 && S == 6)
+                return launch_qp_cell<G, S, ND, NQ, 3>(A, st);
+            else
+                return FCX_ERR_ARG;
         default: return launch_qp_cell<G, S, ND, NQ, 2>(A, st);
         }
     }
+    if (mode == 3 || pos != nullptr)
+        return FCX_ERR_ARG;  // records / node-major slots need the QP-parallel kernels
     unsigned long long grid = (ncells + ASM_THREADS - 1) / ASM_THREADS;
     const unsigned long long cap = (unsigned long long)sm_count() * 16;
     if (grid > cap)
@@ -544,11 +582,11 @@ static int launch_cell(int mode, size_t ncells, const int *dofmap, const double 
 static int dispatch_cell(int mode, int gdim, int sdim, size_t ncells, int nq, int nd,
                          const int *dofmap, const double *p, const double *dphi, const double *w,
                          const double *Jinv, const double *detJ, const double *qvec,
-                         const double *tangent, double *fe, cudaStream_t st)
+                         const double *tangent, double *fe, const int *pos, cudaStream_t st)
 {
 #define FCX_CELL_CASE(G, S, ND, NQ) \
     if (gdim == G && sdim == S && nd == ND && nq == NQ) \
-        return launch_cell<G, S, ND, NQ>(mode, ncells, dofmap, p, dphi, w, Jinv, detJ, qvec, tangent, fe, st);
+        return launch_cell<G, S, ND, NQ>(mode, ncells, dofmap, p, dphi, w, Jinv, detJ, qvec, tangent, fe, pos, st);
     FCX_CELL_CASE(3, 6, 10, 4)  // P2 tetrahedron, q_degree 2
     FCX_CELL_CASE(3, 6, 4, 1)   // P1 tetrahedron, q_degree 1
     FCX_CELL_CASE(3, 6, 4, 4)   // P1 tetrahedron, q_degree 2
@@ -572,39 +610,52 @@ int fcx_fe_stride(int gdim) { return gdim == 3 ? 4 : (gdim == 1 || gdim == 2 ? g
 
 int fcx_internal_force(int gdim, int sdim, size_t ncells, int nq, int nd, const double *dphi_ref,
                        const double *weights, const double *Jinv, const double *detJ,
-                       const double *stress, double *fe, void *stream)
+                       const double *stress, double *fe, const int *fe_pos, void *stream)
 {
     if (ncells == 0)
         return FCX_OK;
     if (!dphi_ref || !weights || !Jinv || !detJ || !stress || !fe)
         return FCX_ERR_NULL;
     return dispatch_cell(0, gdim, sdim, ncells, nq, nd, nullptr, nullptr, dphi_ref, weights, Jinv,
-                         detJ, stress, nullptr, fe, static_cast<cudaStream_t>(stream));
+                         detJ, stress, nullptr, fe, fe_pos, static_cast<cudaStream_t>(stream));
 }
 
 int fcx_tangent_apply(int gdim, int sdim, size_t ncells, int nq, int nd, const int *dofmap,
                       const double *p, const double *dphi_ref, const double *weights,
                       const double *Jinv, const double *detJ, const double *tangent, double *fe,
-                      void *stream)
+                      const int *fe_pos, void *stream)
 {
     if (ncells == 0)
         return FCX_OK;
     if (!dofmap || !p || !dphi_ref || !weights || !Jinv || !detJ || !tangent || !fe)
         return FCX_ERR_NULL;
     return dispatch_cell(1, gdim, sdim, ncells, nq, nd, dofmap, p, dphi_ref, weights, Jinv, detJ,
-                         nullptr, tangent, fe, static_cast<cudaStream_t>(stream));
+                         nullptr, tangent, fe, fe_pos, static_cast<cudaStream_t>(stream));
+}
+
+int fcx_tangent_apply_rec(int gdim, int sdim, size_t ncells, int nq, int nd, const int *dofmap,
+                          const double *p, const double *dphi_ref, const double *weights,
+                          const double *Jinv, const double *detJ, const double *tangent_rec,
+                          double *fe, const int *fe_pos, void *stream)
+{
+    if (ncells == 0)
+        return FCX_OK;
+    if (!dofmap || !p || !dphi_ref || !weights || !Jinv || !detJ || !tangent_rec || !fe)
+        return FCX_ERR_NULL;
+    return dispatch_cell(3, gdim, sdim, ncells, nq, nd, dofmap, p, dphi_ref, weights, Jinv, detJ,
+                         nullptr, tangent_rec, fe, fe_pos, static_cast<cudaStream_t>(stream));
 }
 
 int fcx_tangent_diag(int gdim, int sdim, size_t ncells, int nq, int nd, const double *dphi_ref,
                      const double *weights, const double *Jinv, const double *detJ,
-                     const double *tangent, double *fe, void *stream)
+                     const double *tangent, double *fe, const int *fe_pos, void *stream)
 {
     if (ncells == 0)
         return FCX_OK;
     if (!dphi_ref || !weights || !Jinv || !detJ || !tangent || !fe)
         return FCX_ERR_NULL;
     return dispatch_cell(2, gdim, sdim, ncells, nq, nd, nullptr, nullptr, dphi_ref, weights, Jinv,
-                         detJ, nullptr, tangent, fe, static_cast<cudaStream_t>(stream));
+                         detJ, nullptr, tangent, fe, fe_pos, static_cast<cudaStream_t>(stream));
 }
 
 int fcx_gather_sum(int gdim, size_t nnodes, const long long *adj_ptr, const int *adj_idx,
@@ -614,7 +665,7 @@ int fcx_gather_sum(int gdim, size_t nnodes, const long long *adj_ptr, const int 
         return FCX_ERR_ARG;
     if (nnodes == 0)
         return FCX_OK;
-    if (!adj_ptr || !adj_idx || !fe || !out)
+    if (!adj_ptr || !fe || !out)
         return FCX_ERR_NULL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned long long grid = (nnodes + 255) / 256;

@@ -43,6 +43,7 @@ struct MisesFormArgs {
     double *eps1;               // [n][6]
     double *alpha1;             // [n]
     double *grad_out;           // [n][9] or nullptr
+    double *trec;               // [n][10] or nullptr: tangent records (4 coefficients + flow direction)
     unsigned char *flag;        // [n] or nullptr
     int *status;                // int[2] or nullptr
     unsigned long long *ticket;
@@ -172,6 +173,14 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
                     A.eps1[qg * 6 + i] = ep[i];
                 }
                 A.alpha1[qg] = al;
+            }
+            if (A.trec != nullptr) {  // 80 B instead of 288: what the matrix-free Jacobian action reads
+                double *r = A.trec + qg * 10;
+                *reinterpret_cast<double2 *>(r + 0) = make_double2(coef[0], coef[1]);
+                *reinterpret_cast<double2 *>(r + 2) = make_double2(coef[2], coef[3]);
+                *reinterpret_cast<double2 *>(r + 4) = make_double2(xn[0], xn[1]);
+                *reinterpret_cast<double2 *>(r + 6) = make_double2(xn[2], xn[3]);
+                *reinterpret_cast<double2 *>(r + 8) = make_double2(xn[4], xn[5]);
             }
             double c[6][6];
 #pragma unroll

@@ -47,6 +47,8 @@ class NewtonSolver:
         self.reduce_over_ranks = False  # sum norms/dots over torch.distributed ranks
         self.residual_history: list[float] = []
         self.krylov_iterations: list[int] = []
+        self.profile = False  # accumulate wall time of the linear solves (adds two syncs per solve)
+        self.linear_solve_s = 0.0
 
     # ------------------------------------------------------------ helpers
     def _dot(self, a, b) -> float:
@@ -86,20 +88,32 @@ class NewtonSolver:
         return t
 
     def _solve_cg(self, apply, rhs, free_mask, diag):
-        """Jacobi-preconditioned CG on the free dofs (projected operator P J P).  All
-        scalars stay on the device; the host looks at the residual norm only every
-        ``cg_check_every`` iterations, so an iteration is a fixed sequence of enqueued
-        kernels (two element kernels of problem.J_apply + a handful of vector ops)."""
+        """Jacobi-preconditioned CG on the free dofs (projected operator P J P).  All scalars stay
+        on the device; the host looks at the residual norm only every ``cg_check_every``
+        iterations, so an iteration is a fixed sequence of enqueued kernels: the two element
+        kernels of problem.J_apply + the three fused vector kernels of csrc/fcx_pcg.cu
+        (deterministic reductions).  With several ranks the three scalars are summed over ranks
+        (NCCL all-reduce of one / two doubles)."""
         import torch
 
+        from .. import _buffers as B
+        from .._lib import check, lib
+
+        L = lib()
+        dev = rhs.device
+        n = rhs.numel()
+        stream = B.current_stream_ptr(dev.index)
         fm = free_mask.to(torch.float64)
-        minv = fm / torch.where(diag.abs() > 0, diag, torch.ones_like(diag))
+        minv = (fm / torch.where(diag.abs() > 0, diag, torch.ones_like(diag))).contiguous()
         x = torch.zeros_like(rhs)
-        r = rhs * fm
-        z = minv * r
-        p = z.clone()
+        r = (rhs * fm).contiguous()
+        p = minv * r
         Ap = torch.empty_like(rhs)
-        rz = self._rsum(torch.dot(r, z))
+        scratch = torch.empty(int(L.fcx_pcg_scratch_doubles()), dtype=torch.float64, device=dev)
+        ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        sc = torch.zeros(4, dtype=torch.float64, device=dev)  # [rz, pAp, rz_new, rr]
+        rz, pAp, new2 = sc[0:1], sc[1:2], sc[2:4]
+        rz.copy_(self._rsum(torch.dot(r, p)).reshape(1))
         r0 = float(torch.sqrt(self._rsum(torch.dot(r, r))).item())
         if r0 == 0.0:
             return x, 0
@@ -107,18 +121,19 @@ class NewtonSolver:
         it = 0
         while it < self.cg_max_it:
             apply(p, Ap)
-            Ap.mul_(fm)
-            pAp = self._rsum(torch.dot(p, Ap))
-            alpha = torch.where(pAp > 0, rz / pAp, torch.zeros_like(rz))  # exact convergence: stay at x
-            x.addcmul_(p, alpha)
-            r.addcmul_(Ap, -alpha)
+            check(L.fcx_pcg_pap(n, p.data_ptr(), Ap.data_ptr(), minv.data_ptr(), scratch.data_ptr(),
+                                ticket.data_ptr(), pAp.data_ptr(), stream), "fcx_pcg_pap")
+            self._rsum(pAp)
+            check(L.fcx_pcg_update_xr(n, x.data_ptr(), r.data_ptr(), p.data_ptr(), Ap.data_ptr(), minv.data_ptr(),
+                                      rz.data_ptr(), pAp.data_ptr(), scratch.data_ptr(), ticket.data_ptr(),
+                                      new2.data_ptr(), stream), "fcx_pcg_update_xr")
+            self._rsum(new2)
             it += 1
-            if it % self.cg_check_every == 0 and float(self._rsum(torch.dot(r, r)).item()) <= tol2:
+            if it % self.cg_check_every == 0 and float(sc[3].item()) <= tol2:
                 break
-            torch.mul(minv, r, out=z)
-            rz_new = self._rsum(torch.dot(r, z))
-            p.mul_(torch.where(rz > 0, rz_new / rz, torch.zeros_like(rz))).add_(z)
-            rz = rz_new
+            check(L.fcx_pcg_update_p(n, p.data_ptr(), r.data_ptr(), minv.data_ptr(), sc[2:3].data_ptr(),
+                                     rz.data_ptr(), stream), "fcx_pcg_update_p")
+            rz.copy_(sc[2:3])
         return x, it
 
     # -------------------------------------------------------------- solve
@@ -166,7 +181,15 @@ class NewtonSolver:
             if use_dense:
                 dx, kit = self._solve_dense(pb.J_apply, rhs, free)
             else:
+                if self.profile:
+                    import time
+
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
                 dx, kit = self._solve_cg(pb.J_apply, rhs, free, pb.J_diag())
+                if self.profile:
+                    torch.cuda.synchronize()
+                    self.linear_solve_s += time.perf_counter() - t0
             dx[bc_dofs] = b[bc_dofs]  # identity rows: dx_bc = x_bc - g
             self.krylov_iterations.append(kit)
             x.add_(dx, alpha=-self.relaxation_parameter)

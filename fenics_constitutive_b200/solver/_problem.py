@@ -212,6 +212,13 @@ class IncrSmallStrainProblem:
         ptr, idx = node_adjacency(self.V.dofmap, self.V.num_nodes)
         self._adj_ptr = torch.as_tensor(ptr, dtype=torch.int64, device=dev)
         self._adj_idx = torch.as_tensor(idx, dtype=torch.int32, device=dev)
+        # 3-D elements with 4 QPs: element vectors are written in node-major slot order (fe_pos = inverse
+        # of adj_idx) so the node-wise sum streams them contiguously (include/fcx.h)
+        self._fe_pos = None
+        if self.gdim == 3 and T.nq == 4:
+            pos = np.empty(idx.size, dtype=np.int32)
+            pos[idx] = np.arange(idx.size, dtype=np.int32)
+            self._fe_pos = torch.as_tensor(pos, dtype=torch.int32, device=dev)
         # element vectors [ncells][nd][fs]; 3-D slots are padded to one 32-byte sector (include/fcx.h)
         self._fe = torch.empty(self.num_cells * T.nd * lib().fcx_fe_stride(self.gdim), dtype=torch.float64, device=dev)
 
@@ -229,6 +236,11 @@ class IncrSmallStrainProblem:
             and l0.law.eps_layout == "aos" and (T.nd, T.nq) in ((10, 4), (4, 1), (4, 4))
         )
         self.keep_del_grad_u = True  # fused path: also store grad_del_u (72 B/QP) for inspection
+        # fused path: form() also emits the tangent as 10-double records (4 coefficients + flow
+        # direction) and J_apply reads those -- 80 instead of 288 B per QP per Krylov iteration
+        self.use_tangent_records = True
+        self._trec = torch.empty(self.nqp * 10, dtype=torch.float64, device=dev) if self.fused else None
+        self._trec_valid = False
 
     # ------------------------------------------------------------------ form
     def form(self, x=None) -> None:
@@ -238,6 +250,7 @@ class IncrSmallStrainProblem:
         if self.fused:
             self._form_fused()
             return
+        self._trec_valid = False
         for law in self._law_on_submeshs:
             law.evaluate(self.sim_time, self.incr_disp, self.stress, self.tangent)
 
@@ -266,8 +279,10 @@ class IncrSmallStrainProblem:
             h0["eps_n"].x.array.data_ptr(), h1["eps_n"].x.array.data_ptr(),
             h0["alpha"].x.array.data_ptr(), h1["alpha"].x.array.data_ptr(),
             ctx.displacement_gradient_fn.x.array.data_ptr() if self.keep_del_grad_u else None,
+            self._trec.data_ptr() if self.use_tangent_records else None,
             flag.data_ptr() if flag is not None else None, status.data_ptr(), stream,
         )
+        self._trec_valid = self.use_tangent_records
         law.plastic_flag = flag
         check(rc, "IncrSmallStrainProblem.form (fcx_mises_form)")
         if not law.defer_errors:
@@ -278,9 +293,16 @@ class IncrSmallStrainProblem:
         T = self.tables
         return (self.gdim, self.sdim, self.num_cells, T.nq, T.nd)
 
+    def _pos_ptr(self):
+        """Device pointer of fe_pos when the element kernels write node-major slots, else None."""
+        if self._fe_pos is not None and lib().fcx_tune(b"fem_variant", -1) != 0:
+            return self._fe_pos.data_ptr()
+        return None
+
     def _gather_sum(self, out, alpha=1.0, beta=0.0) -> None:
         L = lib()
-        check(L.fcx_gather_sum(self.gdim, self.V.num_nodes, self._adj_ptr.data_ptr(), self._adj_idx.data_ptr(),
+        idx = None if self._pos_ptr() is not None else self._adj_idx.data_ptr()
+        check(L.fcx_gather_sum(self.gdim, self.V.num_nodes, self._adj_ptr.data_ptr(), idx,
                                self._fe.data_ptr(), out.data_ptr(), alpha, beta,
                                B.current_stream_ptr(self.device.index)), "fcx_gather_sum")
 
@@ -296,7 +318,7 @@ class IncrSmallStrainProblem:
         check(L.fcx_set_device(self.device.index))
         check(L.fcx_internal_force(g, s, nc, nq, nd, self._dphi.data_ptr(), self._weights.data_ptr(),
                                    self._Jinv.data_ptr(), self._detJ.data_ptr(),
-                                   self.stress.current.x.array.data_ptr(), self._fe.data_ptr(),
+                                   self.stress.current.x.array.data_ptr(), self._fe.data_ptr(), self._pos_ptr(),
                                    B.current_stream_ptr(self.device.index)), "fcx_internal_force")
         self._gather_sum(b)
         b.sub_(self.f_ext)
@@ -310,10 +332,18 @@ class IncrSmallStrainProblem:
             out = torch.empty_like(p)
         L = lib()
         g, s, nc, nq, nd = self._tables_args()
+        if self.fused and self._trec_valid and self.use_tangent_records and L.fcx_tune(b"fem_variant", -1) != 0:
+            check(L.fcx_tangent_apply_rec(g, s, nc, nq, nd, self._dofmap.data_ptr(), p.data_ptr(),
+                                          self._dphi.data_ptr(), self._weights.data_ptr(), self._Jinv.data_ptr(),
+                                          self._detJ.data_ptr(), self._trec.data_ptr(), self._fe.data_ptr(),
+                                          self._pos_ptr(), B.current_stream_ptr(self.device.index)),
+                  "fcx_tangent_apply_rec")
+            self._gather_sum(out)
+            return out
         check(L.fcx_tangent_apply(g, s, nc, nq, nd, self._dofmap.data_ptr(), p.data_ptr(),
                                   self._dphi.data_ptr(), self._weights.data_ptr(), self._Jinv.data_ptr(),
                                   self._detJ.data_ptr(), self.tangent.x.array.data_ptr(), self._fe.data_ptr(),
-                                  B.current_stream_ptr(self.device.index)), "fcx_tangent_apply")
+                                  self._pos_ptr(), B.current_stream_ptr(self.device.index)), "fcx_tangent_apply")
         self._gather_sum(out)
         return out
 
@@ -326,7 +356,8 @@ class IncrSmallStrainProblem:
         g, s, nc, nq, nd = self._tables_args()
         check(L.fcx_tangent_diag(g, s, nc, nq, nd, self._dphi.data_ptr(), self._weights.data_ptr(),
                                  self._Jinv.data_ptr(), self._detJ.data_ptr(), self.tangent.x.array.data_ptr(),
-                                 self._fe.data_ptr(), B.current_stream_ptr(self.device.index)), "fcx_tangent_diag")
+                                 self._fe.data_ptr(), self._pos_ptr(), B.current_stream_ptr(self.device.index)),
+              "fcx_tangent_diag")
         self._gather_sum(out)
         return out
 

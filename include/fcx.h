@@ -180,12 +180,14 @@ int fcx_gather_grad(int gdim, size_t ncells, int nq, int nd, const int *dofmap,
  * arrays (stress_cur, eps_n1, alpha1, tangent) only written; a pair may alias
  * (in-place).  grad_out: optional [ncells*nq][3][3] copy of grad_del_u.
  * (nd, nq) in {(10,4), (4,1), (4,4)}; FCX_ERR_ARG otherwise (use
- * fcx_gather_grad + fcx_mises_evaluate). */
+ * fcx_gather_grad + fcx_mises_evaluate).  * tangent_rec: optional [ncells*nq][10], 16-byte aligned: the tangent of each point as
+ *   {ka + cpp*2/3, ka - cpp/3, cpp, cnn, xn[6]} (see fcx_tangent_apply_rec). */
 int fcx_mises_form(const double *params_host, size_t ncells, int nq, int nd, const int *dofmap,
                    const double *u, const double *u_prev, const double *dphi_ref,
                    const double *Jinv, const double *stress_prev, double *stress_cur,
                    double *tangent, const double *eps_n0, double *eps_n1, const double *alpha0,
-                   double *alpha1, double *grad_out, unsigned char *plastic_flag, int *status,
+                   double *alpha1, double *grad_out, double *tangent_rec,
+                   unsigned char *plastic_flag, int *status,
                    void *stream);
 
 /* Residual and Jacobian action of IncrSmallStrainProblem on the device
@@ -201,20 +203,52 @@ int fcx_mises_form(const double *params_host, size_t ncells, int nq, int nd, con
  *   fcx_tangent_diag     fe = diagonal of the element matrix
  * fcx_gather_sum then forms out[node][j] = beta*out + alpha * sum over the
  * node's (cell, local index) adjacency (adj_ptr [nnodes+1] int64, adj_idx
- * int32 = cell*nd + a) in a fixed order -- deterministic, no atomics. */
+ * int32 = cell*nd + a) in a fixed order -- deterministic, no atomics.
+ * fe_pos (optional, 3-D elements with 4 quadrature points only): [ncells][nd] int32, the slot of
+ * (cell, local node) in the node-sorted adjacency (the inverse of adj_idx).  The element kernel
+ * then writes fe in NODE-major slot order and fcx_gather_sum is called with adj_idx = NULL: it
+ * reads each node's contributions as one contiguous run (HBM fetches 64 bytes per missed sector,
+ * so the cell-major layout costs 2.7x the bytes on the read side, profiles/r1n).
+ * fcx_tangent_apply_rec is fcx_tangent_apply for VonMises3D tangents given as the 10-double
+ * records fcx_mises_form can emit (tangent_rec [ncells*nq][10] = ka+cpp*2/3, ka-cpp/3, cpp, cnn,
+ * xn[6]; tangent = ka*xioi + cpp*xpp + cnn*outer(xn,xn), reference
+ * models/mises_plasticity_isotropic_hardening.py:170-175): 80 instead of 288 bytes per QP per
+ * Krylov iteration; gdim 3 only. */
 int fcx_fe_stride(int gdim);
 int fcx_internal_force(int gdim, int sdim, size_t ncells, int nq, int nd, const double *dphi_ref,
                        const double *weights, const double *Jinv, const double *detJ,
-                       const double *stress, double *fe, void *stream);
+                       const double *stress, double *fe, const int *fe_pos, void *stream);
 int fcx_tangent_apply(int gdim, int sdim, size_t ncells, int nq, int nd, const int *dofmap,
                       const double *p, const double *dphi_ref, const double *weights,
                       const double *Jinv, const double *detJ, const double *tangent, double *fe,
-                      void *stream);
+                      const int *fe_pos, void *stream);
+int fcx_tangent_apply_rec(int gdim, int sdim, size_t ncells, int nq, int nd, const int *dofmap,
+                          const double *p, const double *dphi_ref, const double *weights,
+                          const double *Jinv, const double *detJ, const double *tangent_rec,
+                          double *fe, const int *fe_pos, void *stream);
 int fcx_tangent_diag(int gdim, int sdim, size_t ncells, int nq, int nd, const double *dphi_ref,
                      const double *weights, const double *Jinv, const double *detJ,
-                     const double *tangent, double *fe, void *stream);
+                     const double *tangent, double *fe, const int *fe_pos, void *stream);
 int fcx_gather_sum(int gdim, size_t nnodes, const long long *adj_ptr, const int *adj_idx,
                    const double *fe, double *out, double alpha, double beta, void *stream);
+
+/* Fused vector kernels of one Jacobi-preconditioned CG iteration (the linear solve inside the
+ * stand-in NewtonSolver; the reference leaves it to PETSc via dolfinx.nls.petsc.NewtonSolver).
+ * All scalars are DEVICE doubles; reductions are deterministic (per-CTA partials summed in index
+ * order by the last CTA).  minv = inverse Jacobi diagonal, 0 on constrained dofs (also the mask).
+ * scratch: fcx_pcg_scratch_doubles() doubles; ticket: one zero-initialised unsigned.
+ *   fcx_pcg_pap        out[0]  = sum_free p.Ap
+ *   fcx_pcg_update_xr  alpha = rz/pAp (0 if pAp <= 0); x += alpha p; r -= alpha Ap on free dofs;
+ *                      out2[0] = sum r.(minv r), out2[1] = sum r.r
+ *   fcx_pcg_update_p   p = minv r + (rz_new/rz) p */
+size_t fcx_pcg_scratch_doubles(void);
+int fcx_pcg_pap(size_t n, const double *p, const double *Ap, const double *minv, double *scratch,
+                unsigned *ticket, double *out, void *stream);
+int fcx_pcg_update_xr(size_t n, double *x, double *r, const double *p, const double *Ap,
+                      const double *minv, const double *rz, const double *pAp, double *scratch,
+                      unsigned *ticket, double *out2, void *stream);
+int fcx_pcg_update_p(size_t n, double *p, const double *r, const double *minv, const double *rz_new,
+                     const double *rz, void *stream);
 
 /* -------------------------------------------------------------------- host */
 

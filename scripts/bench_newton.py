@@ -73,6 +73,7 @@ solver = S.NewtonSolver(None, problem)
 solver.linear_solver = "cg"
 solver.cg_rtol = args.cg_rtol
 solver.reduce_over_ranks = world > 1
+solver.profile = True
 if args.newton_steps_only > 0:
     solver.cg_max_it = args.newton_steps_only
     solver.max_it = 2
@@ -149,7 +150,9 @@ if rank == 0:
         "cells_per_gpu": problem.num_cells, "qps_per_gpu": nqp, "dofs_per_gpu": V.num_dofs,
         "degree": args.degree, "q_degree": qd, "load_steps": args.steps, "newton_iterations": newton_its,
         "krylov_iterations": krylov, "cg_rtol": args.cg_rtol, "fused_form": problem.fused,
-        "setup_s": round(setup_s, 2), "solve_s": round(solve_s, 3), "form_calls": form_calls,
+        "setup_s": round(setup_s, 2), "solve_s": round(solve_s, 3),
+        "linear_solve_s": round(solver.linear_solve_s, 3),
+        "ms_per_krylov_iteration": 1e3 * solver.linear_solve_s / max(1, sum(sum(k) for k in krylov)), "form_calls": form_calls,
         "qp_updates_per_s_whole_solve": world * nqp * form_calls / solve_s,
         "plastic_fraction_final": round(plastic_frac, 4), "mean_sigma_xx": sxx,
         "kernel_ms": {"form_fused": ms_form, "F": ms_F, "J_apply": ms_J, "J_diag": ms_D, "gather_sum_alone": ms_gs},

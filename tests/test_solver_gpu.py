@@ -134,6 +134,41 @@ def test_fem_kernels_many_tiles_per_cta(name, mk, degree, qd, cons, ctas_per_sm)
     assert np.abs(g - gref).max() <= 1e-13 * np.abs(gref).max()
 
 
+@pytest.mark.parametrize("degree,qd,n,scale", [(2, 2, (9, 8, 7), 1.0e-4), (1, 2, (6, 5, 5), 3.0e-4)])
+def test_jacobian_action_from_tangent_records(degree, qd, n, scale):
+    """Fused form() also emits the VonMises3D tangent as 10-double records; the matrix-free Jacobian
+    action computed from them (80 B/QP) equals the one from the dense 6x6 tangents (288 B/QP) and the
+    oracle's assembled matrix, on a mixed elastic/plastic state."""
+    import torch
+
+    mesh = S.create_unit_cube(*n)
+    V = S.FunctionSpace(mesh, degree)
+    u = S.Function(V)
+    law = VonMises3D(MISES)
+    law.record_plastic_flag = True
+    pb = S.IncrSmallStrainProblem(law, u, [], qd)
+    assert pb.fused and pb.use_tangent_records
+    rng = np.random.default_rng(23)
+    u.x.array.copy_(torch.from_numpy(rng.standard_normal(V.num_dofs) * scale).to(pb.device))
+    pb.form(u.x.array)
+    frac = float(law.plastic_flag.double().mean().item())
+    assert 0.02 < frac < 0.98, frac
+    p = torch.from_numpy(rng.standard_normal(V.num_dofs)).to(pb.device)
+    assert pb._trec_valid
+    y_rec = np_(pb.J_apply(p)).copy()
+    pb.use_tangent_records = False
+    y_full = np_(pb.J_apply(p)).copy()
+    pb.use_tangent_records = True
+    assert np.abs(y_rec - y_full).max() <= 1e-12 * np.abs(y_full).max()
+    K = oracle_for(pb).tangent_matrix(np_(pb.tangent.x.array))
+    ref = K @ np_(p)
+    assert np.abs(y_rec - ref).max() <= 1e-12 * np.abs(ref).max()
+    # the unfused path invalidates the records
+    pb.fused = False
+    pb.form(u.x.array)
+    assert not pb._trec_valid
+
+
 @pytest.mark.parametrize("degree,qd,n,scale", [(2, 2, (5, 4, 3), 2e-4), (1, 1, (6, 5, 5), 4e-4), (1, 2, (3, 3, 3), 7e-4)])
 def test_fused_form_equals_unfused_and_oracle(degree, qd, n, scale):
     """fcx_mises_form == gather + trial reset + evaluate, bit for bit, and both match the oracle.
