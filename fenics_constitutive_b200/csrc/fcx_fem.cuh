@@ -67,6 +67,50 @@ __device__ __forceinline__ void grad_at_qp(const double *tabq, const double *K, 
         }
 }
 
+// grad_at_qp for QPT consecutive quadrature points of ONE cell handled by one thread: each nodal
+// increment is fetched once and used for all QPT points (per point the same operations in the
+// same order as grad_at_qp, hence the same bits).  tab0 = table of the first point; the tables of
+// consecutive points are ND*G doubles apart.
+template <int G, int ND, int QPT, class LoadDu>
+__device__ __forceinline__ void grad_at_qps(const double *tab0, const double *K, LoadDu &&du,
+                                            double (*g)[G * G])
+{
+    double T[QPT][G][G];
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq)
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                T[qq][k][j] = 0.0;
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+        double v[G];
+        du(a, v);
+#pragma unroll
+        for (int qq = 0; qq < QPT; ++qq)
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                const double d = tab0[(qq * ND + a) * G + k];
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    T[qq][k][j] = fma(d, v[j], T[qq][k][j]);
+            }
+    }
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq)
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < G; ++k)
+                    acc = fma(K[k * G + i], T[qq][k][j], acc);
+                g[qq][i * G + j] = acc;
+            }
+}
+
 // One node's G components of a blocked nodal vector (node-major, block size G).
 // G = 3: the 24-byte record is 8-byte aligned only, but one of its two halves is
 // always 16-byte aligned -- even nodes load (x, y) as a pair and z alone, odd
@@ -114,6 +158,28 @@ __device__ __forceinline__ void grad_of_increment(const double *tabq, const doub
             g);
     else
         grad_at_qp<G, ND>(tabq, K, [&](int a, double *v) { load_node<G>(u, (size_t)dm[a], v); }, g);
+}
+
+// grad_at_qps for the increment u - u_prev (see grad_of_increment).
+template <int G, int ND, int QPT>
+__device__ __forceinline__ void grads_of_increment(const double *tab0, const double *K, const int *dm,
+                                                   const double *__restrict__ u,
+                                                   const double *__restrict__ u_prev, double (*g)[G * G])
+{
+    if (u_prev != nullptr)
+        grad_at_qps<G, ND, QPT>(
+            tab0, K,
+            [&](int a, double *v) {
+                double w[G];
+                load_node<G>(u, (size_t)dm[a], v);
+                load_node<G>(u_prev, (size_t)dm[a], w);
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    v[j] -= w[j];
+            },
+            g);
+    else
+        grad_at_qps<G, ND, QPT>(tab0, K, [&](int a, double *v) { load_node<G>(u, (size_t)dm[a], v); }, g);
 }
 
 // physical basis gradient of local function a at a QP:  gphi[i] = sum_k K[k][i] * dref[k]

@@ -10,7 +10,8 @@
 // Jinv[k][i] = dX_k/dx_i:
 //     T[k][j]     = sum_a dphi_ref[q][a][k] * du[a][j]
 //     grad[i][j]  = sum_k Jinv[k][i] * T[k][j]              (grad_at_qp, fcx_fem.cuh)
-// One thread owns one QUADRATURE POINT of a tile of whole cells (64 or 96 QPs).
+// One thread owns one QUADRATURE POINT (two of a cell's four for 4-point rules) of a tile of
+// whole cells (64, 96 or 128 QPs).
 // The tile's dofmap rows and Jinv blocks are contiguous ranges and arrive by 1-D
 // bulk async copies (TMA) one tile ahead; the nodal increments are gathered
 // straight from L1/L2 (the NQ threads of a cell hit the same sectors; two load
@@ -41,7 +42,12 @@ struct GatherArgs {
 
 template <int G, int ND, int NQ>
 struct GatherCfg {
-    static constexpr int TILE = fem_tile<NQ>();
+    // QPs per thread: a thread that owns two of a cell's four points fetches every nodal increment
+    // once for both -- the kernel is bound by instruction issue (loads, address arithmetic), not
+    // by DRAM (profiles/r1n: 650 thread-instructions per QP with one point per thread).
+    static constexpr int QPT = (NQ == 4) ? 2 : 1;
+    static constexpr int THREADS = fem_tile<NQ>();
+    static constexpr int TILE = THREADS * QPT;  // QPs per tile
     static constexpr int CPT = TILE / NQ;
     static constexpr int GG = G * G;
     static constexpr int DOF_DBL = (CPT * ND + 1) / 2;
@@ -54,7 +60,8 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
     gather_kernel(const __grid_constant__ GatherArgs A)
 {
     using Cfg = GatherCfg<G, ND, NQ>;
-    constexpr int TILE = Cfg::TILE, CPT = Cfg::CPT, GG = Cfg::GG;
+    constexpr int TILE = Cfg::TILE, CPT = Cfg::CPT, GG = Cfg::GG, QPT = Cfg::QPT, NT = Cfg::THREADS;
+    constexpr int TPC = NQ / QPT;  // threads per cell
     static_assert(CPT % 16 == 0, "tile ranges must be 16-byte multiples");
     extern __shared__ __align__(128) double smem[];
     double *s_out = smem;                                   // [2][TILE][GG]
@@ -65,7 +72,7 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
     __shared__ unsigned long long s_next[2];  // slot = iteration parity (one CTA barrier per tile)
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < NQ * ND * G; i += TILE)
+    for (int i = tid; i < NQ * ND * G; i += NT)
         s_tab[i] = A.dphi_ref[i];
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -98,33 +105,27 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
             mbar_wait(bar, parity);
             parity ^= 1;
         } else {  // ragged last tile / unaligned views
-            for (int i = tid; i < ncell * GG; i += TILE)
+            for (int i = tid; i < ncell * GG; i += NT)
                 s_jinv[i] = A.Jinv[c0 * GG + i];
-            for (int i = tid; i < ncell * ND; i += TILE)
+            for (int i = tid; i < ncell * ND; i += NT)
                 s_dof[i] = A.dofmap[c0 * ND + i];
             __syncthreads();
         }
         {
-            const bool active = tid < cnt;
-            const int lc = tid / NQ, q = tid - lc * NQ;
-            double K[GG], g[GG];
+            const int lc = tid / TPC, q = (tid - lc * TPC) * QPT;  // first of this thread's QPT points
+            const int lq = lc * NQ + q;                            // tile-local QP index
+            if (lq < cnt) {                                        // whole cells: all QPT points valid
+                double K[GG], g[QPT][GG];
 #pragma unroll
-            for (int i = 0; i < GG; ++i)
-                K[i] = s_jinv[lc * GG + i];  // (idle lanes: in-bounds stage garbage, never stored)
-            if (active)
-                grad_of_increment<G, ND>(s_tab + q * ND * G, K, s_dof + lc * ND, A.u, A.u_prev, g);
-            if (active) {
-                if (bulk) {
-                    double *o = s_out + (buf * TILE + tid) * GG;
+                for (int i = 0; i < GG; ++i)
+                    K[i] = s_jinv[lc * GG + i];
+                grads_of_increment<G, ND, QPT>(s_tab + q * ND * G, K, s_dof + lc * ND, A.u, A.u_prev, g);
+                double *o = bulk ? s_out + (buf * TILE + lq) * GG : A.grad + (q0 + lq) * GG;
 #pragma unroll
-                    for (int i = 0; i < GG; ++i)
-                        o[i] = g[i];
-                } else {
-                    double *o = A.grad + (q0 + tid) * GG;
+                for (int qq = 0; qq < QPT; ++qq)
 #pragma unroll
                     for (int i = 0; i < GG; ++i)
-                        o[i] = g[i];
-                }
+                        o[qq * GG + i] = g[qq][i];
             }
         }
         if (bulk)
@@ -201,7 +202,7 @@ static int launch_gather(size_t ncells, const int *dofmap, const double *u, cons
         if (e != cudaSuccess)
             return note_cuda_error(e, "cudaFuncSetAttribute(gather)");
         int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, Cfg::TILE, Cfg::smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, Cfg::THREADS, Cfg::smem_bytes);
         if (e != cudaSuccess)
             return note_cuda_error(e, "cudaOccupancy(gather)");
         occ = o > 0 ? o : 1;
@@ -215,7 +216,7 @@ static int launch_gather(size_t ncells, const int *dofmap, const double *u, cons
     GatherArgs A{dofmap, u, u_prev, dphi, Jinv, grad, (unsigned long long)ncells,
                  (ntiles > grid) ? tile_ticket(st) : nullptr,
                  (al16(dofmap) && al16(Jinv) && al16(grad)) ? 1 : 0};
-    kern<<<(unsigned)grid, Cfg::TILE, Cfg::smem_bytes, st>>>(A);
+    kern<<<(unsigned)grid, Cfg::THREADS, Cfg::smem_bytes, st>>>(A);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return note_cuda_error(cudaGetLastError(), "gather_kernel launch");
 }

@@ -654,6 +654,85 @@ static int run_pipeline(const HostArr *arr, int narr, size_t n, Launch &&launch,
     return status[0] > 0 ? status[0] : FCX_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Constant-tangent models (LinearElasticityModel, SpringKelvinModel, SpringMaxwellModel): every
+// point gets the same s*s matrix, so the tangent -- 63 % of what elastic FULL sends back -- does not
+// cross PCIe at all: the matrix is taken from the GPU once (one point evaluated on a zero state)
+// and the host threads replicate it into the caller's array with streaming stores.
+// ---------------------------------------------------------------------------
+template <class Launch>
+static int run_pipeline_const_tangent(HostArr *arr, int narr, int tangent_idx, int ss, size_t n,
+                                      Launch &&launch)
+{
+    double *tangent = (double *)arr[tangent_idx].dst;
+    if (!g_wire || n < 4096 || ss > 36)
+        return run_pipeline(arr, narr, n, launch);
+    double tmpl[36];
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        size_t off[MAXARR], total = 0;
+        for (int a = 0; a < narr; ++a) {
+            off[a] = total;
+            total += round256(arr[a].bpq * 128);
+        }
+        int rc = ensure_ctx(total);
+        if (rc != FCX_OK)
+            return rc;
+        cudaStream_t st = g_ctx.stream[0];
+        cudaError_t e = cudaMemsetAsync(g_ctx.buf[0], 0, total, st);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaMemsetAsync(template)");
+        void *dev[MAXARR];
+        for (int a = 0; a < narr; ++a)
+            dev[a] = g_ctx.buf[0] + off[a];
+        rc = launch(dev, 1, st, g_ctx.status);
+        if (rc != FCX_OK)
+            return rc;
+        e = cudaMemcpyAsync(tmpl, dev[tangent_idx], sizeof(double) * ss, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "template download");
+    }
+    arr[tangent_idx].dst = nullptr;  // stays on the device
+    Packer P;
+    P.enqueue = [](void **, void *, void *, size_t, cudaStream_t) { return (int)FCX_OK; };
+    P.expand = [tangent, ss, &tmpl](size_t q0, size_t cnt, const void *, Group &g) {
+        Pool &pool = Pool::get();
+        const int nt = pool_threads();
+        pool.ensure(nt);
+        size_t parts = cnt / 4096;
+        if (parts < 1)
+            parts = 1;
+        if (parts > (size_t)nt)
+            parts = nt;
+        const size_t per = (cnt + parts - 1) / parts;
+        for (size_t a = 0; a < cnt; a += per) {
+            const size_t b = a + per < cnt ? a + per : cnt;
+            g.add();
+            pool.submit([=, &tmpl, &g] {
+                double *T = tangent + (q0 + a) * ss;
+                const size_t m = b - a;
+                if (ss % 2 == 0 && (reinterpret_cast<uintptr_t>(T) & 15u) == 0) {
+                    __m128d tm[18];
+                    for (int k = 0; k < ss / 2; ++k)
+                        tm[k] = _mm_loadu_pd(tmpl + 2 * k);
+                    for (size_t q = 0; q < m; ++q, T += ss)
+                        for (int k = 0; k < ss / 2; ++k)
+                            _mm_stream_pd(T + 2 * k, tm[k]);
+                    _mm_sfence();
+                } else {
+                    for (size_t q = 0; q < m; ++q, T += ss)
+                        for (int k = 0; k < ss; ++k)
+                            T[k] = tmpl[k];
+                }
+                g.done();
+            });
+        }
+    };
+    return run_pipeline(arr, narr, n, launch, &P);
+}
+
 }  // namespace fcx
 
 using namespace fcx;
@@ -741,8 +820,8 @@ int fcx_elastic_evaluate_host(int constraint, const double *D, size_t n, const d
     if (!D || !grad || !stress || !tangent)
         return FCX_ERR_NULL;
     const size_t d = sizeof(double);
-    const HostArr arr[3] = {{grad, nullptr, d * g * g}, {stress, stress, d * s}, {nullptr, tangent, d * s * s}};
-    return run_pipeline(arr, 3, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
+    HostArr arr[3] = {{grad, nullptr, d * g * g}, {stress, stress, d * s}, {nullptr, tangent, d * s * s}};
+    return run_pipeline_const_tangent(arr, 3, 2, s * s, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
         return fcx_elastic_evaluate(constraint, D, cnt, (const double *)dev[0], (double *)dev[1],
                                     (double *)dev[2], st);
     });
@@ -897,9 +976,9 @@ int fcx_kelvin_evaluate_host(int constraint, const double *D0, const double *I2,
     if (!D0 || !I2 || !grad || !stress || !tangent || !ev || !et)
         return FCX_ERR_NULL;
     const size_t d = sizeof(double);
-    const HostArr arr[5] = {{grad, nullptr, d * g * g}, {stress, stress, d * s},
-                            {nullptr, tangent, d * s * s}, {ev, ev, d * s}, {et, et, d * s}};
-    return run_pipeline(arr, 5, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
+    HostArr arr[5] = {{grad, nullptr, d * g * g}, {stress, stress, d * s},
+                      {nullptr, tangent, d * s * s}, {ev, ev, d * s}, {et, et, d * s}};
+    return run_pipeline_const_tangent(arr, 5, 2, s * s, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
         return fcx_kelvin_evaluate(constraint, D0, I2, mu0, lam0, mu1, tau, del_t, cnt,
                                    (const double *)dev[0], (double *)dev[1], (double *)dev[2],
                                    (double *)dev[3], (double *)dev[4], st);
@@ -920,9 +999,9 @@ int fcx_maxwell_evaluate_host(int constraint, const double *D0, const double *D1
     if (!D0 || !D1 || !grad || !stress || !tangent || !ev || !et)
         return FCX_ERR_NULL;
     const size_t d = sizeof(double);
-    const HostArr arr[5] = {{grad, nullptr, d * g * g}, {stress, stress, d * s},
-                            {nullptr, tangent, d * s * s}, {ev, ev, d * s}, {et, et, d * s}};
-    return run_pipeline(arr, 5, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
+    HostArr arr[5] = {{grad, nullptr, d * g * g}, {stress, stress, d * s},
+                      {nullptr, tangent, d * s * s}, {ev, ev, d * s}, {et, et, d * s}};
+    return run_pipeline_const_tangent(arr, 5, 2, s * s, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
         return fcx_maxwell_evaluate(constraint, D0, D1, mu1, tau, del_t, cnt,
                                     (const double *)dev[0], (double *)dev[1], (double *)dev[2],
                                     (double *)dev[3], (double *)dev[4], st);

@@ -14,6 +14,8 @@
 // it doubles as the free-dof mask.
 #include <cuda_runtime.h>
 
+#include <cstdint>
+
 #include "../../include/fcx.h"
 #include "fcx_internal.h"
 
@@ -67,22 +69,44 @@ __device__ __forceinline__ void finish_reduction(const double *mine, double *par
     }
 }
 
+// The reduction kernels read 16 bytes per access, two pairs per trip with independent
+// accumulators (the first, one-double-per-trip versions were latency-bound at 1.8-2.3 TB/s,
+// profiles/r1w): branch-free, fixed summation order per thread.
+
 // out[0] = sum_i p_i * Ap_i over free dofs
 __global__ void __launch_bounds__(PCG_THREADS)
     pcg_pAp_kernel(size_t n, const double *__restrict__ p, const double *__restrict__ Ap,
                    const double *__restrict__ minv, double *partials, double *out, unsigned *ticket)
 {
     __shared__ double sh[PCG_THREADS / 32];
-    double acc = 0.0;
+    const size_t n2 = n / 2;
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+    const double2 *a2 = reinterpret_cast<const double2 *>(Ap);
+    const double2 *m2 = reinterpret_cast<const double2 *>(minv);
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     const size_t stride = (size_t)gridDim.x * PCG_THREADS;
-    for (size_t i = (size_t)blockIdx.x * PCG_THREADS + threadIdx.x; i < n; i += stride)
-        if (minv[i] != 0.0)
-            acc = fma(p[i], Ap[i], acc);
-    double mine[1] = {block_sum(acc, sh)};
+    size_t i = (size_t)blockIdx.x * PCG_THREADS + threadIdx.x;
+    for (; i + stride < n2; i += 2 * stride) {
+        const double2 pa = p2[i], aa = a2[i], ma = m2[i];
+        const double2 pb = p2[i + stride], ab = a2[i + stride], mb = m2[i + stride];
+        acc0 = fma(ma.x != 0.0 ? pa.x : 0.0, aa.x, acc0);
+        acc1 = fma(ma.y != 0.0 ? pa.y : 0.0, aa.y, acc1);
+        acc2 = fma(mb.x != 0.0 ? pb.x : 0.0, ab.x, acc2);
+        acc3 = fma(mb.y != 0.0 ? pb.y : 0.0, ab.y, acc3);
+    }
+    for (; i < n2; i += stride) {
+        const double2 pa = p2[i], aa = a2[i], ma = m2[i];
+        acc0 = fma(ma.x != 0.0 ? pa.x : 0.0, aa.x, acc0);
+        acc1 = fma(ma.y != 0.0 ? pa.y : 0.0, aa.y, acc1);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+        acc0 = fma(minv[n - 1] != 0.0 ? p[n - 1] : 0.0, Ap[n - 1], acc0);
+    double mine[1] = {block_sum((acc0 + acc1) + (acc2 + acc3), sh)};
     finish_reduction<1>(mine, partials, out, ticket);
 }
 
-// alpha = rz / pAp (0 if pAp <= 0);  x += alpha p;  r = (r - alpha Ap) on free dofs;
+// alpha = rz / pAp (0 if pAp <= 0);  x += alpha p;  r -= alpha Ap  (free dofs; r is and stays 0
+// on constrained dofs: alpha is masked there);
 // out[0] = sum r.(minv r) (= rz_new),  out[1] = sum r.r
 __global__ void __launch_bounds__(PCG_THREADS)
     pcg_update_xr_kernel(size_t n, double *__restrict__ x, double *__restrict__ r,
@@ -94,21 +118,48 @@ __global__ void __launch_bounds__(PCG_THREADS)
     __shared__ double sh[PCG_THREADS / 32];
     const double den = *pAp;
     const double alpha = den > 0.0 ? *rz / den : 0.0;
-    double a0 = 0.0, a1 = 0.0;
+    const size_t n2 = n / 2;
+    double2 *x2 = reinterpret_cast<double2 *>(x);
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+    const double2 *a2 = reinterpret_cast<const double2 *>(Ap);
+    const double2 *m2 = reinterpret_cast<const double2 *>(minv);
+    double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+    auto one = [&](double m, double pv, double av, double &xv, double &rv, double &s, double &q) {
+        const double al = m != 0.0 ? alpha : 0.0;
+        xv = fma(al, pv, xv);
+        rv = fma(-al, av, rv);
+        s = fma(rv * m, rv, s);
+        q = fma(rv, rv, q);
+    };
     const size_t stride = (size_t)gridDim.x * PCG_THREADS;
-    for (size_t i = (size_t)blockIdx.x * PCG_THREADS + threadIdx.x; i < n; i += stride) {
-        const double m = minv[i];
-        if (m != 0.0) {
-            x[i] = fma(alpha, p[i], x[i]);
-            const double ri = fma(-alpha, Ap[i], r[i]);
-            r[i] = ri;
-            a0 = fma(ri * m, ri, a0);
-            a1 = fma(ri, ri, a1);
-        }
+    size_t i = (size_t)blockIdx.x * PCG_THREADS + threadIdx.x;
+    for (; i + stride < n2; i += 2 * stride) {
+        const double2 pa = p2[i], aa = a2[i], ma = m2[i];
+        const double2 pb = p2[i + stride], ab = a2[i + stride], mb = m2[i + stride];
+        double2 xa = x2[i], ra = r2[i], xb = x2[i + stride], rb = r2[i + stride];
+        one(ma.x, pa.x, aa.x, xa.x, ra.x, s0, q0);
+        one(ma.y, pa.y, aa.y, xa.y, ra.y, s1, q1);
+        one(mb.x, pb.x, ab.x, xb.x, rb.x, s0, q0);
+        one(mb.y, pb.y, ab.y, xb.y, rb.y, s1, q1);
+        x2[i] = xa;
+        r2[i] = ra;
+        x2[i + stride] = xb;
+        r2[i + stride] = rb;
     }
+    for (; i < n2; i += stride) {
+        const double2 pa = p2[i], aa = a2[i], ma = m2[i];
+        double2 xa = x2[i], ra = r2[i];
+        one(ma.x, pa.x, aa.x, xa.x, ra.x, s0, q0);
+        one(ma.y, pa.y, aa.y, xa.y, ra.y, s1, q1);
+        x2[i] = xa;
+        r2[i] = ra;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+        one(minv[n - 1], p[n - 1], Ap[n - 1], x[n - 1], r[n - 1], s0, q0);
     double mine[2];
-    mine[0] = block_sum(a0, sh);
-    mine[1] = block_sum(a1, sh);
+    mine[0] = block_sum(s0 + s1, sh);
+    mine[1] = block_sum(q0 + q1, sh);
     finish_reduction<2>(mine, partials, out, ticket);
 }
 
@@ -145,6 +196,8 @@ int fcx_pcg_pap(size_t n, const double *p, const double *Ap, const double *minv,
 {
     if (!p || !Ap || !minv || !scratch || !ticket || !out)
         return FCX_ERR_NULL;
+    if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(Ap) | reinterpret_cast<uintptr_t>(minv)) & 15u)
+        return FCX_ERR_ARG;  // vectors must be 16-byte aligned
     pcg_pAp_kernel<<<pcg_grid(n), PCG_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(n, p, Ap, minv, scratch,
                                                                                       out, ticket);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -157,6 +210,9 @@ int fcx_pcg_update_xr(size_t n, double *x, double *r, const double *p, const dou
 {
     if (!x || !r || !p || !Ap || !minv || !rz || !pAp || !scratch || !ticket || !out2)
         return FCX_ERR_NULL;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(p) |
+         reinterpret_cast<uintptr_t>(Ap) | reinterpret_cast<uintptr_t>(minv)) & 15u)
+        return FCX_ERR_ARG;  // vectors must be 16-byte aligned
     pcg_update_xr_kernel<<<pcg_grid(n), PCG_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         n, x, r, p, Ap, minv, rz, pAp, scratch, out2, ticket);
     g_launches.fetch_add(1, std::memory_order_relaxed);
