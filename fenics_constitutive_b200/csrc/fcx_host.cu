@@ -241,7 +241,7 @@ struct Packer {
     size_t dev_bytes = 0;   // device scratch per slot
     size_t wire_bytes = 0;  // pinned bytes per slot
     // enqueue the pack kernels of one chunk after the model kernel
-    std::function<int(void **dev, void *scratch, void *wire, size_t cnt, cudaStream_t st)> enqueue;
+    std::function<int(void **dev, void *scratch, void *wire, size_t q0, size_t cnt, cudaStream_t st)> enqueue;
     // expand chunk [q0, q0 + cnt) from the wire into the caller's arrays (tasks on the pool)
     std::function<void(size_t q0, size_t cnt, const void *wire, Group &g)> expand;
 };
@@ -364,7 +364,7 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
         if (rc == FCX_OK)
             rc = launch(dev, cnt, st, g_ctx.status);
         if (rc == FCX_OK && packer)
-            rc = packer->enqueue(dev, g_ctx.buf[slot] + scratch_off, g_ctx.pin[slot] + wire_off, cnt, st);
+            rc = packer->enqueue(dev, g_ctx.buf[slot] + scratch_off, g_ctx.pin[slot] + wire_off, q0, cnt, st);
         for (int a = 0; a < narr && rc == FCX_OK; ++a) {
             if (arr[a].dst) {
                 void *dst = pageable[a] ? (void *)(g_ctx.pin[slot] + pin_out[a])
@@ -411,23 +411,29 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
 
 
 // ---------------------------------------------------------------------------
-// Packed download wire of VonMises3D (fcx_mises_evaluate_host).
+// Download wire of the plastic models (VonMises3D and the comfe-rs MisesPlasticityLinearHardening3D /
+// DruckerPrager3D / DruckerPragerHyperbolic3D mirrors).
 //
-// 288 of the 392 bytes a Mises point sends back are its 6x6 tangent, and the
-// host-array path is bound by the PCIe link (49 GB/s each way on this pool,
-// profiles/r1j_pcie_probe.log).  But the tangent is bitwise symmetric
-// (ka*xioi + cpp*xpp + cnn*outer(xn, xn): products commute) and an ELASTIC point
-// has the same tangent as every other elastic point and leaves eps_n / alpha
-// untouched.  So per chunk the GPU sends
-//     stress (all points, plain DMA), one flag byte per point, and for the plastic
-//     points only a 28-double record [21 upper-triangle entries, eps_n[6], alpha],
-// compacted in point order (exclusive scan of the flags), written by the pack
-// kernel straight into the pinned ring slot; host threads mirror the triangle /
-// copy the constant elastic tangent (computed once on the GPU) into the caller's
-// arrays.  104 + 1 + 224 p bytes per point instead of 392 (p = plastic fraction).
-// Data movement only: every double the caller sees was computed on the GPU.
+// 288 of the 392 bytes a 3-D point sends back are its 6x6 tangent, and the host-array path is
+// bound by the PCIe link (49 GB/s each way on this pool, profiles/r1j_pcie_probe.log) and by what
+// the host threads can copy.  But an ELASTIC point has the same tangent as every other elastic
+// point and leaves its history untouched.  So per chunk the GPU sends
+//     stress (all points, plain DMA), one flag byte per point, and for the PLASTIC points only
+//     a record, compacted in point order (exclusive scan of the flags) and written by the pack
+//     kernel straight into the pinned ring slot (zero-copy stores over PCIe);
+// host threads scatter the records and copy the constant elastic tangent (computed once on the
+// GPU) into the caller's arrays.  Data movement only: every double the caller sees was computed
+// on the GPU.  What a record holds depends on the caller's tangent array:
+//   * page-locked (pinned / fcx_host_register) and 16-byte aligned -- DIRECT mode: a kernel
+//     stores the plastic points' 36 tangent entries straight into the caller's array through its
+//     device alias (288-byte runs of 16-byte stores over PCIe); the record is the history only
+//     (7 doubles).  PCIe: 48 + 1 + 344 p bytes per point; the host threads touch 56 p bytes of
+//     records and stream 288 (1 - p) bytes of constant tangent -- instead of reading and
+//     re-writing every tangent (mode below), which was what bound the pinned path.
+//   * pageable -- SLOT mode: record = tangent + history, where a bitwise-symmetric tangent
+//     (VonMises3D: ka*xioi + cpp*xpp + cnn*outer(xn, xn), products commute) travels as its 21
+//     upper-triangle entries and is mirrored by the host threads; others travel as all 36.
 // ---------------------------------------------------------------------------
-constexpr int WIRE_REC = 28;
 
 // pos[q] = number of plastic points before q in the chunk; *count = total.  One CTA.
 __global__ void __launch_bounds__(1024)
@@ -474,46 +480,81 @@ __global__ void __launch_bounds__(1024)
         *count_out = carry;
 }
 
-// rec[pos[q]] = [upper triangle of tangent[q] (row-major, i <= j), eps_n[q], alpha[q]] for plastic q
+// rec[pos[q]] = [tangent part of q (nt = 0: none, 21: upper triangle row-major i <= j, 36: all),
+//                h0[q][0..w0), h1[q][0..w1)]   for plastic q
 __global__ void wire_pack_kernel(const unsigned char *__restrict__ flag, const unsigned *__restrict__ pos,
-                                 const double *__restrict__ tangent, const double *__restrict__ eps,
-                                 const double *__restrict__ alpha, unsigned cnt, double *__restrict__ rec)
+                                 const double *__restrict__ tangent, int nt, const double *__restrict__ h0,
+                                 int w0, const double *__restrict__ h1, int w1, unsigned cnt,
+                                 double *__restrict__ rec)
 {
     // k -> offset of the k-th upper-triangle entry in the row-major 6x6
     const int tri[21] = {0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 14, 15, 16, 17, 21, 22, 23, 28, 29, 35};
-    const unsigned long long total = (unsigned long long)cnt * WIRE_REC;
+    const int R = nt + w0 + w1;
+    const unsigned long long total = (unsigned long long)cnt * R;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const unsigned q = (unsigned)(i / WIRE_REC);
-        const int k = (int)(i - (unsigned long long)q * WIRE_REC);
+        const unsigned q = (unsigned)(i / R);
+        const int k = (int)(i - (unsigned long long)q * R);
         if (!flag[q])
             continue;
         double v;
-        if (k < 21)
-            v = tangent[(size_t)q * 36 + tri[k]];
-        else if (k < 27)
-            v = eps[(size_t)q * 6 + (k - 21)];
+        if (k < nt)
+            v = tangent[(size_t)q * 36 + (nt == 21 ? tri[k] : k)];
+        else if (k < nt + w0)
+            v = h0[(size_t)q * w0 + (k - nt)];
         else
-            v = alpha[q];
-        rec[(size_t)pos[q] * WIRE_REC + k] = v;
+            v = h1[(size_t)q * w1 + (k - nt - w0)];
+        rec[(size_t)pos[q] * R + k] = v;
     }
 }
 
-struct MisesWire {
+// DIRECT mode: the plastic points' tangents go from the chunk buffer straight into the caller's
+// page-locked array (`dst` = its device alias at the chunk's first point), 16 bytes per thread,
+// consecutive threads on consecutive addresses (18 per point).
+__global__ void wire_direct_kernel(const unsigned char *__restrict__ flag, const double2 *__restrict__ tangent,
+                                   unsigned cnt, double2 *__restrict__ dst)
+{
+    const unsigned long long total = (unsigned long long)cnt * 18;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const unsigned q = (unsigned)(i / 18);
+        if (flag[q])
+            dst[i] = tangent[i];
+    }
+}
+
+struct PlasticWire {
     // caller arrays
-    double *tangent, *eps, *alpha;
-    unsigned char *user_flag;  // or nullptr
-    double tmpl[36];           // elastic tangent, computed on the GPU
-    size_t chunk;
+    double *tangent = nullptr;
+    double *tangent_dev = nullptr;  // device alias of `tangent` (DIRECT mode) or nullptr
+    int nt = 36;                    // tangent doubles per record: 0 (direct), 21 (triangle) or 36
+    int nh = 1;                     // history arrays scattered from the record
+    double *hist[2] = {nullptr, nullptr};
+    int hw[2] = {0, 0};
+    unsigned char *user_flag = nullptr;
+    double tmpl[36];  // elastic tangent, computed on the GPU
+    size_t chunk = 0;
+    int rec() const { return nt + hw[0] + hw[1]; }
     // wire layout inside the pinned slot
     size_t off_count() const { return 0; }
     size_t off_flag() const { return 256; }
     size_t off_rec() const { return 256 + round256(chunk); }
-    size_t wire_bytes() const { return off_rec() + chunk * WIRE_REC * sizeof(double); }
+    size_t wire_bytes() const { return off_rec() + chunk * rec() * sizeof(double); }
     size_t dev_bytes() const { return chunk * sizeof(unsigned); }
 };
 
-static void mises_wire_expand(const MisesWire &W, size_t q0, size_t cnt, const void *wire, Group &g)
+static inline void copy_doubles(double *dst, const double *src, int n, bool stream)
+{
+    if (stream && n % 2 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        for (int m = 0; m < n; m += 2)
+            _mm_stream_pd(dst + m, _mm_loadu_pd(src + m));
+    } else {
+        for (int m = 0; m < n; ++m)
+            dst[m] = src[m];
+    }
+}
+
+static void plastic_wire_expand(const PlasticWire &W, size_t q0, size_t cnt, const void *wire, Group &g)
 {
     const char *base = (const char *)wire;
     const unsigned char *flag = (const unsigned char *)(base + W.off_flag());
@@ -537,7 +578,8 @@ static void mises_wire_expand(const MisesWire &W, size_t q0, size_t cnt, const v
         pool.submit([=, &W, &g] {
             // Streaming (non-temporal) stores: the caller's arrays are written once and not read
             // here, so skipping the read-for-ownership saves a third of the host-DRAM traffic.
-            const bool nt = ((reinterpret_cast<uintptr_t>(W.tangent) | reinterpret_cast<uintptr_t>(W.eps)) & 15u) == 0;
+            const bool nts = (reinterpret_cast<uintptr_t>(W.tangent) & 15u) == 0;
+            const int R = W.rec();
             __m128d tm[18];
             for (int k = 0; k < 18; ++k)
                 tm[k] = _mm_loadu_pd(W.tmpl + 2 * k);
@@ -545,35 +587,33 @@ static void mises_wire_expand(const MisesWire &W, size_t q0, size_t cnt, const v
             for (size_t q = a; q < b; ++q) {
                 double *T = W.tangent + (q0 + q) * 36;
                 if (flag[q]) {
-                    const double *R = rec + rr * WIRE_REC;
-                    double full[36];
-                    int k = 0;
-                    for (int i = 0; i < 6; ++i)
-                        for (int j = i; j < 6; ++j, ++k) {
-                            full[i * 6 + j] = R[k];
-                            full[j * 6 + i] = R[k];
-                        }
-                    if (nt) {
-                        for (int m = 0; m < 18; ++m)
-                            _mm_stream_pd(T + 2 * m, _mm_loadu_pd(full + 2 * m));
-                        double *E = W.eps + (q0 + q) * 6;
-                        for (int m = 0; m < 3; ++m)
-                            _mm_stream_pd(E + 2 * m, _mm_loadu_pd(R + 21 + 2 * m));
-                    } else {
-                        memcpy(T, full, sizeof full);
-                        memcpy(W.eps + (q0 + q) * 6, R + 21, 6 * sizeof(double));
+                    const double *P = rec + rr * R;
+                    if (W.nt == 21) {
+                        double full[36];
+                        int k = 0;
+                        for (int i = 0; i < 6; ++i)
+                            for (int j = i; j < 6; ++j, ++k) {
+                                full[i * 6 + j] = P[k];
+                                full[j * 6 + i] = P[k];
+                            }
+                        copy_doubles(T, full, 36, nts);
+                    } else if (W.nt == 36) {
+                        copy_doubles(T, P, 36, nts);
+                    }  // nt == 0: the GPU wrote this tangent in place
+                    const double *H = P + W.nt;
+                    for (int h = 0; h < W.nh; ++h) {
+                        copy_doubles(W.hist[h] + (q0 + q) * W.hw[h], H, W.hw[h], nts && W.hw[h] > 1);
+                        H += W.hw[h];
                     }
-                    W.alpha[q0 + q] = R[27];
                     ++rr;
-                } else if (nt) {
+                } else if (nts) {
                     for (int m = 0; m < 18; ++m)
                         _mm_stream_pd(T + 2 * m, tm[m]);
                 } else {
                     memcpy(T, W.tmpl, sizeof W.tmpl);
                 }
             }
-            if (nt)
-                _mm_sfence();
+            _mm_sfence();
             if (W.user_flag)
                 memcpy(W.user_flag + q0 + a, flag + a, b - a);
             g.done();
@@ -581,7 +621,24 @@ static void mises_wire_expand(const MisesWire &W, size_t q0, size_t cnt, const v
     }
 }
 
-static int g_wire = 1;  // packed download wire for the Mises host path
+static int g_wire = 2;  // download wire of the plastic host paths: 0 off, 1 slot records only, 2 + direct tangents
+
+// Device alias of a page-locked host range (pinned allocation or cudaHostRegister), or nullptr.
+static void *device_alias(const void *p, size_t bytes)
+{
+    if (p == nullptr || bytes == 0)
+        return nullptr;
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess ||
+        cudaPointerGetAttributes(&a1, (const char *)p + bytes - 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || a0.devicePointer == nullptr ||
+        (const char *)a1.devicePointer - (const char *)a0.devicePointer != (ptrdiff_t)(bytes - 1))
+        return nullptr;
+    return a0.devicePointer;
+}
 
 // launch(dev_ptrs, q_count, stream, status_dev) enqueues the kernel for one chunk.
 template <class Launch>
@@ -696,7 +753,7 @@ static int run_pipeline_const_tangent(HostArr *arr, int narr, int tangent_idx, i
     }
     arr[tangent_idx].dst = nullptr;  // stays on the device
     Packer P;
-    P.enqueue = [](void **, void *, void *, size_t, cudaStream_t) { return (int)FCX_OK; };
+    P.enqueue = [](void **, void *, void *, size_t, size_t, cudaStream_t) { return (int)FCX_OK; };
     P.expand = [tangent, ss, &tmpl](size_t q0, size_t cnt, const void *, Group &g) {
         Pool &pool = Pool::get();
         const int nt = pool_threads();
@@ -733,6 +790,128 @@ static int run_pipeline_const_tangent(HostArr *arr, int narr, int tangent_idx, i
     return run_pipeline(arr, narr, n, launch, &P);
 }
 
+// ---------------------------------------------------------------------------
+// Host pipeline shared by the plastic models.  Chunk arrays (dev[] of `launch`):
+//   0 grad [9]   1 stress [6]   2 tangent [36]   3 history 0   4 history 1 (or unused)   5 flag
+// With the wire on, tangent / history / flag stay on the device and leave through the
+// PlasticWire (see above); otherwise every array is downloaded by plain DMA.
+// ---------------------------------------------------------------------------
+struct PlasticHost {
+    const double *grad;
+    double *stress, *tangent;
+    int nh;
+    double *hist[2];
+    int hw[2];
+    unsigned char *flag;
+    bool symmetric;  // tangent bitwise symmetric: slot records carry the upper triangle only
+};
+
+template <class Launch>
+static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
+{
+    const size_t d = sizeof(double);
+    const size_t bpq[6] = {d * 9, d * 6, d * 36, d * H.hw[0], H.nh > 1 ? d * H.hw[1] : 0, 1};
+    if (g_wire && n >= 4096) {
+        // elastic tangent as the kernel produces it: one virgin point with a zero increment
+        // (elastic for any sensible parameter set; otherwise fall through to the plain path)
+        PlasticWire W;
+        bool elastic0 = false;
+        {
+            std::lock_guard<std::mutex> lock(g_mu);
+            size_t off[6], total = 0;
+            for (int a = 0; a < 6; ++a) {
+                off[a] = total;
+                total += round256(bpq[a] * 128);
+            }
+            int rc = ensure_ctx(total);
+            if (rc != FCX_OK)
+                return rc;
+            cudaStream_t st = g_ctx.stream[0];
+            cudaError_t e = cudaMemsetAsync(g_ctx.buf[0], 0, total, st);
+            if (e != cudaSuccess)
+                return note_cuda_error(e, "cudaMemsetAsync(template)");
+            void *dev[6];
+            for (int a = 0; a < 6; ++a)
+                dev[a] = g_ctx.buf[0] + off[a];
+            rc = launch(dev, 1, st, nullptr);
+            if (rc != FCX_OK)
+                return rc;
+            unsigned char f0 = 1;
+            e = cudaMemcpyAsync(W.tmpl, dev[2], sizeof W.tmpl, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(&f0, dev[5], 1, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess)
+                e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess)
+                return note_cuda_error(e, "template download");
+            elastic0 = (f0 == 0);
+        }
+        if (elastic0) {
+            size_t chunk = g_chunk_staged < g_chunk ? g_chunk_staged : g_chunk;
+            chunk = chunk < n ? chunk : n;
+            chunk = (chunk + 127) & ~(size_t)127;
+            W.chunk = chunk;
+            W.tangent = H.tangent;
+            W.nh = H.nh;
+            for (int h = 0; h < 2; ++h) {
+                W.hist[h] = h < H.nh ? H.hist[h] : nullptr;
+                W.hw[h] = h < H.nh ? H.hw[h] : 0;
+            }
+            W.user_flag = H.flag;
+            W.nt = H.symmetric ? 21 : 36;
+            if (g_wire >= 2 && (reinterpret_cast<uintptr_t>(H.tangent) & 15u) == 0) {
+                W.tangent_dev = (double *)device_alias(H.tangent, n * 36 * d);
+                if (W.tangent_dev != nullptr && (reinterpret_cast<uintptr_t>(W.tangent_dev) & 15u) == 0)
+                    W.nt = 0;
+                else
+                    W.tangent_dev = nullptr;
+            }
+            Packer P;
+            P.dev_bytes = W.dev_bytes();
+            P.wire_bytes = W.wire_bytes();
+            P.enqueue = [&W](void **dev, void *scratch, void *wire, size_t q0, size_t cnt, cudaStream_t st) {
+                char *wb = (char *)wire;
+                unsigned *pos = (unsigned *)scratch;
+                const unsigned char *fl = (const unsigned char *)dev[5];
+                const unsigned cap = (unsigned)sm_count() * 8;
+                wire_scan_kernel<<<1, 1024, 0, st>>>(fl, (unsigned)cnt, pos, (unsigned *)(wb + W.off_count()));
+                unsigned long long work = (unsigned long long)cnt * W.rec();
+                unsigned grid = (unsigned)((work + 255) / 256);
+                wire_pack_kernel<<<grid > cap ? cap : grid, 256, 0, st>>>(
+                    fl, pos, (const double *)dev[2], W.nt, (const double *)dev[3], W.hw[0], (const double *)dev[4],
+                    W.hw[1], (unsigned)cnt, (double *)(wb + W.off_rec()));
+                g_launches.fetch_add(2, std::memory_order_relaxed);
+                if (W.tangent_dev != nullptr) {
+                    work = (unsigned long long)cnt * 18;
+                    grid = (unsigned)((work + 255) / 256);
+                    wire_direct_kernel<<<grid > cap ? cap : grid, 256, 0, st>>>(
+                        fl, (const double2 *)dev[2], (unsigned)cnt, (double2 *)(W.tangent_dev + q0 * 36));
+                    g_launches.fetch_add(1, std::memory_order_relaxed);
+                }
+                cudaError_t e = cudaGetLastError();
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(wb + W.off_flag(), fl, cnt, cudaMemcpyDeviceToHost, st);
+                return note_cuda_error(e, "plastic wire pack");
+            };
+            P.expand = [&W](size_t q0, size_t cnt, const void *wire, Group &g) {
+                plastic_wire_expand(W, q0, cnt, wire, g);
+            };
+            // tangent, history, flag: uploaded / kept on the device as before, downloaded by the wire
+            const HostArr arr[6] = {{H.grad, nullptr, bpq[0]},  {H.stress, H.stress, bpq[1]},
+                                    {nullptr, nullptr, bpq[2]}, {H.hist[0], nullptr, bpq[3]},
+                                    {H.nh > 1 ? H.hist[1] : nullptr, nullptr, bpq[4]}, {nullptr, nullptr, 1}};
+            return run_pipeline(arr, 6, n, launch, &P);
+        }
+    }
+    const HostArr arr[6] = {{H.grad, nullptr, bpq[0]},
+                            {H.stress, H.stress, bpq[1]},
+                            {nullptr, H.tangent, bpq[2]},
+                            {H.hist[0], H.hist[0], bpq[3]},
+                            {H.nh > 1 ? H.hist[1] : nullptr, H.nh > 1 ? H.hist[1] : nullptr, bpq[4]},
+                            {nullptr, H.flag, 1}};
+    return run_pipeline(arr, 6, n, launch);
+}
+
 }  // namespace fcx
 
 using namespace fcx;
@@ -759,7 +938,7 @@ int fcx_host_wire(int on)
 {
     const int old = g_wire;
     if (on >= 0)
-        g_wire = on ? 1 : 0;
+        g_wire = on > 2 ? 2 : on;
     return old;
 }
 
@@ -835,91 +1014,11 @@ int fcx_mises_evaluate_host(const double *params, size_t n, const double *grad, 
         return FCX_OK;
     if (!params || !grad || !stress || !tangent || !eps_n || !alpha)
         return FCX_ERR_NULL;
-    const size_t d = sizeof(double);
-    if (g_wire && n >= 4096) {
-        // elastic tangent as the kernel produces it: one virgin point with a zero increment
-        // (elastic whenever y0 > 0; otherwise fall through to the plain path)
-        MisesWire W{};
-        {
-            std::lock_guard<std::mutex> lock(g_mu);
-            int rc = ensure_ctx(4096);
-            if (rc != FCX_OK)
-                return rc;
-            double *z = (double *)g_ctx.buf[0];
-            cudaStream_t st = g_ctx.stream[0];
-            cudaError_t e = cudaMemsetAsync(z, 0, (9 + 6 + 36 + 6 + 1) * d + 8, st);
-            if (e != cudaSuccess)
-                return note_cuda_error(e, "cudaMemsetAsync(template)");
-            unsigned char *fl = (unsigned char *)(z + 58);
-            rc = fcx_mises_evaluate(params, 1, z, z + 9, z + 15, z + 51, z + 57, FCX_LAYOUT_AOS, fl, nullptr, st);
-            if (rc != FCX_OK)
-                return rc;
-            double host[59];
-            e = cudaMemcpyAsync(host, z, sizeof host, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess)
-                e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess)
-                return note_cuda_error(e, "template download");
-            unsigned char f0;
-            memcpy(&f0, &host[58], 1);
-            memcpy(W.tmpl, host + 15, sizeof W.tmpl);
-            if (f0 != 0)
-                W.chunk = 0;  // degenerate parameters: the zero state yields
-            else
-                W.chunk = 1;
-        }
-        if (W.chunk != 0) {
-            size_t chunk = g_chunk_staged < g_chunk ? g_chunk_staged : g_chunk;
-            chunk = chunk < n ? chunk : n;
-            chunk = (chunk + 127) & ~(size_t)127;
-            W.chunk = chunk;
-            W.tangent = tangent;
-            W.eps = eps_n;
-            W.alpha = alpha;
-            W.user_flag = plastic_flag;
-            Packer P;
-            P.dev_bytes = W.dev_bytes();
-            P.wire_bytes = W.wire_bytes();
-            P.enqueue = [&W](void **dev, void *scratch, void *wire, size_t cnt, cudaStream_t st) {
-                char *wb = (char *)wire;
-                unsigned *pos = (unsigned *)scratch;
-                const unsigned char *fl = (const unsigned char *)dev[5];
-                wire_scan_kernel<<<1, 1024, 0, st>>>(fl, (unsigned)cnt, pos, (unsigned *)(wb + W.off_count()));
-                unsigned long long work = (unsigned long long)cnt * WIRE_REC;
-                unsigned grid = (unsigned)((work + 255) / 256);
-                const unsigned cap = (unsigned)sm_count() * 8;
-                if (grid > cap)
-                    grid = cap;
-                wire_pack_kernel<<<grid, 256, 0, st>>>(fl, pos, (const double *)dev[2], (const double *)dev[3],
-                                                       (const double *)dev[4], (unsigned)cnt,
-                                                       (double *)(wb + W.off_rec()));
-                g_launches.fetch_add(2, std::memory_order_relaxed);
-                cudaError_t e = cudaGetLastError();
-                if (e == cudaSuccess)
-                    e = cudaMemcpyAsync(wb + W.off_flag(), fl, cnt, cudaMemcpyDeviceToHost, st);
-                return note_cuda_error(e, "mises wire pack");
-            };
-            P.expand = [&W](size_t q0, size_t cnt, const void *wire, Group &g) {
-                mises_wire_expand(W, q0, cnt, wire, g);
-            };
-            // tangent, eps_n, alpha, flag: uploaded / kept on the device as before, downloaded by the wire
-            const HostArr arr[6] = {{grad, nullptr, d * 9}, {stress, stress, d * 6}, {nullptr, nullptr, d * 36},
-                                    {eps_n, nullptr, d * 6}, {alpha, nullptr, d},    {nullptr, nullptr, 1}};
-            return run_pipeline(arr, 6, n, [&](void **dev, size_t cnt, cudaStream_t st, int *status) {
-                return fcx_mises_evaluate(params, cnt, (const double *)dev[0], (double *)dev[1],
-                                          (double *)dev[2], (double *)dev[3], (double *)dev[4],
-                                          FCX_LAYOUT_AOS, (unsigned char *)dev[5], status, st);
-            }, &P);
-        }
-    }
-    const HostArr arr[6] = {{grad, nullptr, d * 9}, {stress, stress, d * 6},
-                            {nullptr, tangent, d * 36}, {eps_n, eps_n, d * 6},
-                            {alpha, alpha, d}, {nullptr, plastic_flag, 1}};
-    return run_pipeline(arr, 6, n, [&](void **dev, size_t cnt, cudaStream_t st, int *status) {
+    const PlasticHost H{grad, stress, tangent, 2, {eps_n, alpha}, {6, 1}, plastic_flag, true};
+    return run_plastic_host(H, n, [&](void **dev, size_t cnt, cudaStream_t st, int *status) {
         return fcx_mises_evaluate(params, cnt, (const double *)dev[0], (double *)dev[1],
                                   (double *)dev[2], (double *)dev[3], (double *)dev[4],
-                                  FCX_LAYOUT_AOS,
-                                  plastic_flag ? (unsigned char *)dev[5] : nullptr, status, st);
+                                  FCX_LAYOUT_AOS, (unsigned char *)dev[5], status, st);
     });
 }
 
@@ -931,14 +1030,13 @@ int fcx_mises_linear_hardening_evaluate_host(const double *params, size_t n, con
         return FCX_OK;
     if (!params || !grad || !stress || !tangent || !history)
         return FCX_ERR_NULL;
-    const size_t d = sizeof(double);
-    const HostArr arr[5] = {{grad, nullptr, d * 9}, {stress, stress, d * 6},
-                            {nullptr, tangent, d * 36}, {history, history, d * 7},
-                            {nullptr, plastic_flag, 1}};
-    return run_pipeline(arr, 5, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
-        return fcx_mises_linear_hardening_evaluate(
-            params, cnt, (const double *)dev[0], (double *)dev[1], (double *)dev[2],
-            (double *)dev[3], plastic_flag ? (unsigned char *)dev[4] : nullptr, st);
+    // full 36-entry records on the slot wire: kappa*1(x)1 + c*P_dev + c'*n n^T is symmetric too, but
+    // nothing pins that bit for bit for this model, so the triangle shortcut is not taken
+    const PlasticHost H{grad, stress, tangent, 1, {history, nullptr}, {7, 0}, plastic_flag, false};
+    return run_plastic_host(H, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
+        return fcx_mises_linear_hardening_evaluate(params, cnt, (const double *)dev[0], (double *)dev[1],
+                                                   (double *)dev[2], (double *)dev[3],
+                                                   (unsigned char *)dev[5], st);
     });
 }
 
@@ -950,14 +1048,12 @@ int fcx_drucker_prager_evaluate_host(int hyperbolic, const double *params, size_
         return FCX_OK;
     if (!params || !grad || !stress || !tangent || !history)
         return FCX_ERR_NULL;
-    const size_t d = sizeof(double);
-    const HostArr arr[5] = {{grad, nullptr, d * 9}, {stress, stress, d * 6},
-                            {nullptr, tangent, d * 36}, {history, history, d * 7},
-                            {nullptr, plastic_flag, 1}};
-    return run_pipeline(arr, 5, n, [&](void **dev, size_t cnt, cudaStream_t st, int *status) {
+    // non-associated flow makes the tangent non-symmetric: full records
+    const PlasticHost H{grad, stress, tangent, 1, {history, nullptr}, {7, 0}, plastic_flag, false};
+    return run_plastic_host(H, n, [&](void **dev, size_t cnt, cudaStream_t st, int *status) {
         return fcx_drucker_prager_evaluate(hyperbolic, params, cnt, (const double *)dev[0],
                                            (double *)dev[1], (double *)dev[2], (double *)dev[3],
-                                           plastic_flag ? (unsigned char *)dev[4] : nullptr, status, st);
+                                           (unsigned char *)dev[5], status, st);
     });
 }
 

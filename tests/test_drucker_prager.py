@@ -222,14 +222,15 @@ def test_gpu_drucker_prager_vs_oracle(name, gcls, ocls, prm, n):
 
 
 @pytest.mark.gpu
-def test_gpu_drucker_prager_failure_reporting():
+@pytest.mark.parametrize("n", [1000, 20_000], ids=["plain_d2h", "download_wire"])
+def test_gpu_drucker_prager_failure_reporting(n):
     """Points where the Rust code would panic (apex assert of the classic model) raise RuntimeError on
-    both paths and keep their input stress / history; the other points are still updated."""
+    both paths and keep their input stress / history; the other points are still updated.  (The host
+    path sends n >= 4096 over the download wire of csrc/fcx_host.cu.)"""
     import torch
 
     from fenics_constitutive_b200 import models as M
 
-    n = 1000
     grad = make_grad(n, 9).reshape(n, 9)
     grad[17, [0, 4, 8]] = 0.02  # far beyond the apex
     grad = grad.ravel()

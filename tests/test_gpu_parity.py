@@ -400,15 +400,17 @@ def test_elastic_16m_linearity():
 
 # ------------------------------------------------------------------ host-memory kinds
 
-@pytest.mark.parametrize("wire", [1, 0], ids=["packed_wire", "plain_d2h"])
+@pytest.mark.parametrize("wire", [2, 1, 0], ids=["direct_wire", "slot_wire", "plain_d2h"])
 @pytest.mark.parametrize("kind", ["pageable_staged", "pageable_driver", "pinned", "registered", "mixed"])
 def test_host_path_memory_kinds(kind, wire):
     """The host entry points give bit-identical results for every kind of caller memory:
     ordinary (pageable) numpy arrays staged by the library's host-thread pool or by the driver,
     page-locked arrays, registered arrays, and a mix (per-array decision).  Chunk size lowered
-    so the ring slots wrap many times and the last chunk is ragged.  With and without the packed
-    download wire (plastic points only: upper triangle + eps_n + alpha; elastic tangents filled on
-    the host from the GPU-computed constant)."""
+    so the ring slots wrap many times and the last chunk is ragged.  With and without the download
+    wire (plastic points only; elastic tangents filled on the host from the GPU-computed constant):
+    `slot_wire` = compacted records [upper triangle, eps_n, alpha] expanded by the host threads,
+    `direct_wire` = additionally, page-locked tangent arrays get the plastic tangents stored in
+    place by a kernel through the array's device alias (records carry the history only)."""
     from fenics_constitutive_b200._lib import lib
 
     n = 300_007
@@ -455,3 +457,67 @@ def test_host_path_memory_kinds(kind, wire):
     for got, ref in zip(arrs[1:] + [law.plastic_flag], want):
         assert np.array_equal(got, ref)
     assert np.array_equal(arrs[0], grad)  # read-only input untouched
+
+
+RUST_PRM = {"mu": np.array([80769.0]), "kappa": np.array([175000.0])}
+
+
+def _rust_law(name):
+    from fenics_constitutive_b200 import models as M
+
+    if name == "mises_lin":
+        return M.MisesPlasticityLinearHardening3D({**RUST_PRM, "y_0": np.array([1200.0]), "h": np.array([200.0])})
+    prm = {**RUST_PRM, "a": np.array([300.0]), "b": np.array([0.05]), "b_flow": np.array([0.01])}
+    if name == "dp_hyperbolic":
+        prm["d"] = np.array([40.0])
+        return M.DruckerPragerHyperbolic3D(prm)
+    return M.DruckerPrager3D(prm)
+
+
+@pytest.mark.parametrize("wire", [2, 1, 0], ids=["direct_wire", "slot_wire", "plain_d2h"])
+@pytest.mark.parametrize("kind", ["pageable", "pinned", "tangent_pinned"])
+@pytest.mark.parametrize("name", ["mises_lin", "dp_classic", "dp_hyperbolic"])
+def test_host_path_wire_rust_models(name, kind, wire):
+    """Same as test_host_path_memory_kinds for the comfe-rs plastic mirrors (one [n][7] history
+    array; non-symmetric Drucker-Prager tangents travel as full 36-entry records on the slot
+    wire): two consecutive increments, every array bit-identical to the device path."""
+    from fenics_constitutive_b200._lib import lib
+
+    n = 150_001
+    rng = np.random.default_rng(5)
+
+    def increment(f):
+        if name == "mises_lin":
+            return rng.standard_normal(n * 9) * 2.9e-3 * f
+        g = rng.standard_normal((n, 9)) * 1.7e-3 * f  # deviator-dominated: far from the cone's apex
+        g[:, [0, 4, 8]] = rng.standard_normal((n, 3)) * 4e-4 * f
+        return g.ravel()
+
+    grads = [increment(1.0), increment(0.5)]
+    law = _rust_law(name)
+    law.record_plastic_flag = True
+    d = [torch.zeros(n * 6, dtype=torch.float64, device="cuda"),
+         torch.full((n * 36,), float("nan"), dtype=torch.float64, device="cuda"),
+         torch.zeros(n * 7, dtype=torch.float64, device="cuda")]
+    arrs = [np.zeros(n * 6), np.full(n * 36, np.nan), np.zeros(n * 7)]
+    keep = []
+    for i in ((0, 1, 2) if kind == "pinned" else (1,) if kind == "tangent_pinned" else ()):
+        t = torch.from_numpy(arrs[i].copy()).pin_memory()
+        keep.append(t)
+        arrs[i] = t.numpy()
+    L = lib()
+    old_chunk = L.fcx_host_chunk_qps(40_000)
+    old_wire = L.fcx_host_wire(wire)
+    try:
+        for step, g in enumerate(grads):
+            law.evaluate(0.0, 1.0, dev(g), d[0], d[1], {"history": d[2]})
+            torch.cuda.synchronize()
+            want_flag = law.plastic_flag.cpu().numpy()
+            assert 0.1 < want_flag.mean() < 0.9
+            law.evaluate(0.0, 1.0, g, arrs[0], arrs[1], {"history": arrs[2]})
+            assert np.array_equal(law.plastic_flag, want_flag), f"flag step {step}"
+            for got, ref, what in zip(arrs, d, ("stress", "tangent", "history")):
+                assert np.array_equal(got, ref.cpu().numpy()), f"{what} step {step}"
+    finally:
+        L.fcx_host_chunk_qps(old_chunk)
+        L.fcx_host_wire(old_wire)
