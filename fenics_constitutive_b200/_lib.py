@@ -58,6 +58,8 @@ SIGNATURES = {
     "fcx_host_staging": (_ci, [_ci]),
     "fcx_host_threads": (_ci, [_ci]),
     "fcx_host_wire": (_ci, [_ci]),
+    "fcx_host_trace": (_ci, [_ci]),
+    "fcx_host_stats": (_ci, [_vp, _ci]),
     "fcx_host_chunk_qps": (_sz, [_sz]),
     "fcx_host_release": (None, []),
     "fcx_launch_count": (ctypes.c_ulonglong, []),

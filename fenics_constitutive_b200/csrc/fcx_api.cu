@@ -60,6 +60,7 @@ static int g_mises_tile = 64;  // QPs per tile of the output-staged kernel (64 o
 // Hand tiles out through an atomic ticket counter (all tile kernels).
 static int g_dynamic_tiles = 1;
 static int g_fem_variant = 1;
+static int g_gather_variant = 1;  // 1 = nodal values staged by cp.async one tile ahead (gather_staged_kernel)
 static int g_hints = 8;  // bit1: evict_first on bulk loads, bit2: on bulk stores,
                          // bit3: constant tangents written by bulk stores from shared memory
 
@@ -104,6 +105,7 @@ unsigned long long *tile_ticket(cudaStream_t stream)
 }
 int tuned_ctas_per_sm() { return g_ctas_per_sm; }
 int fem_variant() { return g_fem_variant; }
+int gather_variant() { return g_gather_variant; }
 
 template <class M, int TILE>
 static int launch_tile_t(const typename M::Params &prm, const SegPtrs<M::nseg()> &io,
@@ -452,6 +454,12 @@ int fcx_tune(const char *key, int value)
         const int old = g_fem_variant;
         if (value >= 0)  // negative = query
             g_fem_variant = value;
+        return old;
+    }
+    if (key && strcmp(key, "gather_variant") == 0) {
+        const int old = g_gather_variant;
+        if (value >= 0)  // negative = query
+            g_gather_variant = value;
         return old;
     }
     if (key && strcmp(key, "tile") == 0) {

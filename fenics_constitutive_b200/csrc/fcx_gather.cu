@@ -153,6 +153,153 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
         bulk_wait_read_all();
 }
 
+// ---------------------------------------------------------------------------
+// gather_staged_kernel: the same map with the NODAL VALUES staged one tile ahead.
+//
+// gather_kernel above is bound by the latency of its nodal loads: 16 resident warps per SM
+// (100 registers, 23 KB of shared memory per 64-thread CTA) each waiting on L2 most of the time
+// (ncu profiles/r1y: 9 of 11 stall cycles per issue are long-scoreboard, DRAM at 33 %, issue
+// slots at 30 %).  Here the gathers are per-thread 8-byte cp.async copies (LDGSTS) into shared
+// memory -- they cost an issue slot but no register and no stall -- issued for tile i+1 while
+// tile i is computed, so a CTA keeps a whole tile of nodal values (7.7 KB for 32 P2 tets) in
+// flight all the time:
+//     A(i): bulk copies of dofmap / Jinv rows of tile i            (thread 0, two tiles ahead)
+//     B(i): cp.async of du[dofmap(i)] -> s_du[i & 1]               (all threads, one tile ahead)
+//     C(i): grad_at_qps from shared memory -> s_out, one bulk store
+// Same fma chains in the same order as gather_kernel (grad_at_qps), hence the same bits.
+// Whole 16-byte-aligned tiles only; launch_gather sends the ragged tail (and unaligned views)
+// to gather_kernel.
+// ---------------------------------------------------------------------------
+template <int G, int ND, int NQ, bool PREV>
+struct StagedCfg {
+    using Base = GatherCfg<G, ND, NQ>;
+    static constexpr int NDU = Base::CPT * ND * G;  // nodal doubles per tile
+    static constexpr int NVEC = PREV ? 2 : 1;
+    static constexpr int DOF_DBL = Base::DOF_DBL;
+    static constexpr size_t smem_bytes =
+        sizeof(double) * ((size_t)Base::TILE * Base::GG + 2 * NVEC * NDU + 3 * Base::CPT * Base::GG +
+                          3 * DOF_DBL + NQ * ND * G + 4);
+};
+
+template <int G, int ND, int NQ, bool PREV>
+__global__ void __launch_bounds__(fem_tile<NQ>())
+    gather_staged_kernel(const __grid_constant__ GatherArgs A)
+{
+    using Cfg = GatherCfg<G, ND, NQ>;
+    using SC = StagedCfg<G, ND, NQ, PREV>;
+    constexpr int TILE = Cfg::TILE, CPT = Cfg::CPT, GG = Cfg::GG, QPT = Cfg::QPT, NT = Cfg::THREADS;
+    constexpr int TPC = NQ / QPT, NDU = SC::NDU, NVEC = SC::NVEC;
+    static_assert(CPT % 16 == 0, "tile ranges must be 16-byte multiples");
+    extern __shared__ __align__(128) double smem[];
+    double *s_out = smem;                          // [TILE][GG]
+    double *s_du = s_out + TILE * GG;              // [2][NVEC][NDU]
+    double *s_jinv = s_du + 2 * NVEC * NDU;        // [3][CPT][GG]
+    double *s_dofd = s_jinv + 3 * CPT * GG;        // [3][CPT][ND] ints
+    double *s_tab = s_dofd + 3 * SC::DOF_DBL;      // [NQ][ND][G]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_tab + NQ * ND * G);  // [3]
+    __shared__ unsigned long long s_tile[4];
+    auto dof_slot = [&](int s) { return reinterpret_cast<int *>(s_dofd + s * SC::DOF_DBL); };
+
+    const int tid = threadIdx.x;
+    const unsigned long long ntiles = A.ncells / CPT;  // whole tiles only
+    for (int i = tid; i < NQ * ND * G; i += NT)
+        s_tab[i] = A.dphi_ref[i];
+    auto issue_A = [&](unsigned long long t, int s) {
+        const unsigned long long c0 = t * CPT;
+        mbar_arrive_expect_tx(bar + s, (uint32_t)(sizeof(double) * CPT * GG + sizeof(int) * CPT * ND));
+        bulk_g2s(s_jinv + s * CPT * GG, A.Jinv + c0 * GG, (uint32_t)(sizeof(double) * CPT * GG), bar + s);
+        bulk_g2s(dof_slot(s), A.dofmap + c0 * ND, (uint32_t)(sizeof(int) * CPT * ND), bar + s);
+    };
+    auto next_ticket = [&]() -> unsigned long long {
+        return gridDim.x + atomicAdd(A.ticket, 1ULL);
+    };
+    auto issue_B = [&](int s, int b) {
+        const int *dm = dof_slot(s);
+        double *dst = s_du + b * NVEC * NDU;
+        for (int e = tid; e < NDU; e += NT) {
+            const int cn = e / G, j = e - cn * G;
+            const size_t src = (size_t)dm[cn] * G + j;
+            cp_async_8(dst + e, A.u + src);
+            if (PREV)
+                cp_async_8(dst + NDU + e, A.u_prev + src);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < 3; ++s)
+            mbar_init(bar + s, 1);
+        fence_mbar_init();
+        const unsigned long long t0 = blockIdx.x, t1 = next_ticket();
+        s_tile[0] = t0;
+        s_tile[1] = t1;
+        issue_A(t0, 0);  // grid <= ntiles: the first tile always exists
+        if (t1 < ntiles)
+            issue_A(t1, 1);
+    }
+    __syncthreads();
+    uint32_t phase = 0;  // bit s = parity of the next completion of bar[s]
+    mbar_wait(bar + 0, 0);
+    phase ^= 1u;
+    issue_B(0, 0);
+    cp_async_commit();
+
+    for (int i = 0;; ++i) {
+        const unsigned long long tile = s_tile[i & 3];
+        if (tile >= ntiles)
+            break;
+        const int s0 = i % 3, s1 = (i + 1) % 3, s2 = (i + 2) % 3;
+        if (tid == 0) {
+            const unsigned long long t2 = next_ticket();
+            s_tile[(i + 2) & 3] = t2;
+            if (t2 < ntiles)
+                issue_A(t2, s2);
+        }
+        const unsigned long long tile1 = s_tile[(i + 1) & 3];
+        if (tile1 < ntiles) {
+            mbar_wait(bar + s1, (phase >> s1) & 1u);
+            phase ^= 1u << s1;
+            issue_B(s1, (i + 1) & 1);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();  // this thread's share of B(i) has landed
+        if (tid == 0)
+            bulk_wait_read_all();  // the previous tile's store has left s_out
+        __syncthreads();           // B(i) complete for every thread; s_out free
+        {
+            const int lc = tid / TPC, q = (tid - lc * TPC) * QPT;
+            const int lq = lc * NQ + q;
+            double K[GG], g[QPT][GG];
+            const double *kin = s_jinv + s0 * CPT * GG + lc * GG;
+#pragma unroll
+            for (int k = 0; k < GG; ++k)
+                K[k] = kin[k];
+            const double *du = s_du + (i & 1) * NVEC * NDU + lc * ND * G;
+            grad_at_qps<G, ND, QPT>(
+                s_tab + q * ND * G, K,
+                [&](int a, double *v) {
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+                        v[j] = PREV ? du[a * G + j] - du[NDU + a * G + j] : du[a * G + j];
+                },
+                g);
+            double *o = s_out + lq * GG;
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq)
+#pragma unroll
+                for (int k = 0; k < GG; ++k)
+                    o[qq * GG + k] = g[qq][k];
+        }
+        fence_proxy_async_smem();
+        __syncthreads();  // results staged; s_du[i & 1], Jinv slot s0 consumed
+        if (tid == 0) {
+            bulk_s2g(A.grad + tile * TILE * GG, s_out, (uint32_t)(sizeof(double) * TILE * GG));
+            bulk_commit();
+        }
+    }
+    cp_async_wait<0>();
+    if (tid == 0)
+        bulk_wait_read_all();
+}
+
 // Generic fallback for element/quadrature combinations without a compiled
 // specialisation: one thread per (cell, qp), runtime loops.
 __global__ void gather_generic_kernel(int G, int nq, int nd, const int *__restrict__ dofmap,
@@ -190,8 +337,8 @@ __global__ void gather_generic_kernel(int G, int nq, int nd, const int *__restri
 }
 
 template <int G, int ND, int NQ>
-static int launch_gather(size_t ncells, const int *dofmap, const double *u, const double *u_prev,
-                         const double *dphi, const double *Jinv, double *grad, cudaStream_t st)
+static int launch_gather_plain(size_t ncells, const int *dofmap, const double *u, const double *u_prev,
+                               const double *dphi, const double *Jinv, double *grad, cudaStream_t st)
 {
     using Cfg = GatherCfg<G, ND, NQ>;
     auto kern = gather_kernel<G, ND, NQ>;
@@ -219,6 +366,60 @@ static int launch_gather(size_t ncells, const int *dofmap, const double *u, cons
     kern<<<(unsigned)grid, Cfg::THREADS, Cfg::smem_bytes, st>>>(A);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return note_cuda_error(cudaGetLastError(), "gather_kernel launch");
+}
+
+template <int G, int ND, int NQ, bool PREV>
+static int launch_gather_staged(size_t nfull_cells, const int *dofmap, const double *u, const double *u_prev,
+                                const double *dphi, const double *Jinv, double *grad, cudaStream_t st)
+{
+    using Cfg = GatherCfg<G, ND, NQ>;
+    using SC = StagedCfg<G, ND, NQ, PREV>;
+    auto kern = gather_staged_kernel<G, ND, NQ, PREV>;
+    static int occ = -1;
+    if (occ < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)SC::smem_bytes);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaFuncSetAttribute(gather staged)");
+        int o = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, Cfg::THREADS, SC::smem_bytes);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaOccupancy(gather staged)");
+        occ = o > 0 ? o : 1;
+    }
+    const unsigned long long ntiles = nfull_cells / Cfg::CPT;
+    const int per_sm = tuned_ctas_per_sm() > 0 ? tuned_ctas_per_sm() : occ;
+    unsigned long long grid = (unsigned long long)sm_count() * per_sm;
+    if (grid > ntiles)
+        grid = ntiles;
+    unsigned long long *ticket = tile_ticket(st);
+    if (ticket == nullptr)
+        return -1;  // dynamic tiles switched off: caller falls back to gather_kernel
+    GatherArgs A{dofmap, u, u_prev, dphi, Jinv, grad, (unsigned long long)nfull_cells, ticket, 1};
+    kern<<<(unsigned)grid, Cfg::THREADS, SC::smem_bytes, st>>>(A);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "gather_staged_kernel launch");
+}
+
+template <int G, int ND, int NQ>
+static int launch_gather(size_t ncells, const int *dofmap, const double *u, const double *u_prev,
+                         const double *dphi, const double *Jinv, double *grad, cudaStream_t st)
+{
+    using Cfg = GatherCfg<G, ND, NQ>;
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const size_t nfull = ncells / Cfg::CPT * Cfg::CPT;
+    // staged kernel (fcx_tune "gather_variant" 1): whole aligned tiles
+    if (gather_variant() >= 1 && nfull >= (size_t)Cfg::CPT * 4 && al16(dofmap) && al16(Jinv) && al16(grad)) {
+        int rc = u_prev ? launch_gather_staged<G, ND, NQ, true>(nfull, dofmap, u, u_prev, dphi, Jinv, grad, st)
+                        : launch_gather_staged<G, ND, NQ, false>(nfull, dofmap, u, u_prev, dphi, Jinv, grad, st);
+        if (rc != -1) {
+            if (rc != FCX_OK || nfull == ncells)
+                return rc;
+            return launch_gather_plain<G, ND, NQ>(ncells - nfull, dofmap + nfull * ND, u, u_prev, dphi,
+                                                  Jinv + nfull * G * G, grad + nfull * NQ * G * G, st);
+        }
+    }
+    return launch_gather_plain<G, ND, NQ>(ncells, dofmap, u, u_prev, dphi, Jinv, grad, st);
 }
 
 }  // namespace fcx

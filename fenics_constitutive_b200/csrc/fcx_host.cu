@@ -21,6 +21,7 @@
 #include <emmintrin.h>  // SSE2 streaming stores (x86-64 baseline) for the wire expansion
 
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <condition_variable>
 #include <cstdint>
@@ -62,6 +63,24 @@ static size_t g_chunk = (size_t)1 << 18;
 static size_t g_chunk_staged = (size_t)1 << 16;  // smaller chunks: the ring slots are pinned memory
 static int g_staging = 1;                        // stage pageable arrays with the host-thread pool
 static int g_threads = 0;                        // 0 = auto
+
+// Phase timings of the last staged / wire pipeline run (fcx_host_stats): where the wall time of a
+// host-array call goes.  GPU phases are per-chunk event intervals summed over chunks (they overlap
+// across the three streams, so their sum may exceed the wall time).
+struct HostStats {
+    double total_s = 0, main_wait_slot_s = 0, main_stage_in_s = 0, main_enqueue_s = 0;
+    double drain_event_wait_s = 0, drain_expand_s = 0;
+    double gpu_h2d_s = 0, gpu_kernel_s = 0, gpu_pack_s = 0, gpu_d2h_s = 0;
+    double chunks = 0, chunk_qps = 0;
+};
+static HostStats g_stats;
+static int g_trace = 0;  // fcx_host_trace(1): also record per-chunk GPU phase events
+static cudaEvent_t g_tev[NSLOT][5] = {};
+
+static inline double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // ---- host-thread pool (memcpy only) -----------------------------------------
 class Pool {
@@ -288,6 +307,15 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
         return note_cuda_error(e, "cudaMemcpy(status init)");
     int device = 0;
     cudaGetDevice(&device);
+    HostStats S;
+    S.chunk_qps = (double)chunk;
+    const bool trace = g_trace != 0;
+    if (trace)
+        for (int s = 0; s < NSLOT; ++s)
+            for (int k = 0; k < 5; ++k)
+                if (g_tev[s][k] == nullptr)
+                    cudaEventCreate(&g_tev[s][k]);
+    const double t_begin = now_s();
 
     struct Item {
         size_t q0, cnt;
@@ -312,9 +340,21 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
                 it = queue.front();
                 queue.pop_front();
             }
+            const double t0 = now_s();
             cudaError_t de = cudaEventSynchronize(g_ctx.done[it.slot]);
+            const double t1 = now_s();
+            S.drain_event_wait_s += t1 - t0;
             if (de != cudaSuccess && drain_rc == FCX_OK)
                 drain_rc = note_cuda_error(de, "cudaEventSynchronize(chunk)");
+            if (de == cudaSuccess && trace) {
+                float ms[4] = {0, 0, 0, 0};
+                for (int k = 0; k < 4; ++k)
+                    cudaEventElapsedTime(&ms[k], g_tev[it.slot][k], g_tev[it.slot][k + 1]);
+                S.gpu_h2d_s += 1e-3 * ms[0];
+                S.gpu_kernel_s += 1e-3 * ms[1];
+                S.gpu_pack_s += 1e-3 * ms[2];
+                S.gpu_d2h_s += 1e-3 * ms[3];
+            }
             if (de == cudaSuccess) {
                 Group g;
                 for (int a = 0; a < narr; ++a)
@@ -324,6 +364,7 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
                 if (packer)
                     packer->expand(it.q0, it.cnt, g_ctx.pin[it.slot] + wire_off, g);
                 g.wait();
+                S.drain_expand_s += now_s() - t1;
             }
             {
                 std::lock_guard<std::mutex> l(mu);
@@ -336,11 +377,15 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
     int slot = 0;
     for (size_t q0 = 0; q0 < n && rc == FCX_OK; q0 += chunk, slot = (slot + 1) % NSLOT) {
         const size_t cnt = (n - q0 < chunk) ? n - q0 : chunk;
+        const double tw0 = now_s();
         {
             std::unique_lock<std::mutex> l(mu);
             cv.wait(l, [&] { return !slot_busy[slot]; });
             slot_busy[slot] = true;
         }
+        const double tw1 = now_s();
+        S.main_wait_slot_s += tw1 - tw0;
+        S.chunks += 1;
         {
             Group g;  // stage-in: caller's pageable arrays -> pinned slot
             for (int a = 0; a < narr; ++a)
@@ -349,7 +394,11 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
                                   cnt * arr[a].bpq, g);
             g.wait();
         }
+        const double tw2 = now_s();
+        S.main_stage_in_s += tw2 - tw1;
         cudaStream_t st = g_ctx.stream[slot];
+        if (trace)
+            cudaEventRecord(g_tev[slot][0], st);
         void *dev[MAXARR];
         for (int a = 0; a < narr && rc == FCX_OK; ++a) {
             dev[a] = g_ctx.buf[slot] + off[a];
@@ -361,10 +410,16 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
                     rc = note_cuda_error(e, "cudaMemcpyAsync(H2D)");
             }
         }
+        if (trace)
+            cudaEventRecord(g_tev[slot][1], st);
         if (rc == FCX_OK)
             rc = launch(dev, cnt, st, g_ctx.status);
+        if (trace)
+            cudaEventRecord(g_tev[slot][2], st);
         if (rc == FCX_OK && packer)
             rc = packer->enqueue(dev, g_ctx.buf[slot] + scratch_off, g_ctx.pin[slot] + wire_off, q0, cnt, st);
+        if (trace)
+            cudaEventRecord(g_tev[slot][3], st);
         for (int a = 0; a < narr && rc == FCX_OK; ++a) {
             if (arr[a].dst) {
                 void *dst = pageable[a] ? (void *)(g_ctx.pin[slot] + pin_out[a])
@@ -374,6 +429,8 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
                     rc = note_cuda_error(e, "cudaMemcpyAsync(D2H)");
             }
         }
+        if (trace)
+            cudaEventRecord(g_tev[slot][4], st);
         if (rc == FCX_OK) {
             e = cudaEventRecord(g_ctx.done[slot], st);
             if (e != cudaSuccess)
@@ -386,6 +443,7 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
             }
             cv.notify_all();
         }
+        S.main_enqueue_s += now_s() - tw2;
     }
     {
         std::lock_guard<std::mutex> l(mu);
@@ -398,6 +456,8 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
         if (e != cudaSuccess && rc == FCX_OK)
             rc = note_cuda_error(e, "cudaStreamSynchronize");
     }
+    S.total_s = now_s() - t_begin;
+    g_stats = S;
     if (rc != FCX_OK)
         return rc;
     if (drain_rc != FCX_OK)
@@ -940,6 +1000,26 @@ int fcx_host_wire(int on)
     if (on >= 0)
         g_wire = on > 2 ? 2 : on;
     return old;
+}
+
+int fcx_host_trace(int on)
+{
+    const int old = g_trace;
+    if (on >= 0)
+        g_trace = on ? 1 : 0;
+    return old;
+}
+
+int fcx_host_stats(double *out, int n)
+{
+    const double v[12] = {g_stats.total_s, g_stats.main_wait_slot_s, g_stats.main_stage_in_s, g_stats.main_enqueue_s,
+                          g_stats.drain_event_wait_s, g_stats.drain_expand_s, g_stats.gpu_h2d_s, g_stats.gpu_kernel_s,
+                          g_stats.gpu_pack_s, g_stats.gpu_d2h_s, g_stats.chunks, g_stats.chunk_qps};
+    if (!out)
+        return FCX_ERR_NULL;
+    for (int i = 0; i < n && i < 12; ++i)
+        out[i] = v[i];
+    return 12;
 }
 
 int fcx_host_threads(int n)

@@ -16,4 +16,6 @@ unsigned long long *tile_ticket(cudaStream_t stream);
 // (1 = QP-parallel bulk-staged FEM kernels, 0 = one-thread-per-cell kernels).
 int tuned_ctas_per_sm();
 int fem_variant();
+// fcx_tune "gather_variant": 1 = gather_staged_kernel (cp.async-staged nodal values), 0 = gather_kernel.
+int gather_variant();
 }  // namespace fcx

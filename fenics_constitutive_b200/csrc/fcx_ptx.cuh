@@ -121,6 +121,25 @@ __device__ __forceinline__ void fence_proxy_async_smem()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// Per-thread 8-byte async copy global -> shared (SASS LDGSTS): no register staging, no scoreboard
+// stall; completion is tracked by the issuing thread's cp.async groups.  L1-allocating (.ca): the
+// FEM kernels gather nodal values that neighbouring cells of the same tile share.
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)),
+                 "l"(__cvta_generic_to_global(gmem_src))
+                 : "memory");
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+// Wait until at most N of this thread's most recent cp.async groups are still pending.
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // Streaming 16-byte global store (two doubles), no L1 allocation.
 __device__ __forceinline__ void st_stream_v2(double *p, double a, double b)
 {

@@ -292,12 +292,20 @@ int fcx_host_unregister(void *ptr);
  * size (0 = query; default min(16, cores - 2)).  Both return the old value. */
 int fcx_host_staging(int on);
 int fcx_host_threads(int n);
-/* fcx_mises_evaluate_host sends its results over a packed wire (stress for every point, a flag
- * byte, and for PLASTIC points only the 21 upper-triangle tangent entries + eps_n + alpha; the
- * host threads mirror the triangle and copy the constant elastic tangent -- bit-identical
- * arrays, 104 + 1 + 224 p bytes per point over PCIe instead of 392).  0 = plain D2H of every
- * array, -1 = query; returns the old value. */
+/* The plastic models' *_host entry points send their results over a download wire (stress for
+ * every point, a flag byte, and for PLASTIC points only a compacted record; the host threads
+ * scatter the records and copy the constant elastic tangent -- bit-identical arrays).
+ * 1 = records carry tangent (VonMises3D: its 21 upper-triangle entries) + history;
+ * 2 (default) = additionally, a page-locked caller tangent array gets the plastic tangents stored
+ * in place by a kernel through its device alias, records carry the history only;
+ * 0 = plain D2H of every array, -1 = query; returns the old value. */
 int fcx_host_wire(int on);
+/* Where the wall time of the last staged / wire host call went: out[0..12) = total_s,
+ * main_wait_slot_s, main_stage_in_s, main_enqueue_s, drain_event_wait_s, drain_expand_s,
+ * gpu_h2d_s, gpu_kernel_s, gpu_pack_s, gpu_d2h_s (per-chunk event intervals summed over chunks;
+ * recorded only after fcx_host_trace(1)), chunks, chunk_qps.  Returns 12. */
+int fcx_host_stats(double *out, int n);
+int fcx_host_trace(int on);
 /* QPs per pipeline chunk of the *_host entry points (default 1<<18); 0 = query. */
 size_t fcx_host_chunk_qps(size_t new_value);
 /* Release the streams / staging buffers cached by the *_host entry points. */

@@ -121,3 +121,41 @@ def test_gpu_gather_feeds_evaluate():
     from _util import TOL_PLASTIC, assert_close
     assert_close(st.cpu().numpy(), ref[0], 6, TOL_PLASTIC, "stress")
     assert_close(tg.cpu().numpy(), ref[1], 36, TOL_PLASTIC, "tangent")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gdim,degree,qdeg,ncells", [(3, 2, 2, 40_007), (3, 2, 2, 4 * 32), (3, 1, 1, 9_001), (3, 1, 2, 5_000),
+                                                      (2, 2, 2, 7_777), (2, 1, 2, 3_333), (1, 2, 2, 2_049), (1, 1, 1, 1_000)])
+@pytest.mark.parametrize("with_prev", [True, False])
+def test_gpu_gather_staged_kernel_bitwise(gdim, degree, qdeg, ncells, with_prev):
+    """gather_staged_kernel (nodal values staged by cp.async one tile ahead, fcx_tune
+    "gather_variant" 1, the default) runs the same fma chains as gather_kernel: bit-identical
+    output, ragged tails and many tiles per CTA included; and both match the oracle."""
+    import torch
+
+    from fenics_constitutive_b200._lib import lib
+
+    rng = np.random.default_rng(ncells)
+    pts, _ = G.simplex_quadrature(gdim, qdeg)
+    dphi = G.lagrange_gradients(gdim, degree, pts)
+    nd = dphi.shape[1]
+    nnodes = max(50, ncells // 3)
+    dofmap = rng.integers(0, nnodes, size=(ncells, nd)).astype(np.int32)
+    Jinv = rng.standard_normal((ncells, gdim, gdim)) + 3 * np.eye(gdim)
+    u = rng.standard_normal(nnodes * gdim)
+    u_prev = rng.standard_normal(nnodes * gdim) if with_prev else None
+    op = G.IncrementalGradient(gdim, dofmap, dphi, Jinv)
+    L = lib()
+    outs = []
+    old = L.fcx_tune(b"gather_variant", -1)
+    try:
+        for variant in (0, 1, 1):
+            L.fcx_tune(b"gather_variant", variant)
+            out = torch.full((op.num_qps * gdim * gdim,), float("nan"), dtype=torch.float64, device="cuda")
+            op.evaluate(torch.from_numpy(u).cuda(), torch.from_numpy(u_prev).cuda() if with_prev else None, out)
+            outs.append(out.cpu().numpy())
+    finally:
+        L.fcx_tune(b"gather_variant", old)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2])
+    ref = om.gather_grad(gdim, dofmap, u, u_prev, dphi, Jinv)
+    assert np.max(np.abs(outs[1] - ref)) <= 1e-12 * np.abs(ref).max()
