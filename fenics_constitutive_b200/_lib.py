@@ -59,6 +59,7 @@ SIGNATURES = {
     "fcx_host_threads": (_ci, [_ci]),
     "fcx_host_wire": (_ci, [_ci]),
     "fcx_host_trace": (_ci, [_ci]),
+    "fcx_host_slots": (_ci, [_ci]),
     "fcx_host_stats": (_ci, [_vp, _ci]),
     "fcx_host_chunk_qps": (_sz, [_sz]),
     "fcx_host_release": (None, []),

@@ -2,7 +2,7 @@
 //
 // This is the path a CPU-side caller takes: dolfinx hands `law.evaluate` host
 // numpy arrays (reference solver/_lawonsubmesh.py:86-94).  The QP axis is cut
-// into chunks; chunk c runs entirely on stream c % NSLOT:
+// into chunks; chunk c runs entirely on stream c % nslot (fcx_host_slots, default 6):
 //     H2D(inputs of c) -> kernel(c) -> D2H(outputs of c)
 // so the upload of chunk c+1, the kernel of chunk c and the download of chunk
 // c-1 overlap on the two copy engines and the SMs.  Stream order alone makes
@@ -37,7 +37,7 @@
 
 namespace fcx {
 
-constexpr int NSLOT = 3;
+constexpr int NSLOT = 8;  // maximum; g_nslot of them are used
 constexpr int MAXARR = 8;
 
 struct HostArr {
@@ -47,12 +47,14 @@ struct HostArr {
 };
 
 struct HostCtx {
-    cudaStream_t stream[NSLOT] = {nullptr, nullptr, nullptr};
-    char *buf[NSLOT] = {nullptr, nullptr, nullptr};
+    cudaStream_t stream[NSLOT] = {};
+    char *buf[NSLOT] = {};
     size_t cap = 0;  // bytes per slot
-    char *pin[NSLOT] = {nullptr, nullptr, nullptr};  // pinned ring slots (pageable callers)
+    int nbuf = 0;    // slots that have a device buffer of `cap` bytes
+    char *pin[NSLOT] = {};  // pinned ring slots (pageable callers, wire records)
     size_t pin_cap = 0;
-    cudaEvent_t done[NSLOT] = {nullptr, nullptr, nullptr};
+    int npin = 0;
+    cudaEvent_t done[NSLOT] = {};
     int *status = nullptr;
     bool ready = false;
 };
@@ -63,6 +65,10 @@ static size_t g_chunk = (size_t)1 << 18;
 static size_t g_chunk_staged = (size_t)1 << 16;  // smaller chunks: the ring slots are pinned memory
 static int g_staging = 1;                        // stage pageable arrays with the host-thread pool
 static int g_threads = 0;                        // 0 = auto
+// Chunks in flight.  The pipeline is a closed loop of stations (upload engine, kernels + download,
+// host-thread expansion); with 3 slots it ran at ~60 % of its slowest station
+// (profiles/r1za_host_wire_stats.jsonl), hence 6.
+static int g_nslot = 6;
 
 // Phase timings of the last staged / wire pipeline run (fcx_host_stats): where the wall time of a
 // host-array call goes.  GPU phases are per-chunk event intervals summed over chunks (they overlap
@@ -135,6 +141,7 @@ struct Group {
     std::mutex mu;
     std::condition_variable cv;
     int pending = 0;
+    std::function<void()> on_zero;  // optional: runs (on the finishing thread) when the count reaches 0
     void add()
     {
         std::lock_guard<std::mutex> l(mu);
@@ -142,9 +149,16 @@ struct Group {
     }
     void done()
     {
-        std::lock_guard<std::mutex> l(mu);
-        if (--pending == 0)
-            cv.notify_all();
+        std::function<void()> fire;  // a copy: the Group may be gone once on_zero has run
+        {
+            std::lock_guard<std::mutex> l(mu);
+            if (--pending == 0) {
+                cv.notify_all();
+                fire = on_zero;
+            }
+        }
+        if (fire)
+            fire();
     }
     void wait()
     {
@@ -214,19 +228,23 @@ static int ensure_ctx(size_t need)
             return note_cuda_error(e, "cudaMalloc(status)");
         g_ctx.ready = true;
     }
-    if (need > g_ctx.cap) {
+    if (need > g_ctx.cap || g_ctx.nbuf < g_nslot) {
+        if (need < g_ctx.cap)
+            need = g_ctx.cap;
         for (int s = 0; s < NSLOT; ++s) {
             if (g_ctx.buf[s])
                 cudaFree(g_ctx.buf[s]);
             g_ctx.buf[s] = nullptr;
         }
         g_ctx.cap = 0;
-        for (int s = 0; s < NSLOT; ++s) {
+        g_ctx.nbuf = 0;
+        for (int s = 0; s < g_nslot; ++s) {
             cudaError_t e = cudaMalloc(&g_ctx.buf[s], need);
             if (e != cudaSuccess)
                 return note_cuda_error(e, "cudaMalloc(chunk buffer)");
         }
         g_ctx.cap = need;
+        g_ctx.nbuf = g_nslot;
     }
     return FCX_OK;
 }
@@ -235,20 +253,24 @@ static inline size_t round256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int ensure_pin(size_t need)
 {
-    if (need <= g_ctx.pin_cap)
+    if (need <= g_ctx.pin_cap && g_ctx.npin >= g_nslot)
         return FCX_OK;
+    if (need < g_ctx.pin_cap)
+        need = g_ctx.pin_cap;
     for (int s = 0; s < NSLOT; ++s) {
         if (g_ctx.pin[s])
             cudaFreeHost(g_ctx.pin[s]);
         g_ctx.pin[s] = nullptr;
     }
     g_ctx.pin_cap = 0;
-    for (int s = 0; s < NSLOT; ++s) {
+    g_ctx.npin = 0;
+    for (int s = 0; s < g_nslot; ++s) {
         cudaError_t e = cudaHostAlloc((void **)&g_ctx.pin[s], need, cudaHostAllocMapped);
         if (e != cudaSuccess)
             return note_cuda_error(e, "cudaHostAlloc(ring slot)");
     }
     g_ctx.pin_cap = need;
+    g_ctx.npin = g_nslot;
     return FCX_OK;
 }
 
@@ -321,12 +343,24 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
         size_t q0, cnt;
         int slot;
     };
+    const int nslot = g_nslot;
     std::mutex mu;
     std::condition_variable cv;
     std::deque<Item> queue;     // chunks whose GPU work has been enqueued, in order
-    bool slot_busy[NSLOT] = {false, false, false};
+    bool slot_busy[NSLOT] = {};
     bool finished = false;      // no more chunks will be queued
     int drain_rc = FCX_OK;
+    // Expansion of a finished chunk runs on the pool while the drain thread already waits for the
+    // next chunk; the last task of a chunk frees its slot.
+    Group expand_group[NSLOT];
+    double expand_t0[NSLOT] = {};
+    for (int s = 0; s < nslot; ++s)
+        expand_group[s].on_zero = [&, s] {
+            std::lock_guard<std::mutex> l(mu);  // notify under the lock: nothing is touched after it
+            S.drain_expand_s += now_s() - expand_t0[s];
+            slot_busy[s] = false;
+            cv.notify_all();
+        };
 
     std::thread drain([&] {
         cudaSetDevice(device);
@@ -355,27 +389,23 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
                 S.gpu_pack_s += 1e-3 * ms[2];
                 S.gpu_d2h_s += 1e-3 * ms[3];
             }
+            Group &g = expand_group[it.slot];
+            expand_t0[it.slot] = t1;
+            g.add();  // guard: the slot is not freed before every task has been submitted
             if (de == cudaSuccess) {
-                Group g;
                 for (int a = 0; a < narr; ++a)
                     if (arr[a].dst && pageable[a])
                         parallel_copy((char *)arr[a].dst + it.q0 * arr[a].bpq,
                                       g_ctx.pin[it.slot] + pin_out[a], it.cnt * arr[a].bpq, g);
                 if (packer)
                     packer->expand(it.q0, it.cnt, g_ctx.pin[it.slot] + wire_off, g);
-                g.wait();
-                S.drain_expand_s += now_s() - t1;
             }
-            {
-                std::lock_guard<std::mutex> l(mu);
-                slot_busy[it.slot] = false;
-            }
-            cv.notify_all();
+            g.done();
         }
     });
 
     int slot = 0;
-    for (size_t q0 = 0; q0 < n && rc == FCX_OK; q0 += chunk, slot = (slot + 1) % NSLOT) {
+    for (size_t q0 = 0; q0 < n && rc == FCX_OK; q0 += chunk, slot = (slot + 1) % nslot) {
         const size_t cnt = (n - q0 < chunk) ? n - q0 : chunk;
         const double tw0 = now_s();
         {
@@ -442,6 +472,9 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
                 queue.push_back(Item{q0, cnt, slot});
             }
             cv.notify_all();
+        } else {
+            std::lock_guard<std::mutex> l(mu);
+            slot_busy[slot] = false;  // never queued: nobody else will free it
         }
         S.main_enqueue_s += now_s() - tw2;
     }
@@ -451,6 +484,15 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
     }
     cv.notify_all();
     drain.join();
+    {
+        std::unique_lock<std::mutex> l(mu);  // the expansions still running on the pool
+        cv.wait(l, [&] {
+            for (int s = 0; s < nslot; ++s)
+                if (slot_busy[s])
+                    return false;
+            return true;
+        });
+    }
     for (int s = 0; s < NSLOT; ++s) {
         e = cudaStreamSynchronize(g_ctx.stream[s]);
         if (e != cudaSuccess && rc == FCX_OK)
@@ -734,7 +776,7 @@ static int run_pipeline(const HostArr *arr, int narr, size_t n, Launch &&launch,
         return note_cuda_error(e, "cudaMemcpy(status init)");
 
     int slot = 0;
-    for (size_t q0 = 0; q0 < n; q0 += chunk, slot = (slot + 1) % NSLOT) {
+    for (size_t q0 = 0; q0 < n; q0 += chunk, slot = (slot + 1) % g_nslot) {
         const size_t cnt = (n - q0 < chunk) ? n - q0 : chunk;
         cudaStream_t st = g_ctx.stream[slot];
         void *dev[MAXARR];
@@ -999,6 +1041,15 @@ int fcx_host_wire(int on)
     const int old = g_wire;
     if (on >= 0)
         g_wire = on > 2 ? 2 : on;
+    return old;
+}
+
+int fcx_host_slots(int n)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    const int old = g_nslot;
+    if (n > 0)
+        g_nslot = n < 2 ? 2 : (n > NSLOT ? NSLOT : n);
     return old;
 }
 

@@ -300,6 +300,9 @@ int fcx_host_threads(int n);
  * in place by a kernel through its device alias, records carry the history only;
  * 0 = plain D2H of every array, -1 = query; returns the old value. */
 int fcx_host_wire(int on);
+/* Chunks in flight in the *_host pipelines (streams / device buffers / pinned ring slots):
+ * 2..8, default 6; 0 = query.  Returns the old value. */
+int fcx_host_slots(int n);
 /* Where the wall time of the last staged / wire host call went: out[0..12) = total_s,
  * main_wait_slot_s, main_stage_in_s, main_enqueue_s, drain_event_wait_s, drain_expand_s,
  * gpu_h2d_s, gpu_kernel_s, gpu_pack_s, gpu_d2h_s (per-chunk event intervals summed over chunks;

@@ -19,7 +19,7 @@ from fenics_constitutive_b200 import synthetic  # noqa: E402
 from fenics_constitutive_b200._lib import lib  # noqa: E402
 from fenics_constitutive_b200.models import VonMises3D  # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 8_000_000
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16_000_000
 L = lib()
 pin = lambda m: torch.empty(m, dtype=torch.float64).pin_memory()  # noqa: E731
 h = [pin(n * 9), pin(n * 6), pin(n * 6), pin(n), pin(n * 36)]
@@ -33,10 +33,11 @@ names = ["total_s", "main_wait_slot_s", "main_stage_in_s", "main_enqueue_s", "dr
 L.fcx_host_trace(1)
 for mem, arrs in (("pinned", h), ("pageable", pg)):
     for wire in (1, 2):
-        for thr, chunk in ((14, 1 << 16), (14, 1 << 18), (6, 1 << 16)):
+        for thr, chunk, slots in ((14, 1 << 16, 3), (14, 1 << 16, 6), (14, 1 << 16, 8), (14, 1 << 15, 8), (14, 1 << 17, 6), (8, 1 << 16, 6)):
             L.fcx_host_wire(wire)
             L.fcx_host_threads(thr)
             L.fcx_host_chunk_qps(chunk)
+            L.fcx_host_slots(slots)
             for rep in range(2):
                 for a in arrs[1:4]:
                     a.zero_()
@@ -46,6 +47,6 @@ for mem, arrs in (("pinned", h), ("pageable", pg)):
                 dt = time.perf_counter() - t0
             st = (ctypes.c_double * 12)()
             L.fcx_host_stats(st, 12)
-            row = {"memory": mem, "wire": wire, "threads": thr, "MQPs": round(n / dt / 1e6, 1)}
+            row = {"memory": mem, "wire": wire, "threads": thr, "slots": slots, "MQPs": round(n / dt / 1e6, 1)}
             row.update({k: round(v, 4) for k, v in zip(names, st)})
             print(json.dumps(row), flush=True)

@@ -521,3 +521,36 @@ def test_host_path_wire_rust_models(name, kind, wire):
     finally:
         L.fcx_host_chunk_qps(old_chunk)
         L.fcx_host_wire(old_wire)
+
+
+@pytest.mark.parametrize("slots", [2, 3, 8])
+@pytest.mark.parametrize("kind", ["pageable", "pinned"])
+def test_host_path_slots_in_flight(kind, slots):
+    """fcx_host_slots: the number of chunks in flight (streams, device buffers, ring slots) changes the
+    schedule -- expansions of finished chunks overlap on the pool -- never the result."""
+    from fenics_constitutive_b200._lib import lib
+
+    n = 200_003
+    grad, s0, e0, a0 = synthetic.mises_inputs_numpy(n, seed=5)
+    d = [dev(grad), dev(s0), torch.empty(n * 36, dtype=torch.float64, device="cuda"), dev(e0), dev(a0)]
+    law = VonMises3D(MISES)
+    law.record_plastic_flag = True
+    law.evaluate(0.0, 1.0, d[0], d[1], d[2], {"eps_n": d[3], "alpha": d[4]})
+    torch.cuda.synchronize()
+    want = [t.cpu().numpy() for t in d[1:]] + [law.plastic_flag.cpu().numpy()]
+    arrs = [grad.copy(), s0.copy(), np.full(n * 36, np.nan), e0.copy(), a0.copy()]
+    keep = []
+    if kind == "pinned":
+        for i, a in enumerate(arrs):
+            t = torch.from_numpy(a).pin_memory()
+            keep.append(t)
+            arrs[i] = t.numpy()
+    L = lib()
+    old_slots, old_chunk = L.fcx_host_slots(slots), L.fcx_host_chunk_qps(8_192)
+    try:
+        law.evaluate(0.0, 1.0, arrs[0], arrs[1], arrs[2], {"eps_n": arrs[3], "alpha": arrs[4]})
+    finally:
+        L.fcx_host_slots(old_slots)
+        L.fcx_host_chunk_qps(old_chunk)
+    for got, ref in zip(arrs[1:] + [law.plastic_flag], want):
+        assert np.array_equal(got, ref)
