@@ -60,6 +60,8 @@ SIGNATURES = {
     "fcx_host_wire": (_ci, [_ci]),
     "fcx_host_trace": (_ci, [_ci]),
     "fcx_host_slots": (_ci, [_ci]),
+    "fcx_host_debug_skip": (_ci, [_ci]),
+    "fcx_host_timeline": (_ci, [_vp, _ci]),
     "fcx_host_stats": (_ci, [_vp, _ci]),
     "fcx_host_chunk_qps": (_sz, [_sz]),
     "fcx_host_release": (None, []),

@@ -80,8 +80,18 @@ struct HostStats {
     double chunks = 0, chunk_qps = 0;
 };
 static HostStats g_stats;
+// DIAGNOSTIC ONLY (fcx_host_debug_skip): leave phases of the staged pipeline out to see what the others
+// cost -- results are garbage while any bit is set.  1 uploads, 2 wire kernels, 4 download DMAs,
+// 8 host expansion, 16 model kernel.
+static int g_skip = 0;
 static int g_trace = 0;  // fcx_host_trace(1): also record per-chunk GPU phase events
 static cudaEvent_t g_tev[NSLOT][5] = {};
+static cudaEvent_t g_t0ev = nullptr;
+// Per-chunk timeline of the last traced run (fcx_host_timeline), seconds since the call began:
+// [chunk, slot, host: slot acquired, enqueued | gpu: chain start, h2d done, kernel done, pack done,
+//  d2h done | host: drain woke, expansion done]
+constexpr int TL_COLS = 11;
+static std::vector<double> g_timeline;
 
 static inline double now_s()
 {
@@ -337,12 +347,20 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
             for (int k = 0; k < 5; ++k)
                 if (g_tev[s][k] == nullptr)
                     cudaEventCreate(&g_tev[s][k]);
+    std::vector<double> TL;
+    if (trace) {
+        if (g_t0ev == nullptr)
+            cudaEventCreate(&g_t0ev);
+        TL.assign(((n + chunk - 1) / chunk) * TL_COLS, 0.0);
+        cudaEventRecord(g_t0ev, g_ctx.stream[0]);
+    }
     const double t_begin = now_s();
 
     struct Item {
         size_t q0, cnt;
         int slot;
     };
+    auto tl = [&](size_t q0, int col) -> double & { return TL[(q0 / chunk) * TL_COLS + col]; };
     const int nslot = g_nslot;
     std::mutex mu;
     std::condition_variable cv;
@@ -354,10 +372,13 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
     // next chunk; the last task of a chunk frees its slot.
     Group expand_group[NSLOT];
     double expand_t0[NSLOT] = {};
+    size_t expand_q0[NSLOT] = {};
     for (int s = 0; s < nslot; ++s)
         expand_group[s].on_zero = [&, s] {
             std::lock_guard<std::mutex> l(mu);  // notify under the lock: nothing is touched after it
             S.drain_expand_s += now_s() - expand_t0[s];
+            if (trace)
+                tl(expand_q0[s], 10) = now_s() - t_begin;
             slot_busy[s] = false;
             cv.notify_all();
         };
@@ -388,11 +409,20 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
                 S.gpu_kernel_s += 1e-3 * ms[1];
                 S.gpu_pack_s += 1e-3 * ms[2];
                 S.gpu_d2h_s += 1e-3 * ms[3];
+                for (int k = 0; k < 5; ++k) {
+                    float abs_ms = 0;
+                    cudaEventElapsedTime(&abs_ms, g_t0ev, g_tev[it.slot][k]);
+                    tl(it.q0, 4 + k) = 1e-3 * abs_ms;
+                }
+                tl(it.q0, 0) = (double)(it.q0 / chunk);
+                tl(it.q0, 1) = it.slot;
+                tl(it.q0, 9) = t1 - t_begin;
             }
             Group &g = expand_group[it.slot];
             expand_t0[it.slot] = t1;
+            expand_q0[it.slot] = it.q0;
             g.add();  // guard: the slot is not freed before every task has been submitted
-            if (de == cudaSuccess) {
+            if (de == cudaSuccess && !(g_skip & 8)) {
                 for (int a = 0; a < narr; ++a)
                     if (arr[a].dst && pageable[a])
                         parallel_copy((char *)arr[a].dst + it.q0 * arr[a].bpq,
@@ -416,6 +446,8 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
         const double tw1 = now_s();
         S.main_wait_slot_s += tw1 - tw0;
         S.chunks += 1;
+        if (trace)
+            tl(q0, 2) = tw1 - t_begin;
         {
             Group g;  // stage-in: caller's pageable arrays -> pinned slot
             for (int a = 0; a < narr; ++a)
@@ -432,7 +464,7 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
         void *dev[MAXARR];
         for (int a = 0; a < narr && rc == FCX_OK; ++a) {
             dev[a] = g_ctx.buf[slot] + off[a];
-            if (arr[a].src) {
+            if (arr[a].src && !(g_skip & 1)) {
                 const void *src = pageable[a] ? (const void *)(g_ctx.pin[slot] + pin_in[a])
                                               : (const void *)((const char *)arr[a].src + q0 * arr[a].bpq);
                 e = cudaMemcpyAsync(dev[a], src, cnt * arr[a].bpq, cudaMemcpyHostToDevice, st);
@@ -442,16 +474,16 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
         }
         if (trace)
             cudaEventRecord(g_tev[slot][1], st);
-        if (rc == FCX_OK)
+        if (rc == FCX_OK && !(g_skip & 16))
             rc = launch(dev, cnt, st, g_ctx.status);
         if (trace)
             cudaEventRecord(g_tev[slot][2], st);
-        if (rc == FCX_OK && packer)
+        if (rc == FCX_OK && packer && !(g_skip & 2))
             rc = packer->enqueue(dev, g_ctx.buf[slot] + scratch_off, g_ctx.pin[slot] + wire_off, q0, cnt, st);
         if (trace)
             cudaEventRecord(g_tev[slot][3], st);
         for (int a = 0; a < narr && rc == FCX_OK; ++a) {
-            if (arr[a].dst) {
+            if (arr[a].dst && !(g_skip & 4)) {
                 void *dst = pageable[a] ? (void *)(g_ctx.pin[slot] + pin_out[a])
                                         : (void *)((char *)arr[a].dst + q0 * arr[a].bpq);
                 e = cudaMemcpyAsync(dst, dev[a], cnt * arr[a].bpq, cudaMemcpyDeviceToHost, st);
@@ -477,6 +509,8 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
             slot_busy[slot] = false;  // never queued: nobody else will free it
         }
         S.main_enqueue_s += now_s() - tw2;
+        if (trace)
+            tl(q0, 3) = now_s() - t_begin;
     }
     {
         std::lock_guard<std::mutex> l(mu);
@@ -500,6 +534,8 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
     }
     S.total_s = now_s() - t_begin;
     g_stats = S;
+    if (trace)
+        g_timeline.swap(TL);
     if (rc != FCX_OK)
         return rc;
     if (drain_rc != FCX_OK)
@@ -537,76 +573,93 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
 //     upper-triangle entries and is mirrored by the host threads; others travel as all 36.
 // ---------------------------------------------------------------------------
 
-// pos[q] = number of plastic points before q in the chunk; *count = total.  One CTA.
+// list[r] = index of the r-th plastic point of the chunk (point order); *count = their number.
+// One CTA; every round takes 16 consecutive flags per thread with one coalesced 16-byte load
+// (the first version let each thread walk 64 consecutive bytes: 32 sectors per warp instruction,
+// 0.15 ms per 64 Ki-point chunk with the PCIe link idle behind it, profiles/r1ze).
 __global__ void __launch_bounds__(1024)
-    wire_scan_kernel(const unsigned char *__restrict__ flag, unsigned cnt, unsigned *__restrict__ pos,
+    wire_scan_kernel(const unsigned char *__restrict__ flag, unsigned cnt, unsigned *__restrict__ list,
                      unsigned *__restrict__ count_out)
 {
     __shared__ unsigned warp_sum[32];
-    __shared__ unsigned carry;
+    __shared__ unsigned round_total;
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned per = (cnt + 1023) / 1024;
-    const unsigned b = tid * per, e = (b + per < cnt) ? b + per : cnt;
-    unsigned mine = 0;
-    for (unsigned q = b; q < e; ++q)
-        mine += flag[q];
-    unsigned incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (unsigned)d)
-            incl += t;
-    }
-    if (lane == 31)
-        warp_sum[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        unsigned w = warp_sum[lane], wi = w;
+    unsigned carry = 0;
+    for (unsigned base = 0; base < cnt; base += 16384) {
+        const unsigned q0 = base + tid * 16;
+        unsigned w[4] = {0, 0, 0, 0};
+        if (q0 + 16 <= cnt) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(flag + q0);  // chunk buffers are 256-byte aligned
+            w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+        } else {
+            for (unsigned k = 0; k < 16; ++k)
+                if (q0 + k < cnt && flag[q0 + k])
+                    w[k >> 2] |= 1u << (8 * (k & 3));
+        }
+        const unsigned mine = __popc(w[0] & 0x01010101u) + __popc(w[1] & 0x01010101u) +
+                              __popc(w[2] & 0x01010101u) + __popc(w[3] & 0x01010101u);
+        unsigned incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, wi, d);
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= (unsigned)d)
-                wi += t;
+                incl += t;
         }
-        warp_sum[lane] = wi - w;  // exclusive
         if (lane == 31)
-            carry = wi;
-    }
-    __syncthreads();
-    unsigned run = warp_sum[wid] + incl - mine;
-    for (unsigned q = b; q < e; ++q) {
-        pos[q] = run;
-        run += flag[q];
+            warp_sum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned ws = warp_sum[lane];
+            unsigned wi = ws;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= (unsigned)d)
+                    wi += t;
+            }
+            warp_sum[lane] = wi - ws;  // exclusive
+            if (lane == 31)
+                round_total = wi;
+        }
+        __syncthreads();
+        unsigned run = carry + warp_sum[wid] + incl - mine;
+#pragma unroll
+        for (unsigned k = 0; k < 16; ++k)
+            if ((w[k >> 2] >> (8 * (k & 3))) & 1u)
+                list[run++] = q0 + k;
+        carry += round_total;
+        __syncthreads();  // warp_sum / round_total are rewritten in the next round
     }
     if (tid == 0)
         *count_out = carry;
 }
 
-// rec[pos[q]] = [tangent part of q (nt = 0: none, 21: upper triangle row-major i <= j, 36: all),
-//                h0[q][0..w0), h1[q][0..w1)]   for plastic q
-__global__ void wire_pack_kernel(const unsigned char *__restrict__ flag, const unsigned *__restrict__ pos,
+// The compact record stream, written front to back: thread o stores double o, so every warp
+// writes 256 consecutive bytes of pinned memory whatever the flags are (52 GB/s over PCIe against
+// 40 for a version whose lanes idled on elastic points, profiles/r1zb_pcie_probe2.log).
+// rec[r] = [tangent part of point q = list[r] (nt = 0: none, 21: upper triangle row-major i <= j,
+//           36: all), h0[q][0..w0), h1[q][0..w1)]
+__global__ void wire_pack_kernel(const unsigned *__restrict__ list, const unsigned *__restrict__ count,
                                  const double *__restrict__ tangent, int nt, const double *__restrict__ h0,
-                                 int w0, const double *__restrict__ h1, int w1, unsigned cnt,
-                                 double *__restrict__ rec)
+                                 int w0, const double *__restrict__ h1, int w1, double *__restrict__ rec)
 {
     // k -> offset of the k-th upper-triangle entry in the row-major 6x6
     const int tri[21] = {0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 14, 15, 16, 17, 21, 22, 23, 28, 29, 35};
     const int R = nt + w0 + w1;
-    const unsigned long long total = (unsigned long long)cnt * R;
+    const unsigned long long total = (unsigned long long)*count * R;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const unsigned q = (unsigned)(i / R);
-        const int k = (int)(i - (unsigned long long)q * R);
-        if (!flag[q])
-            continue;
+    for (unsigned long long o = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += stride) {
+        const unsigned r = (unsigned)(o / R);
+        const int k = (int)(o - (unsigned long long)r * R);
+        const size_t q = list[r];
         double v;
         if (k < nt)
-            v = tangent[(size_t)q * 36 + (nt == 21 ? tri[k] : k)];
+            v = tangent[q * 36 + (nt == 21 ? tri[k] : k)];
         else if (k < nt + w0)
-            v = h0[(size_t)q * w0 + (k - nt)];
+            v = h0[q * w0 + (k - nt)];
         else
-            v = h1[(size_t)q * w1 + (k - nt - w0)];
-        rec[(size_t)pos[q] * R + k] = v;
+            v = h1[q * w1 + (k - nt - w0)];
+        rec[o] = v;
     }
 }
 
@@ -642,7 +695,7 @@ struct PlasticWire {
     size_t off_flag() const { return 256; }
     size_t off_rec() const { return 256 + round256(chunk); }
     size_t wire_bytes() const { return off_rec() + chunk * rec() * sizeof(double); }
-    size_t dev_bytes() const { return chunk * sizeof(unsigned); }
+    size_t dev_bytes() const { return (chunk + 64) * sizeof(unsigned); }  // list + count
 };
 
 static inline void copy_doubles(double *dst, const double *src, int n, bool stream)
@@ -973,15 +1026,15 @@ static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
             P.wire_bytes = W.wire_bytes();
             P.enqueue = [&W](void **dev, void *scratch, void *wire, size_t q0, size_t cnt, cudaStream_t st) {
                 char *wb = (char *)wire;
-                unsigned *pos = (unsigned *)scratch;
+                unsigned *list = (unsigned *)scratch, *count = list + W.chunk;
                 const unsigned char *fl = (const unsigned char *)dev[5];
                 const unsigned cap = (unsigned)sm_count() * 8;
-                wire_scan_kernel<<<1, 1024, 0, st>>>(fl, (unsigned)cnt, pos, (unsigned *)(wb + W.off_count()));
+                wire_scan_kernel<<<1, 1024, 0, st>>>(fl, (unsigned)cnt, list, count);
                 unsigned long long work = (unsigned long long)cnt * W.rec();
                 unsigned grid = (unsigned)((work + 255) / 256);
                 wire_pack_kernel<<<grid > cap ? cap : grid, 256, 0, st>>>(
-                    fl, pos, (const double *)dev[2], W.nt, (const double *)dev[3], W.hw[0], (const double *)dev[4],
-                    W.hw[1], (unsigned)cnt, (double *)(wb + W.off_rec()));
+                    list, count, (const double *)dev[2], W.nt, (const double *)dev[3], W.hw[0],
+                    (const double *)dev[4], W.hw[1], (double *)(wb + W.off_rec()));
                 g_launches.fetch_add(2, std::memory_order_relaxed);
                 if (W.tangent_dev != nullptr) {
                     work = (unsigned long long)cnt * 18;
@@ -1053,12 +1106,30 @@ int fcx_host_slots(int n)
     return old;
 }
 
+int fcx_host_debug_skip(int mask)
+{
+    const int old = g_skip;
+    if (mask >= 0)
+        g_skip = mask;
+    return old;
+}
+
 int fcx_host_trace(int on)
 {
     const int old = g_trace;
     if (on >= 0)
         g_trace = on ? 1 : 0;
     return old;
+}
+
+int fcx_host_timeline(double *out, int max_rows)
+{
+    const int rows = (int)(g_timeline.size() / TL_COLS);
+    if (out)
+        for (int r = 0; r < rows && r < max_rows; ++r)
+            for (int c = 0; c < TL_COLS; ++c)
+                out[r * TL_COLS + c] = g_timeline[(size_t)r * TL_COLS + c];
+    return rows;
 }
 
 int fcx_host_stats(double *out, int n)

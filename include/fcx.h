@@ -309,6 +309,14 @@ int fcx_host_slots(int n);
  * recorded only after fcx_host_trace(1)), chunks, chunk_qps.  Returns 12. */
 int fcx_host_stats(double *out, int n);
 int fcx_host_trace(int on);
+/* DIAGNOSTIC ONLY: leave phases of the staged host pipeline out (1 uploads, 2 wire kernels,
+ * 4 download DMAs, 8 host expansion, 16 model kernel) to time the others; results are garbage
+ * while any bit is set.  -1 = query. */
+int fcx_host_debug_skip(int mask);
+/* Per-chunk timeline of the last traced call, 11 doubles per chunk (seconds since the call began):
+ * chunk, slot, host slot-acquired, host enqueued, gpu chain start, h2d done, kernel done, pack done,
+ * d2h done, host drain woke, host expansion done.  Returns the number of chunks. */
+int fcx_host_timeline(double *out, int max_rows);
 /* QPs per pipeline chunk of the *_host entry points (default 1<<18); 0 = query. */
 size_t fcx_host_chunk_qps(size_t new_value);
 /* Release the streams / staging buffers cached by the *_host entry points. */
