@@ -54,8 +54,7 @@ struct HostCtx {
     char *pin[NSLOT] = {};  // pinned ring slots (pageable callers, wire records)
     size_t pin_cap = 0;
     int npin = 0;
-    cudaEvent_t done[NSLOT] = {};   // chunk's kernels + plain downloads finished
-    cudaEvent_t done2[NSLOT] = {};  // ... and the packer's sized record download (second stage)
+    cudaEvent_t done[NSLOT] = {};
     int *status = nullptr;
     bool ready = false;
 };
@@ -184,7 +183,7 @@ static int pool_threads()
         return g_threads;
     const int hw = (int)std::thread::hardware_concurrency();
     int t = hw > 3 ? hw - 2 : 1;  // leave room for the caller and the drain thread
-    return t > 8 ? 8 : t;         // 8 beat 14 on the 16-core hosts, pinned and pageable (profiles/r1zf)
+    return t > 16 ? 16 : t;
 }
 
 // memcpy split over the pool in pieces of >= 256 KiB
@@ -231,8 +230,6 @@ static int ensure_ctx(size_t need)
         }
         for (int s = 0; s < NSLOT; ++s) {
             cudaError_t e = cudaEventCreateWithFlags(&g_ctx.done[s], cudaEventDisableTiming);
-            if (e == cudaSuccess)
-                e = cudaEventCreateWithFlags(&g_ctx.done2[s], cudaEventDisableTiming);
             if (e != cudaSuccess)
                 return note_cuda_error(e, "cudaEventCreate");
         }
@@ -296,9 +293,6 @@ struct Packer {
     size_t wire_bytes = 0;  // pinned bytes per slot
     // enqueue the pack kernels of one chunk after the model kernel
     std::function<int(void **dev, void *scratch, void *wire, size_t q0, size_t cnt, cudaStream_t st)> enqueue;
-    // optional second stage, called by the drain thread once the chunk's kernels have finished: enqueue
-    // what depends on a number only known then (the DMA of `count` compacted records)
-    std::function<int(void *scratch, void *wire, size_t cnt, cudaStream_t st)> finish;
     // expand chunk [q0, q0 + cnt) from the wire into the caller's arrays (tasks on the pool)
     std::function<void(size_t q0, size_t cnt, const void *wire, Group &g)> expand;
 };
@@ -389,64 +383,20 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
             cv.notify_all();
         };
 
-    // Stage 1: the chunk's kernels and plain downloads are done -> enqueue the packer's sized download.
-    std::deque<Item> queue2;
-    bool finished1 = false;
-    double wait1_s = 0;  // stage-1 event waits (added to drain_event_wait_s after the join)
-    std::thread drain1([&] {
-        cudaSetDevice(device);
-        for (;;) {
-            Item it;
-            {
-                std::unique_lock<std::mutex> l(mu);
-                cv.wait(l, [&] { return !queue.empty() || finished; });
-                if (queue.empty()) {
-                    finished1 = true;
-                    l.unlock();
-                    cv.notify_all();
-                    return;
-                }
-                it = queue.front();
-                queue.pop_front();
-            }
-            cudaStream_t st = g_ctx.stream[it.slot];
-            if (packer && packer->finish && !(g_skip & 2)) {
-                const double t0 = now_s();
-                cudaError_t de = cudaEventSynchronize(g_ctx.done[it.slot]);
-                wait1_s += now_s() - t0;
-                int frc = FCX_OK;
-                if (de != cudaSuccess)
-                    frc = note_cuda_error(de, "cudaEventSynchronize(chunk)");
-                else
-                    frc = packer->finish(g_ctx.buf[it.slot] + scratch_off, g_ctx.pin[it.slot] + wire_off, it.cnt, st);
-                if (frc != FCX_OK && drain_rc == FCX_OK)
-                    drain_rc = frc;
-            }
-            if (trace)
-                cudaEventRecord(g_tev[it.slot][4], st);
-            cudaEventRecord(g_ctx.done2[it.slot], st);
-            {
-                std::lock_guard<std::mutex> l(mu);
-                queue2.push_back(it);
-            }
-            cv.notify_all();
-        }
-    });
-    // Stage 2: everything of the chunk has arrived in host memory -> expansion tasks on the pool.
     std::thread drain([&] {
         cudaSetDevice(device);
         for (;;) {
             Item it;
             {
                 std::unique_lock<std::mutex> l(mu);
-                cv.wait(l, [&] { return !queue2.empty() || finished1; });
-                if (queue2.empty())
+                cv.wait(l, [&] { return !queue.empty() || finished; });
+                if (queue.empty())
                     return;
-                it = queue2.front();
-                queue2.pop_front();
+                it = queue.front();
+                queue.pop_front();
             }
             const double t0 = now_s();
-            cudaError_t de = cudaEventSynchronize(g_ctx.done2[it.slot]);
+            cudaError_t de = cudaEventSynchronize(g_ctx.done[it.slot]);
             const double t1 = now_s();
             S.drain_event_wait_s += t1 - t0;
             if (de != cudaSuccess && drain_rc == FCX_OK)
@@ -541,6 +491,8 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
                     rc = note_cuda_error(e, "cudaMemcpyAsync(D2H)");
             }
         }
+        if (trace)
+            cudaEventRecord(g_tev[slot][4], st);
         if (rc == FCX_OK) {
             e = cudaEventRecord(g_ctx.done[slot], st);
             if (e != cudaSuccess)
@@ -565,9 +517,7 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
         finished = true;
     }
     cv.notify_all();
-    drain1.join();
     drain.join();
-    S.drain_event_wait_s += wait1_s;
     {
         std::unique_lock<std::mutex> l(mu);  // the expansions still running on the pool
         cv.wait(l, [&] {
@@ -745,9 +695,7 @@ struct PlasticWire {
     size_t off_flag() const { return 256; }
     size_t off_rec() const { return 256 + round256(chunk); }
     size_t wire_bytes() const { return off_rec() + chunk * rec() * sizeof(double); }
-    // device scratch: list[chunk], count (+ pad), then the packed records
-    size_t dev_rec_off() const { return round256((chunk + 64) * sizeof(unsigned)); }
-    size_t dev_bytes() const { return dev_rec_off() + chunk * rec() * sizeof(double); }
+    size_t dev_bytes() const { return (chunk + 64) * sizeof(unsigned); }  // list + count
 };
 
 static inline void copy_doubles(double *dst, const double *src, int n, bool stream)
@@ -828,11 +776,7 @@ static void plastic_wire_expand(const PlasticWire &W, size_t q0, size_t cnt, con
     }
 }
 
-// Download wire of the plastic host paths: 0 off, 1 slot records, 2 + direct tangents for page-locked
-// arrays.  Default 1: on this pool's hosts the direct stores lose to the records (133 vs 161-177
-// M QP/s at 16 M points, profiles/r1zf_host_wire_stats.jsonl) -- the host threads' streaming fill
-// of the elastic runs and the GPU's 288-byte runs land in the same cache lines of the same array.
-static int g_wire = 1;
+static int g_wire = 2;  // download wire of the plastic host paths: 0 off, 1 slot records only, 2 + direct tangents
 
 // Device alias of a page-locked host range (pinned allocation or cudaHostRegister), or nullptr.
 static void *device_alias(const void *p, size_t bytes)
@@ -1088,13 +1032,9 @@ static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
                 wire_scan_kernel<<<1, 1024, 0, st>>>(fl, (unsigned)cnt, list, count);
                 unsigned long long work = (unsigned long long)cnt * W.rec();
                 unsigned grid = (unsigned)((work + 255) / 256);
-                // records are packed in DEVICE memory; the drain thread DMAs exactly `count` of them
-                // (Packer::finish).  SM stores straight into the pinned slot reached only ~25 GB/s
-                // inside the pipeline (profiles/r1zf_host_timeline.jsonl) against ~45-50 for the
-                // copy engine.
                 wire_pack_kernel<<<grid > cap ? cap : grid, 256, 0, st>>>(
                     list, count, (const double *)dev[2], W.nt, (const double *)dev[3], W.hw[0],
-                    (const double *)dev[4], W.hw[1], (double *)((char *)scratch + W.dev_rec_off()));
+                    (const double *)dev[4], W.hw[1], (double *)(wb + W.off_rec()));
                 g_launches.fetch_add(2, std::memory_order_relaxed);
                 if (W.tangent_dev != nullptr) {
                     work = (unsigned long long)cnt * 18;
@@ -1106,22 +1046,7 @@ static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
                 cudaError_t e = cudaGetLastError();
                 if (e == cudaSuccess)
                     e = cudaMemcpyAsync(wb + W.off_flag(), fl, cnt, cudaMemcpyDeviceToHost, st);
-                if (e == cudaSuccess)
-                    e = cudaMemcpyAsync(wb + W.off_count(), count, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
                 return note_cuda_error(e, "plastic wire pack");
-            };
-            P.finish = [&W](void *scratch, void *wire, size_t cnt, cudaStream_t st) {
-                char *wb = (char *)wire;
-                unsigned count = 0;
-                memcpy(&count, wb + W.off_count(), sizeof count);
-                if (count > cnt)
-                    return (int)FCX_ERR_ARG;
-                if (count == 0)
-                    return (int)FCX_OK;
-                return note_cuda_error(cudaMemcpyAsync(wb + W.off_rec(), (const char *)scratch + W.dev_rec_off(),
-                                                       (size_t)count * W.rec() * sizeof(double),
-                                                       cudaMemcpyDeviceToHost, st),
-                                       "plastic wire record download");
             };
             P.expand = [&W](size_t q0, size_t cnt, const void *wire, Group &g) {
                 plastic_wire_expand(W, q0, cnt, wire, g);
@@ -1237,9 +1162,6 @@ void fcx_host_release(void)
         if (g_ctx.done[s])
             cudaEventDestroy(g_ctx.done[s]);
         g_ctx.done[s] = nullptr;
-        if (g_ctx.done2[s])
-            cudaEventDestroy(g_ctx.done2[s]);
-        g_ctx.done2[s] = nullptr;
         if (g_ctx.buf[s])
             cudaFree(g_ctx.buf[s]);
         g_ctx.buf[s] = nullptr;
