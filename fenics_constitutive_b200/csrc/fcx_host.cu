@@ -183,7 +183,7 @@ static int pool_threads()
         return g_threads;
     const int hw = (int)std::thread::hardware_concurrency();
     int t = hw > 3 ? hw - 2 : 1;  // leave room for the caller and the drain thread
-    return t > 16 ? 16 : t;
+    return t > 8 ? 8 : t;         // 8 beat 14 on the 16-core hosts, pinned and pageable (profiles/r1zf)
 }
 
 // memcpy split over the pool in pieces of >= 256 KiB
@@ -776,7 +776,14 @@ static void plastic_wire_expand(const PlasticWire &W, size_t q0, size_t cnt, con
     }
 }
 
-static int g_wire = 2;  // download wire of the plastic host paths: 0 off, 1 slot records only, 2 + direct tangents
+// Download wire of the plastic host paths: 0 off, 1 slot records, 2 + direct tangents for page-locked
+// arrays.  Default 1: on this pool's hosts the direct stores lose to the records (122-133 vs 150-177
+// M QP/s, profiles/r1zf_host_wire_stats.jsonl): the whole path is bound by what host memory and the
+// link move together (~51 GB/s of PCIe traffic in both wire modes while the host threads stream the
+// tangents), and the GPU's 288-byte runs share cache lines with the host threads' fills.
+// Tried and reverted (profiles/r1zg_*): packing the records in device memory and letting a second
+// drain stage DMA exactly `count` of them -- same link rate, one more host round trip per chunk.
+static int g_wire = 1;
 
 // Device alias of a page-locked host range (pinned allocation or cudaHostRegister), or nullptr.
 static void *device_alias(const void *p, size_t bytes)

@@ -289,15 +289,17 @@ int fcx_host_unregister(void *ptr);
  * slots by a pool of host threads, both ways, overlapped with the DMA (memcpy
  * only -- no arithmetic on the CPU).  fcx_host_staging(0/1) switches that off/on
  * (off = let the driver stage; -1 = query), fcx_host_threads(n) sets the pool
- * size (0 = query; default min(16, cores - 2)).  Both return the old value. */
+ * size (0 = query; default min(8, cores - 2)).  Both return the old value. */
 int fcx_host_staging(int on);
 int fcx_host_threads(int n);
 /* The plastic models' *_host entry points send their results over a download wire (stress for
  * every point, a flag byte, and for PLASTIC points only a compacted record; the host threads
  * scatter the records and copy the constant elastic tangent -- bit-identical arrays).
  * 1 = records carry tangent (VonMises3D: its 21 upper-triangle entries) + history;
- * 2 (default) = additionally, a page-locked caller tangent array gets the plastic tangents stored
- * in place by a kernel through its device alias, records carry the history only;
+ * 1 is the default;
+ * 2 = additionally, a page-locked caller tangent array gets the plastic tangents stored in place by
+ * a kernel through its device alias, records carry the history only (fewer host-thread bytes, but
+ * slower on the hosts measured so far, profiles/r1zf_host_wire_stats.jsonl);
  * 0 = plain D2H of every array, -1 = query; returns the old value. */
 int fcx_host_wire(int on);
 /* Chunks in flight in the *_host pipelines (streams / device buffers / pinned ring slots):
