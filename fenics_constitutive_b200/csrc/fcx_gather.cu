@@ -169,6 +169,14 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
 // Same fma chains in the same order as gather_kernel (grad_at_qps), hence the same bits.
 // Whole 16-byte-aligned tiles only; launch_gather sends the ragged tail (and unaligned views)
 // to gather_kernel.
+// Measured, 998 250 P2 tets: 0.104 ms against 0.127 (profiles/r1za_gather_ab.jsonl); ncu
+// (profiles/r1zh_gather_ncu_full.json): long-scoreboard stalls gone, now bound by the
+// shared-memory data pipe (l1tex wavefronts at 78 % of peak: 255 LDS + 78 STS + 144 LDGSTS + 180
+// bulk-copy wavefronts per 32-cell tile), DRAM at 48 %.  Tried on top and reverted because slower
+// (0.110 ms, profiles/r1zi_*): lane = cell / warp = quadrature point with the basis-gradient
+// table as constant-bank DFMA operands, odd-stride nodal stage, rotated 16-byte result stores --
+// the table loads it removes were broadcasts that cost one wavefront each, while the padded
+// stage made the LDGSTS writes less regular.
 // ---------------------------------------------------------------------------
 template <int G, int ND, int NQ, bool PREV>
 struct StagedCfg {

@@ -63,6 +63,24 @@ for mk, degree, qd in ((lambda: S.create_unit_cube(9, 9, 8), 2, 2), (lambda: S.c
         pb.J_apply(p)
         pb.J_diag()
 lib().fcx_tune(b"fem_variant", 1)
+# companion gather alone: staged (cp.async) and register-load kernels, several tiles per CTA, ragged tail
+from fenics_constitutive_b200 import gather as G  # noqa: E402
+
+for gdim, degree, qdeg, ncells in ((3, 2, 2, 148 * 32 * 3 + 17), (3, 1, 1, 148 * 64 * 2 + 5), (2, 2, 2, 148 * 32 * 2 + 3)):
+    rng = np.random.default_rng(ncells)
+    pts, _ = G.simplex_quadrature(gdim, qdeg)
+    dphi = G.lagrange_gradients(gdim, degree, pts)
+    nnodes = ncells // 3
+    dofmap = rng.integers(0, nnodes, size=(ncells, dphi.shape[1])).astype(np.int32)
+    Jinv = rng.standard_normal((ncells, gdim, gdim)) + 3 * np.eye(gdim)
+    op = G.IncrementalGradient(gdim, dofmap, dphi, Jinv)
+    uu = torch.randn(nnodes * gdim, dtype=torch.float64, device=dev)
+    out = torch.empty(op.num_qps * gdim * gdim, dtype=torch.float64, device=dev)
+    for variant in (1, 0):
+        lib().fcx_tune(b"gather_variant", variant)
+        op.evaluate(uu, None, out)
+        op.evaluate(uu, uu * 0.5, out)
+lib().fcx_tune(b"gather_variant", 1)
 lib().fcx_tune(b"ctas_per_sm", 0)
 torch.cuda.synchronize()
 print("sanitize_small: done")
