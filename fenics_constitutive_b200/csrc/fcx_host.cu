@@ -177,13 +177,18 @@ struct Group {
     }
 };
 
-static int pool_threads()
+// Pool size.  wide = true for the work that is pure streaming fill (constant-tangent models: 288 B per
+// point written by the host threads, 286 M QP/s with 14 threads, profiles/r1x); the plastic wire and
+// the pageable staging ran best with 8 on the 16-core hosts (profiles/r1zf) -- more threads only add
+// contention with the DMA traffic there.
+static int pool_threads(bool wide = false)
 {
     if (g_threads > 0)
         return g_threads;
     const int hw = (int)std::thread::hardware_concurrency();
-    int t = hw > 3 ? hw - 2 : 1;  // leave room for the caller and the drain thread
-    return t > 8 ? 8 : t;         // 8 beat 14 on the 16-core hosts, pinned and pageable (profiles/r1zf)
+    const int t = hw > 3 ? hw - 2 : 1;  // leave room for the caller and the drain thread
+    const int cap = wide ? 16 : 8;
+    return t > cap ? cap : t;
 }
 
 // memcpy split over the pool in pieces of >= 256 KiB
@@ -918,7 +923,7 @@ static int run_pipeline_const_tangent(HostArr *arr, int narr, int tangent_idx, i
     P.enqueue = [](void **, void *, void *, size_t, size_t, cudaStream_t) { return (int)FCX_OK; };
     P.expand = [tangent, ss, &tmpl](size_t q0, size_t cnt, const void *, Group &g) {
         Pool &pool = Pool::get();
-        const int nt = pool_threads();
+        const int nt = pool_threads(true);
         pool.ensure(nt);
         size_t parts = cnt / 4096;
         if (parts < 1)

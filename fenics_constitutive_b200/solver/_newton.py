@@ -42,6 +42,13 @@ class NewtonSolver:
         self.report = False
         self.linear_solver = "auto"  # "cg" | "dense" | "auto"
         self.cg_rtol = 1e-12
+        # Inexact Newton: None = every linear solve to cg_rtol; "eisenstat-walker" = forcing term
+        # eta_k = gamma (|r_k| / |r_{k-1}|)^2 (choice 2 of Eisenstat & Walker 1996 with their
+        # safeguard), clipped to [cg_rtol, cg_eta_max]: early Newton steps are solved loosely, the
+        # last ones tightly, the Newton tolerances (rtol / atol above) are untouched.
+        self.cg_forcing = None
+        self.cg_eta_max = 1e-2
+        self.cg_eta_gamma = 0.9
         self.cg_max_it = 20000
         self.cg_check_every = 10  # host convergence checks (one sync each)
         self.reduce_over_ranks = False  # sum norms/dots over torch.distributed ranks
@@ -87,7 +94,7 @@ class NewtonSolver:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t
 
-    def _solve_cg(self, apply, rhs, free_mask, diag):
+    def _solve_cg(self, apply, rhs, free_mask, diag, rtol=None):
         """Jacobi-preconditioned CG on the free dofs (projected operator P J P).  All scalars stay
         on the device; the host looks at the residual norm only every ``cg_check_every``
         iterations, so an iteration is a fixed sequence of enqueued kernels: the two element
@@ -117,7 +124,7 @@ class NewtonSolver:
         r0 = float(torch.sqrt(self._rsum(torch.dot(r, r))).item())
         if r0 == 0.0:
             return x, 0
-        tol2 = (self.cg_rtol * r0) ** 2
+        tol2 = ((self.cg_rtol if rtol is None else rtol) * r0) ** 2
         it = 0
         while it < self.cg_max_it:
             apply(p, Ap)
@@ -172,6 +179,8 @@ class NewtonSolver:
         self.residual_history.append(r)
         dx0 = None
         it = 0
+        eta, r_prev = None, None
+        self.forcing_terms = []
         converged = (r < self.atol) if self.convergence_criterion == "residual" else False
         if self.convergence_criterion == "residual" and r0 > 0 and r / r0 < self.rtol:
             converged = True
@@ -186,7 +195,21 @@ class NewtonSolver:
 
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                dx, kit = self._solve_cg(pb.J_apply, rhs, free, pb.J_diag())
+                if self.cg_forcing == "eisenstat-walker":
+                    if r_prev is None:
+                        eta = self.cg_eta_max
+                    else:
+                        new = self.cg_eta_gamma * (r / r_prev) ** 2
+                        safe = self.cg_eta_gamma * eta ** 2
+                        eta = max(new, safe) if safe > 0.1 else new
+                    # ... and never tighter than the Newton tolerances can still use (no over-solving)
+                    target = max(self.atol, self.rtol * r0)
+                    eta = min(self.cg_eta_max, max(eta, self.cg_rtol, 0.5 * target / r if r > 0 else self.cg_rtol))
+                    r_prev = r
+                    self.forcing_terms.append(eta)
+                elif self.cg_forcing is not None:
+                    raise ValueError(f"unknown cg_forcing {self.cg_forcing!r}")
+                dx, kit = self._solve_cg(pb.J_apply, rhs, free, pb.J_diag(), eta)
                 if self.profile:
                     torch.cuda.synchronize()
                     self.linear_solve_s += time.perf_counter() - t0

@@ -39,6 +39,8 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--degree", type=int, default=2)
 ap.add_argument("--cg-rtol", type=float, default=1e-8)
 ap.add_argument("--max-disp", type=float, default=0.012)
+ap.add_argument("--forcing", choices=["none", "ew"], default="none",
+                help="ew = Eisenstat-Walker forcing terms for the Krylov tolerance (inexact Newton)")
 ap.add_argument("--newton-steps-only", type=int, default=0,
                 help="if > 0: stop each load step's CG after this many iterations (kernel timing runs)")
 ap.add_argument("--ab", action="store_true", help="also time the element kernels with fem_variant 0")
@@ -72,6 +74,7 @@ problem.keep_del_grad_u = False
 solver = S.NewtonSolver(None, problem)
 solver.linear_solver = "cg"
 solver.cg_rtol = args.cg_rtol
+solver.cg_forcing = "eisenstat-walker" if args.forcing == "ew" else None
 solver.reduce_over_ranks = world > 1
 solver.profile = True
 if args.newton_steps_only > 0:
@@ -149,7 +152,7 @@ if rank == 0:
         "bench": "full Newton solve, stand-in driver (not dolfinx/PETSc)", "n_gpus": world,
         "cells_per_gpu": problem.num_cells, "qps_per_gpu": nqp, "dofs_per_gpu": V.num_dofs,
         "degree": args.degree, "q_degree": qd, "load_steps": args.steps, "newton_iterations": newton_its,
-        "krylov_iterations": krylov, "cg_rtol": args.cg_rtol, "fused_form": problem.fused,
+        "krylov_iterations": krylov, "cg_rtol": args.cg_rtol, "cg_forcing": args.forcing, "fused_form": problem.fused,
         "setup_s": round(setup_s, 2), "solve_s": round(solve_s, 3),
         "linear_solve_s": round(solver.linear_solve_s, 3),
         "ms_per_krylov_iteration": 1e3 * solver.linear_solve_s / max(1, sum(sum(k) for k in krylov)), "form_calls": form_calls,

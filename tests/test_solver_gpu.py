@@ -284,7 +284,7 @@ def test_plane_stress_and_plane_strain_2d():
             assert np.abs(s[:, 1]).max() < 1e-12
 
 
-def run_mises_uniaxial(n_steps, mesh_n, degree, qd, linear_solver="auto"):
+def run_mises_uniaxial(n_steps, mesh_n, degree, qd, linear_solver="auto", forcing=None, krylov=None):
     mesh = S.create_unit_cube(*mesh_n)
     V = S.functionspace(mesh, ("CG", degree, (3,)))
     u = S.Function(V)
@@ -295,6 +295,7 @@ def run_mises_uniaxial(n_steps, mesh_n, degree, qd, linear_solver="auto"):
     problem = S.IncrSmallStrainProblem(law, u, bcs, q_degree=qd)
     solver = S.NewtonSolver(None, problem)
     solver.linear_solver = linear_solver
+    solver.cg_forcing = forcing
     # oracle twin
     fem = oracle_for(problem)
     opb = F.OracleProblem(om.VonMises3D(MISES), fem, problem.bc_dofs_values)
@@ -304,6 +305,8 @@ def run_mises_uniaxial(n_steps, mesh_n, degree, qd, linear_solver="auto"):
         scalar_x.value = t * 0.05
         niter, converged = solver.solve(u)
         assert converged
+        if krylov is not None:
+            krylov.append(sum(solver.krylov_iterations))
         problem.update()
         on, ook = opb.solve()
         opb.update()
@@ -339,6 +342,18 @@ def test_mises_p2_mesh_cg_vs_oracle():
     assert problem.fused and load[-1] > 1500.0
     # both Newton loops stop at rtol 1e-9 from different linear solvers: iterates agree to ~1e-8
     assert worst < 1e-7
+
+
+def test_mises_p2_mesh_inexact_newton():
+    """Eisenstat-Walker forcing terms (NewtonSolver.cg_forcing): early Newton steps are solved loosely,
+    the Newton tolerances are untouched -- same answer as the oracle's sparse LU, fewer Krylov iterations
+    than with every linear solve taken to cg_rtol."""
+    k_fixed, k_ew = [], []
+    run_mises_uniaxial(4, (3, 3, 3), 2, 2, linear_solver="cg", krylov=k_fixed)
+    _, load, worst, problem, _ = run_mises_uniaxial(4, (3, 3, 3), 2, 2, linear_solver="cg",
+                                                    forcing="eisenstat-walker", krylov=k_ew)
+    assert load[-1] > 1500.0 and worst < 1e-7
+    assert sum(k_ew) < 0.8 * sum(k_fixed), (k_fixed, k_ew)
 
 
 @pytest.mark.parametrize("cls,ocls", [(SpringKelvinModel, om.SpringKelvinModel), (SpringMaxwellModel, om.SpringMaxwellModel)])
