@@ -25,6 +25,7 @@
 #include <climits>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -185,7 +186,14 @@ static int pool_threads(bool wide = false)
 {
     if (g_threads > 0)
         return g_threads;
-    const int hw = (int)std::thread::hardware_concurrency();
+    int hw = (int)std::thread::hardware_concurrency();
+    // one process per GPU (torchrun): the ranks of a node share its cores
+    static const int local_world = [] {
+        const char *e = getenv("LOCAL_WORLD_SIZE");
+        const int v = e ? atoi(e) : 1;
+        return v > 0 ? v : 1;
+    }();
+    hw /= local_world;
     const int t = hw > 3 ? hw - 2 : 1;  // leave room for the caller and the drain thread
     const int cap = wide ? 16 : 8;
     return t > cap ? cap : t;
