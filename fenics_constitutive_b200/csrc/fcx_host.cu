@@ -193,8 +193,11 @@ static int pool_threads(bool wide = false)
         const int v = e ? atoi(e) : 1;
         return v > 0 ? v : 1;
     }();
-    hw /= local_world;
-    const int t = hw > 3 ? hw - 2 : 1;  // leave room for the caller and the drain thread
+    int t = hw > 3 ? hw - 2 : 1;  // leave room for the caller and the drain thread
+    if (local_world > 1) {
+        t = hw / local_world;
+        t = t < 4 ? (hw > 3 ? 4 : 1) : t;
+    }
     const int cap = wide ? 16 : 8;
     return t > cap ? cap : t;
 }
