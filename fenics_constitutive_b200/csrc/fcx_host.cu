@@ -300,7 +300,7 @@ static int ensure_pin(size_t need)
     return FCX_OK;
 }
 
-// Optional "packed wire" for the download side of a model (see MisesWire below): the
+// Optional "packed wire" for the download side of a model (see PlasticWire below): the
 // outputs it covers leave the GPU as a compact stream written by a pack kernel straight
 // into the pinned ring slot (zero-copy stores over PCIe) and are expanded into the
 // caller's arrays by the host-thread pool -- data movement only, no arithmetic.
