@@ -266,6 +266,10 @@ static int ensure_ctx(size_t need)
         g_ctx.nbuf = 0;
         for (int s = 0; s < g_nslot; ++s) {
             cudaError_t e = cudaMalloc(&g_ctx.buf[s], need);
+            // zeroed once: the tangent part is only ever written by bulk async (TMA) stores, which
+            // compute-sanitizer's initcheck does not track (100 % false positives in the pack kernel)
+            if (e == cudaSuccess)
+                e = cudaMemset(g_ctx.buf[s], 0, need);
             if (e != cudaSuccess)
                 return note_cuda_error(e, "cudaMalloc(chunk buffer)");
         }
