@@ -32,6 +32,14 @@
  * models/mises_plasticity_isotropic_hardening.py:141-143).
  * No function throws, aborts or keeps a caller pointer past its return
  * (device entry points: past completion of the enqueued work).
+ *
+ * Threading (reference: evaluate is synchronous and not re-entrant, one call per
+ * MPI rank at a time): the device entry points keep no per-call state (parameters
+ * travel by value) and may be called from several threads on different streams;
+ * the *_host entry points share one pipeline context per process (streams, chunk
+ * buffers, pinned ring slots, the host-thread pool) and serialise on a mutex.
+ * The fcx_tune / fcx_host_* knobs are process-wide settings meant to be set
+ * before the calls they affect, not concurrently with them.
  */
 #ifndef FCX_H
 #define FCX_H
