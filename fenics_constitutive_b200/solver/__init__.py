@@ -15,6 +15,7 @@ from ._problem import (
     SimulationTime,
 )
 from .maps import IdentityMap, SubSpaceMap, build_subspace_map
+from .partitioned import MeshPartition
 from .mesh import (
     Constant,
     DirichletBC,
@@ -37,5 +38,5 @@ __all__ = [
     "IncrementalStress", "History", "LawOnSubMesh", "QuadratureFunction", "IdentityMap", "SubSpaceMap",
     "build_subspace_map", "Mesh", "FunctionSpace", "Function", "Constant", "DirichletBC", "ElementTables",
     "create_unit_interval", "create_unit_square", "create_rectangle", "create_unit_cube", "create_box",
-    "functionspace", "dirichletbc", "locate_dofs_geometrical",
+    "functionspace", "dirichletbc", "locate_dofs_geometrical", "MeshPartition",
 ]

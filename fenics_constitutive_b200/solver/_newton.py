@@ -52,14 +52,27 @@ class NewtonSolver:
         self.cg_max_it = 20000
         self.cg_check_every = 10  # host convergence checks (one sync each)
         self.reduce_over_ranks = False  # sum norms/dots over torch.distributed ranks
+        # solver/partitioned.py MeshPartition (set by MeshPartition.attach): norms and dot products run
+        # over OWNED dofs, ghost values of p (before every Jacobian action) and of x (after every Newton
+        # update) are refreshed from their owners.  None = every rank holds a whole problem.
+        self.partition = None
         self.residual_history: list[float] = []
         self.krylov_iterations: list[int] = []
+        self._owned_mask = None
         self.profile = False  # accumulate wall time of the linear solves (adds two syncs per solve)
         self.linear_solve_s = 0.0
 
     # ------------------------------------------------------------ helpers
+    def _owned(self, like):
+        if self.partition is None:
+            return None
+        if self._owned_mask is None or self._owned_mask.device != like.device:
+            self._owned_mask = self.partition.owned_dof_mask(like.device)
+        return self._owned_mask
+
     def _dot(self, a, b) -> float:
-        v = float((a * b).sum().item())
+        own = self._owned(a)
+        v = float((a * b).sum().item()) if own is None else float((a * b)[own].sum().item())
         if self.reduce_over_ranks:
             v = sum_over_ranks(v, a.device)
         return v
@@ -110,11 +123,15 @@ class NewtonSolver:
         dev = rhs.device
         n = rhs.numel()
         stream = B.current_stream_ptr(dev.index)
-        fm = free_mask.to(torch.float64)
+        own = self._owned(rhs)
+        halo = self.partition.halo_update if self.partition is not None else (lambda v: None)
+        # ghost dofs are masked like constrained ones: every reduction runs over owned free dofs
+        fm = (free_mask if own is None else free_mask & own).to(torch.float64)
         minv = (fm / torch.where(diag.abs() > 0, diag, torch.ones_like(diag))).contiguous()
         x = torch.zeros_like(rhs)
         r = (rhs * fm).contiguous()
         p = minv * r
+        halo(p)
         Ap = torch.empty_like(rhs)
         scratch = torch.empty(int(L.fcx_pcg_scratch_doubles()), dtype=torch.float64, device=dev)
         ticket = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -140,6 +157,7 @@ class NewtonSolver:
                 break
             check(L.fcx_pcg_update_p(n, p.data_ptr(), r.data_ptr(), minv.data_ptr(), sc[2:3].data_ptr(),
                                      rz.data_ptr(), stream), "fcx_pcg_update_p")
+            halo(p)
             rz.copy_(sc[2:3])
         return x, it
 
@@ -216,6 +234,8 @@ class NewtonSolver:
             dx[bc_dofs] = b[bc_dofs]  # identity rows: dx_bc = x_bc - g
             self.krylov_iterations.append(kit)
             x.add_(dx, alpha=-self.relaxation_parameter)
+            if self.partition is not None:
+                self.partition.halo_update(x)
             it += 1
             r = residual()
             self.residual_history.append(r)

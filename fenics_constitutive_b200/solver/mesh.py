@@ -132,6 +132,20 @@ class FunctionSpace:
         self.num_nodes = self.node_coords.shape[0]
         self.num_dofs = self.num_nodes * g
 
+    @classmethod
+    def from_arrays(cls, mesh: Mesh, degree: int, node_coords: np.ndarray, dofmap: np.ndarray) -> "FunctionSpace":
+        """Space with a prescribed node numbering (``solver/partitioned.py``: the local space of a
+        mesh partition numbers its owned nodes first)."""
+        self = cls.__new__(cls)
+        self.mesh, self.degree = mesh, int(degree)
+        self.block_size = mesh.gdim
+        self.node_coords = np.ascontiguousarray(node_coords, dtype=np.float64)
+        self.dofmap = np.ascontiguousarray(dofmap, dtype=np.int32)
+        assert self.dofmap.shape[0] == mesh.num_cells
+        self.num_nodes = self.node_coords.shape[0]
+        self.num_dofs = self.num_nodes * mesh.gdim
+        return self
+
     def sub(self, i: int) -> _SubSpace:
         return _SubSpace(self, i)
 

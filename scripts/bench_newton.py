@@ -39,6 +39,9 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--degree", type=int, default=2)
 ap.add_argument("--cg-rtol", type=float, default=1e-8)
 ap.add_argument("--max-disp", type=float, default=0.012)
+ap.add_argument("--partition", action="store_true",
+                help="ONE mesh partitioned over the ranks (strong scaling; ghost values of nodal vectors exchanged "
+                     "over NCCL, solver/partitioned.py) instead of one whole block per rank (weak scaling)")
 ap.add_argument("--forcing", choices=["none", "ew"], default="none",
                 help="ew = Eisenstat-Walker forcing terms for the Krylov tolerance (inexact Newton)")
 ap.add_argument("--newton-steps-only", type=int, default=0,
@@ -56,7 +59,12 @@ if world > 1:
 
 t0 = time.perf_counter()
 mesh = S.create_unit_cube(args.n, args.n, args.n)
-V = S.functionspace(mesh, ("CG", args.degree, (3,)))
+part = None
+if args.partition:
+    part = S.MeshPartition(mesh, args.degree, rank, world)
+    V = part.V
+else:
+    V = S.functionspace(mesh, ("CG", args.degree, (3,)))
 u = S.Function(V, dev)
 law = VonMises3D(synthetic.MISES_PARAMS)
 law.defer_errors = True
@@ -76,6 +84,8 @@ solver.linear_solver = "cg"
 solver.cg_rtol = args.cg_rtol
 solver.cg_forcing = "eisenstat-walker" if args.forcing == "ew" else None
 solver.reduce_over_ranks = world > 1
+if part is not None:
+    part.attach(solver)
 solver.profile = True
 if args.newton_steps_only > 0:
     solver.cg_max_it = args.newton_steps_only
@@ -125,6 +135,14 @@ law.check_converged()
 alpha = problem._history_0[0]["alpha"].x.array
 plastic_frac = float((alpha > 0).double().mean().item())
 sxx = float(problem.stress_0.x.array[::6].mean().item())
+if part is not None:  # mean over the OWNED cells of all ranks = the global mean
+    import torch.distributed as dist  # noqa: F811
+
+    own = torch.as_tensor(part.cell_owner[part.local_cells] == rank, device=dev).repeat_interleave(problem.nqp // problem.num_cells)
+    acc = torch.stack([problem.stress_0.x.array[::6][own].sum(), (alpha[own] > 0).double().sum(), own.double().sum()])
+    if world > 1:
+        dist.all_reduce(acc)
+    sxx, plastic_frac = float(acc[0] / acc[2]), float(acc[1] / acc[2])
 
 # ---- per-kernel timings on the final state ----
 p = torch.randn(V.num_dofs, dtype=torch.float64, device=dev)
@@ -150,13 +168,17 @@ J_bytes = nqp * 288 + problem.num_cells * (40 + 72 + 8 + 2 * fs + 40) + V.num_do
 if rank == 0:
     print(json.dumps({
         "bench": "full Newton solve, stand-in driver (not dolfinx/PETSc)", "n_gpus": world,
+        "mode": ("one mesh partitioned over the ranks (strong scaling)" if part is not None else "one block per rank (weak scaling)"),
+        "global_cells": mesh.num_cells if part is not None else world * problem.num_cells,
+        "owned_cells_this_rank": part.num_owned_cells if part is not None else problem.num_cells,
+        "halo_neighbours": [(int(s), int(a.size), int(b.size)) for s, a, b in part.neighbours] if part is not None else [],
         "cells_per_gpu": problem.num_cells, "qps_per_gpu": nqp, "dofs_per_gpu": V.num_dofs,
         "degree": args.degree, "q_degree": qd, "load_steps": args.steps, "newton_iterations": newton_its,
         "krylov_iterations": krylov, "cg_rtol": args.cg_rtol, "cg_forcing": args.forcing, "fused_form": problem.fused,
         "setup_s": round(setup_s, 2), "solve_s": round(solve_s, 3),
         "linear_solve_s": round(solver.linear_solve_s, 3),
         "ms_per_krylov_iteration": 1e3 * solver.linear_solve_s / max(1, sum(sum(k) for k in krylov)), "form_calls": form_calls,
-        "qp_updates_per_s_whole_solve": world * nqp * form_calls / solve_s,
+        "qp_updates_per_s_whole_solve": (mesh.num_cells * (nqp // problem.num_cells) if part is not None else world * nqp) * form_calls / solve_s,
         "plastic_fraction_final": round(plastic_frac, 4), "mean_sigma_xx": sxx,
         "kernel_ms": {"form_fused": ms_form, "F": ms_F, "J_apply": ms_J, "J_diag": ms_D, "gather_sum_alone": ms_gs},
         "kernel_ms_fem_variant0": ab,

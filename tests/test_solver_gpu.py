@@ -284,6 +284,46 @@ def test_plane_stress_and_plane_strain_2d():
             assert np.abs(s[:, 1]).max() < 1e-12
 
 
+@pytest.mark.parametrize("degree,qd", [(2, 2), (1, 1)], ids=["readme_cg2", "test_3d_cg1"])
+@pytest.mark.parametrize("kind", ["python", "rust"])
+def test_readme_example_3d_elasticity(kind, degree, qd):
+    """BASELINE.json configs[0] = the reference's README example (README.md:47-78) and its test twin
+    tests/models/test_elasticity.py:336-402: unit cube 2x2x2, FULL LinearElasticityModel (python) /
+    LinearElasticity3D (rust, mu / kappa), left face clamped, right face moved by (0.01, 0, 0), ONE
+    NewtonSolver solve + update().  The reference checks against a pure-FEniCS linear solve; here the twin
+    is the oracle's sparse direct solve of the same discrete problem.  (The README asks for q_degree 1 with
+    CG2, which under-integrates the stiffness; the well-posed q_degree 2 is used for CG2.)"""
+    from fenics_constitutive_b200.models import LinearElasticity3D
+
+    mesh = S.create_unit_cube(2, 2, 2)
+    V = S.functionspace(mesh, ("CG", degree, (3,)))
+    u = S.Function(V)
+    if kind == "python":
+        law = LinearElasticityModel(parameters={"E": E, "nu": NU}, constraint=C.FULL)
+        olaw = om.LinearElasticityModel({"E": E, "nu": NU}, C.FULL)
+    else:
+        prm = {"mu": np.array([E / (2 * (1 + NU))]), "kappa": np.array([E / (3 * (1 - 2 * NU))])}
+        law, olaw = LinearElasticity3D(prm), om.RustLinearElasticity3D(prm)
+    zero, disp = S.Constant(mesh, 0.0), S.Constant(mesh, 0.01)
+    bcs = gpu_bcs(V, [(left, 0, zero), (left, 1, zero), (left, 2, zero),
+                      (right, 0, disp), (right, 1, zero), (right, 2, zero)])
+    problem = S.IncrSmallStrainProblem(law, u, bcs, qd)
+    solver = S.NewtonSolver(None, problem)
+    n, converged = solver.solve(u)
+    assert converged and n == 1  # linear problem: one Newton step
+    problem.update()
+    opb = F.OracleProblem(olaw, oracle_for(problem), problem.bc_dofs_values)
+    on, ook = opb.solve()
+    opb.update()
+    assert ook
+    assert np.abs(u.numpy() - opb.u).max() <= 1e-10 * np.abs(opb.u).max()
+    assert rel_err(problem.stress_0.numpy(), opb.stress_0, 6) <= 1e-9
+    # clamped faces: sigma_xx is positive everywhere and the mean axial stress lies between the
+    # uniaxial-stress (E eps) and uniaxial-strain (E (1 - nu) / ((1 + nu)(1 - 2 nu)) eps) bounds
+    sxx = problem.stress_0.numpy()[::6]
+    assert E * 0.01 < sxx.mean() < E * (1 - NU) / ((1 + NU) * (1 - 2 * NU)) * 0.01
+
+
 def run_mises_uniaxial(n_steps, mesh_n, degree, qd, linear_solver="auto", forcing=None, krylov=None):
     mesh = S.create_unit_cube(*mesh_n)
     V = S.functionspace(mesh, ("CG", degree, (3,)))
