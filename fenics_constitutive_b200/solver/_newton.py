@@ -51,6 +51,12 @@ class NewtonSolver:
         self.cg_eta_gamma = 0.9
         self.cg_max_it = 20000
         self.cg_check_every = 10  # host convergence checks (one sync each)
+        # Krylov iterations between two host checks are captured ONCE per linear solve in a CUDA graph
+        # (our kernels, the scalar all-reduces and the ghost exchange included) and replayed: an iteration
+        # is ~8 launches of 20-300 us each, so with the mesh split over several GPUs the loop is bound by
+        # launch / Python overhead, not by the kernels.  False = enqueue every iteration from Python.
+        self.cg_cuda_graph = True
+        self.cg_graph_replays = 0
         self.reduce_over_ranks = False  # sum norms/dots over torch.distributed ranks
         # solver/partitioned.py MeshPartition (set by MeshPartition.attach): norms and dot products run
         # over OWNED dofs, ghost values of p (before every Jacobian action) and of x (after every Newton
@@ -59,6 +65,9 @@ class NewtonSolver:
         self.residual_history: list[float] = []
         self.krylov_iterations: list[int] = []
         self._owned_mask = None
+        self._cg_stream = None
+        self._cg_graph_ok = True
+        self.cg_graph_error = None
         self.profile = False  # accumulate wall time of the linear solves (adds two syncs per solve)
         self.linear_solve_s = 0.0
 
@@ -142,23 +151,68 @@ class NewtonSolver:
         if r0 == 0.0:
             return x, 0
         tol2 = ((self.cg_rtol if rtol is None else rtol) * r0) ** 2
-        it = 0
-        while it < self.cg_max_it:
+        K = max(1, int(self.cg_check_every))
+
+        def iteration():
+            """One PCG iteration, enqueue-only on the current stream (x, r, p, rz updated in place)."""
             apply(p, Ap)
             check(L.fcx_pcg_pap(n, p.data_ptr(), Ap.data_ptr(), minv.data_ptr(), scratch.data_ptr(),
-                                ticket.data_ptr(), pAp.data_ptr(), stream), "fcx_pcg_pap")
+                                ticket.data_ptr(), pAp.data_ptr(), B.current_stream_ptr(dev.index)), "fcx_pcg_pap")
             self._rsum(pAp)
             check(L.fcx_pcg_update_xr(n, x.data_ptr(), r.data_ptr(), p.data_ptr(), Ap.data_ptr(), minv.data_ptr(),
                                       rz.data_ptr(), pAp.data_ptr(), scratch.data_ptr(), ticket.data_ptr(),
-                                      new2.data_ptr(), stream), "fcx_pcg_update_xr")
+                                      new2.data_ptr(), B.current_stream_ptr(dev.index)), "fcx_pcg_update_xr")
             self._rsum(new2)
-            it += 1
-            if it % self.cg_check_every == 0 and float(sc[3].item()) <= tol2:
-                break
+            # (after the last iteration of a solve this direction update is not used: x is final)
             check(L.fcx_pcg_update_p(n, p.data_ptr(), r.data_ptr(), minv.data_ptr(), sc[2:3].data_ptr(),
-                                     rz.data_ptr(), stream), "fcx_pcg_update_p")
+                                     rz.data_ptr(), B.current_stream_ptr(dev.index)), "fcx_pcg_update_p")
             halo(p)
             rz.copy_(sc[2:3])
+
+        def converged():
+            return float(sc[3].item()) <= tol2  # one host synchronisation
+
+        it = 0
+        if not (self.cg_cuda_graph and rhs.is_cuda):
+            while it < self.cg_max_it:
+                for _ in range(K):
+                    iteration()
+                it += K
+                if converged():
+                    break
+            return x, it
+        # K eager iterations on a side stream first (first-use initialisation: tile-ticket slots of that
+        # stream, NCCL point-to-point communicators), then the same K iterations as a graph
+        side = self._cg_stream if self._cg_stream is not None else torch.cuda.Stream(device=dev)
+        self._cg_stream = side
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(K):
+                iteration()
+            it += K
+            if not converged():
+                graph = None
+                if self._cg_graph_ok:
+                    try:
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph, stream=side):
+                            for _ in range(K):
+                                iteration()
+                    except RuntimeError as exc:  # e.g. a collective that cannot be captured on this stack
+                        self._cg_graph_ok = False
+                        self.cg_graph_error = str(exc)
+                        graph = None
+                while it < self.cg_max_it:
+                    if graph is not None:
+                        graph.replay()
+                        self.cg_graph_replays += 1
+                    else:
+                        for _ in range(K):
+                            iteration()
+                    it += K
+                    if converged():
+                        break
+        torch.cuda.current_stream(dev).wait_stream(side)
         return x, it
 
     # -------------------------------------------------------------- solve

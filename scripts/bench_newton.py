@@ -174,7 +174,8 @@ if rank == 0:
         "halo_neighbours": [(int(s), int(a.size), int(b.size)) for s, a, b in part.neighbours] if part is not None else [],
         "cells_per_gpu": problem.num_cells, "qps_per_gpu": nqp, "dofs_per_gpu": V.num_dofs,
         "degree": args.degree, "q_degree": qd, "load_steps": args.steps, "newton_iterations": newton_its,
-        "krylov_iterations": krylov, "cg_rtol": args.cg_rtol, "cg_forcing": args.forcing, "fused_form": problem.fused,
+        "krylov_iterations": krylov, "cg_rtol": args.cg_rtol, "cg_forcing": args.forcing,
+        "cuda_graph_replays": solver.cg_graph_replays, "cuda_graph_error": solver.cg_graph_error, "fused_form": problem.fused,
         "setup_s": round(setup_s, 2), "solve_s": round(solve_s, 3),
         "linear_solve_s": round(solver.linear_solve_s, 3),
         "ms_per_krylov_iteration": 1e3 * solver.linear_solve_s / max(1, sum(sum(k) for k in krylov)), "form_calls": form_calls,
