@@ -67,6 +67,9 @@ class NewtonSolver:
         self._owned_mask = None
         self._cg_stream = None
         self._cg_graph_ok = True
+        self._cg_graph = None  # (key, torch.cuda.CUDAGraph) of the last captured iteration block
+        self._cg_ws = None
+        self.cg_graph_captures = 0
         self.cg_graph_error = None
         self.profile = False  # accumulate wall time of the linear solves (adds two syncs per solve)
         self.linear_solve_s = 0.0
@@ -116,13 +119,34 @@ class NewtonSolver:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t
 
+    def _cg_workspace(self, like):
+        """Persistent PCG vectors and scalars of one size / device: stable addresses let a captured
+        graph of the iteration be replayed by every later linear solve on the same problem."""
+        import torch
+
+        from .._lib import lib
+
+        ws = self._cg_ws
+        if ws is None or ws["n"] != like.numel() or ws["x"].device != like.device:
+            dev = like.device
+            z = lambda: torch.zeros(like.numel(), dtype=torch.float64, device=dev)  # noqa: E731
+            ws = {"n": like.numel(), "x": z(), "r": z(), "p": z(), "Ap": z(), "minv": z(),
+                  "scratch": torch.empty(int(lib().fcx_pcg_scratch_doubles()), dtype=torch.float64, device=dev),
+                  "ticket": torch.zeros(1, dtype=torch.int32, device=dev),
+                  "sc": torch.zeros(4, dtype=torch.float64, device=dev)}  # [rz, pAp, rz_new, rr]
+            self._cg_ws = ws
+            self._cg_graph = None
+        return ws
+
     def _solve_cg(self, apply, rhs, free_mask, diag, rtol=None):
         """Jacobi-preconditioned CG on the free dofs (projected operator P J P).  All scalars stay
         on the device; the host looks at the residual norm only every ``cg_check_every``
         iterations, so an iteration is a fixed sequence of enqueued kernels: the two element
         kernels of problem.J_apply + the three fused vector kernels of csrc/fcx_pcg.cu
         (deterministic reductions).  With several ranks the three scalars are summed over ranks
-        (NCCL all-reduce of one / two doubles)."""
+        (NCCL all-reduce of one / two doubles) and, on a partitioned mesh, the ghost values of the
+        direction are refreshed.  The returned vector is the solver's workspace: valid until the
+        next linear solve."""
         import torch
 
         from .. import _buffers as B
@@ -131,20 +155,17 @@ class NewtonSolver:
         L = lib()
         dev = rhs.device
         n = rhs.numel()
-        stream = B.current_stream_ptr(dev.index)
         own = self._owned(rhs)
         halo = self.partition.halo_update if self.partition is not None else (lambda v: None)
+        ws = self._cg_workspace(rhs)
+        x, r, p, Ap, minv, scratch, ticket, sc = (ws[k] for k in ("x", "r", "p", "Ap", "minv", "scratch", "ticket", "sc"))
         # ghost dofs are masked like constrained ones: every reduction runs over owned free dofs
         fm = (free_mask if own is None else free_mask & own).to(torch.float64)
-        minv = (fm / torch.where(diag.abs() > 0, diag, torch.ones_like(diag))).contiguous()
-        x = torch.zeros_like(rhs)
-        r = (rhs * fm).contiguous()
-        p = minv * r
+        minv.copy_(fm / torch.where(diag.abs() > 0, diag, torch.ones_like(diag)))
+        x.zero_()
+        torch.mul(rhs, fm, out=r)
+        torch.mul(minv, r, out=p)
         halo(p)
-        Ap = torch.empty_like(rhs)
-        scratch = torch.empty(int(L.fcx_pcg_scratch_doubles()), dtype=torch.float64, device=dev)
-        ticket = torch.zeros(1, dtype=torch.int32, device=dev)
-        sc = torch.zeros(4, dtype=torch.float64, device=dev)  # [rz, pAp, rz_new, rr]
         rz, pAp, new2 = sc[0:1], sc[1:2], sc[2:4]
         rz.copy_(self._rsum(torch.dot(r, p)).reshape(1))
         r0 = float(torch.sqrt(self._rsum(torch.dot(r, r))).item())
@@ -173,7 +194,7 @@ class NewtonSolver:
             return float(sc[3].item()) <= tol2  # one host synchronisation
 
         it = 0
-        if not (self.cg_cuda_graph and rhs.is_cuda):
+        if not (self.cg_cuda_graph and self._cg_graph_ok and rhs.is_cuda):
             while it < self.cg_max_it:
                 for _ in range(K):
                     iteration()
@@ -181,37 +202,50 @@ class NewtonSolver:
                 if converged():
                     break
             return x, it
-        # K eager iterations on a side stream first (first-use initialisation: tile-ticket slots of that
-        # stream, NCCL point-to-point communicators), then the same K iterations as a graph
+        # The K iterations between two host checks as ONE graph launch.  What the graph hard-wires
+        # besides the workspace: the operator's buffers and kernel choice (`graph_signature` of the
+        # object behind `apply`; None = unknown, capture again for every solve).
+        owner = getattr(apply, "__self__", None)
+        sig = owner.graph_signature() if hasattr(owner, "graph_signature") else None
+        key = (id(owner), sig, K, self.reduce_over_ranks, id(self.partition))
         side = self._cg_stream if self._cg_stream is not None else torch.cuda.Stream(device=dev)
         self._cg_stream = side
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(K):
-                iteration()
-            it += K
-            if not converged():
-                graph = None
-                if self._cg_graph_ok:
-                    try:
-                        graph = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(graph, stream=side):
-                            for _ in range(K):
-                                iteration()
-                    except RuntimeError as exc:  # e.g. a collective that cannot be captured on this stack
-                        self._cg_graph_ok = False
-                        self.cg_graph_error = str(exc)
-                        graph = None
-                while it < self.cg_max_it:
-                    if graph is not None:
-                        graph.replay()
-                        self.cg_graph_replays += 1
-                    else:
+            graph = None
+            if sig is not None and self._cg_graph is not None and self._cg_graph[0] == key:
+                graph = self._cg_graph[1]
+            else:
+                # K eager iterations on the side stream first (first-use initialisation: tile-ticket
+                # slots of that stream, NCCL point-to-point communicators), then the capture
+                self._cg_graph = None
+                for _ in range(K):
+                    iteration()
+                it += K
+                if converged():
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    return x, it
+                try:
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=side):
                         for _ in range(K):
                             iteration()
-                    it += K
-                    if converged():
-                        break
+                    self._cg_graph = (key, graph)
+                    self.cg_graph_captures += 1
+                except RuntimeError as exc:  # e.g. a collective that cannot be captured on this stack
+                    self._cg_graph_ok = False
+                    self.cg_graph_error = str(exc)
+                    graph = None
+            while it < self.cg_max_it:
+                if graph is not None:
+                    graph.replay()
+                    self.cg_graph_replays += 1
+                else:
+                    for _ in range(K):
+                        iteration()
+                it += K
+                if converged():
+                    break
         torch.cuda.current_stream(dev).wait_stream(side)
         return x, it
 

@@ -52,7 +52,7 @@ def run(V, part, steps, forcing):
         assert conv
         problem.update()
         its.append((n_it, sum(solver.krylov_iterations)))
-    its.append(("graph replays", solver.cg_graph_replays, solver.cg_graph_error))
+    its.append(("graph captures / replays", solver.cg_graph_captures, solver.cg_graph_replays, solver.cg_graph_error))
     return u, problem, its
 
 
