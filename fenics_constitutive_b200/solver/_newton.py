@@ -51,12 +51,6 @@ class NewtonSolver:
         self.cg_eta_gamma = 0.9
         self.cg_max_it = 20000
         self.cg_check_every = 10  # host convergence checks (one sync each)
-        # Krylov iterations between two host checks are captured ONCE per linear solve in a CUDA graph
-        # (our kernels, the scalar all-reduces and the ghost exchange included) and replayed: an iteration
-        # is ~8 launches of 20-300 us each, so with the mesh split over several GPUs the loop is bound by
-        # launch / Python overhead, not by the kernels.  False = enqueue every iteration from Python.
-        self.cg_cuda_graph = True
-        self.cg_graph_replays = 0
         self.reduce_over_ranks = False  # sum norms/dots over torch.distributed ranks
         # solver/partitioned.py MeshPartition (set by MeshPartition.attach): norms and dot products run
         # over OWNED dofs, ghost values of p (before every Jacobian action) and of x (after every Newton
@@ -65,12 +59,7 @@ class NewtonSolver:
         self.residual_history: list[float] = []
         self.krylov_iterations: list[int] = []
         self._owned_mask = None
-        self._cg_stream = None
-        self._cg_graph_ok = True
-        self._cg_graph = None  # (key, torch.cuda.CUDAGraph) of the last captured iteration block
         self._cg_ws = None
-        self.cg_graph_captures = 0
-        self.cg_graph_error = None
         self.profile = False  # accumulate wall time of the linear solves (adds two syncs per solve)
         self.linear_solve_s = 0.0
 
@@ -120,8 +109,7 @@ class NewtonSolver:
         return t
 
     def _cg_workspace(self, like):
-        """Persistent PCG vectors and scalars of one size / device: stable addresses let a captured
-        graph of the iteration be replayed by every later linear solve on the same problem."""
+        """Persistent PCG vectors and scalars of one size / device (no allocation per linear solve)."""
         import torch
 
         from .._lib import lib
@@ -135,7 +123,6 @@ class NewtonSolver:
                   "ticket": torch.zeros(1, dtype=torch.int32, device=dev),
                   "sc": torch.zeros(4, dtype=torch.float64, device=dev)}  # [rz, pAp, rz_new, rr]
             self._cg_ws = ws
-            self._cg_graph = None
         return ws
 
     def _solve_cg(self, apply, rhs, free_mask, diag, rtol=None):
@@ -193,60 +180,17 @@ class NewtonSolver:
         def converged():
             return float(sc[3].item()) <= tol2  # one host synchronisation
 
+        # Tried and removed (profiles/r1zr_*): the K iterations between two host checks captured as a CUDA
+        # graph (kernels, all-reduces and ghost exchange included).  On one GPU the loop is GPU-bound and the
+        # replayed graph was SLOWER (0.76 vs 0.48 ms per iteration); with the mesh split over two GPUs the
+        # replays, interleaved with eager NCCL calls on another stream, deadlocked on the 1 M-cell problem.
         it = 0
-        if not (self.cg_cuda_graph and self._cg_graph_ok and rhs.is_cuda):
-            while it < self.cg_max_it:
-                for _ in range(K):
-                    iteration()
-                it += K
-                if converged():
-                    break
-            return x, it
-        # The K iterations between two host checks as ONE graph launch.  What the graph hard-wires
-        # besides the workspace: the operator's buffers and kernel choice (`graph_signature` of the
-        # object behind `apply`; None = unknown, capture again for every solve).
-        owner = getattr(apply, "__self__", None)
-        sig = owner.graph_signature() if hasattr(owner, "graph_signature") else None
-        key = (id(owner), sig, K, self.reduce_over_ranks, id(self.partition))
-        side = self._cg_stream if self._cg_stream is not None else torch.cuda.Stream(device=dev)
-        self._cg_stream = side
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            graph = None
-            if sig is not None and self._cg_graph is not None and self._cg_graph[0] == key:
-                graph = self._cg_graph[1]
-            else:
-                # K eager iterations on the side stream first (first-use initialisation: tile-ticket
-                # slots of that stream, NCCL point-to-point communicators), then the capture
-                self._cg_graph = None
-                for _ in range(K):
-                    iteration()
-                it += K
-                if converged():
-                    torch.cuda.current_stream(dev).wait_stream(side)
-                    return x, it
-                try:
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph, stream=side):
-                        for _ in range(K):
-                            iteration()
-                    self._cg_graph = (key, graph)
-                    self.cg_graph_captures += 1
-                except RuntimeError as exc:  # e.g. a collective that cannot be captured on this stack
-                    self._cg_graph_ok = False
-                    self.cg_graph_error = str(exc)
-                    graph = None
-            while it < self.cg_max_it:
-                if graph is not None:
-                    graph.replay()
-                    self.cg_graph_replays += 1
-                else:
-                    for _ in range(K):
-                        iteration()
-                it += K
-                if converged():
-                    break
-        torch.cuda.current_stream(dev).wait_stream(side)
+        while it < self.cg_max_it:
+            for _ in range(K):
+                iteration()
+            it += K
+            if converged():
+                break
         return x, it
 
     # -------------------------------------------------------------- solve

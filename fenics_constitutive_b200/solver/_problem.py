@@ -347,16 +347,6 @@ class IncrSmallStrainProblem:
         self._gather_sum(out)
         return out
 
-    def graph_signature(self):
-        """Everything a captured launch sequence of ``J_apply`` hard-wires (kernel choice and buffer
-        addresses): NewtonSolver replays its CUDA graph of the Krylov iteration while this is unchanged."""
-        L = lib()
-        variant = L.fcx_tune(b"fem_variant", -1)
-        rec = bool(self.fused and self._trec_valid and self.use_tangent_records and variant != 0)
-        src = self._trec if rec else self.tangent.x.array
-        return (rec, variant, src.data_ptr(), self._fe.data_ptr(), self._pos_ptr(), self._dofmap.data_ptr(),
-                self._Jinv.data_ptr(), self._detJ.data_ptr(), self.num_cells, self.V.num_nodes)
-
     def J_diag(self, out=None):
         import torch
 

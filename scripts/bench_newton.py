@@ -42,7 +42,6 @@ ap.add_argument("--max-disp", type=float, default=0.012)
 ap.add_argument("--partition", action="store_true",
                 help="ONE mesh partitioned over the ranks (strong scaling; ghost values of nodal vectors exchanged "
                      "over NCCL, solver/partitioned.py) instead of one whole block per rank (weak scaling)")
-ap.add_argument("--no-graph", action="store_true", help="enqueue every Krylov iteration from Python (no CUDA graph)")
 ap.add_argument("--forcing", choices=["none", "ew"], default="none",
                 help="ew = Eisenstat-Walker forcing terms for the Krylov tolerance (inexact Newton)")
 ap.add_argument("--newton-steps-only", type=int, default=0,
@@ -84,7 +83,6 @@ solver = S.NewtonSolver(None, problem)
 solver.linear_solver = "cg"
 solver.cg_rtol = args.cg_rtol
 solver.cg_forcing = "eisenstat-walker" if args.forcing == "ew" else None
-solver.cg_cuda_graph = not args.no_graph
 solver.reduce_over_ranks = world > 1
 if part is not None:
     part.attach(solver)
@@ -177,8 +175,7 @@ if rank == 0:
         "cells_per_gpu": problem.num_cells, "qps_per_gpu": nqp, "dofs_per_gpu": V.num_dofs,
         "degree": args.degree, "q_degree": qd, "load_steps": args.steps, "newton_iterations": newton_its,
         "krylov_iterations": krylov, "cg_rtol": args.cg_rtol, "cg_forcing": args.forcing,
-        "cuda_graph_replays": solver.cg_graph_replays, "cuda_graph_captures": solver.cg_graph_captures,
-        "cuda_graph_error": solver.cg_graph_error, "fused_form": problem.fused,
+ "fused_form": problem.fused,
         "setup_s": round(setup_s, 2), "solve_s": round(solve_s, 3),
         "linear_solve_s": round(solver.linear_solve_s, 3),
         "ms_per_krylov_iteration": 1e3 * solver.linear_solve_s / max(1, sum(sum(k) for k in krylov)), "form_calls": form_calls,
