@@ -31,6 +31,7 @@ from .mesh import (
     dirichletbc,
     functionspace,
     locate_dofs_geometrical,
+    surface_load,
 )
 
 __all__ = [
@@ -38,5 +39,5 @@ __all__ = [
     "IncrementalStress", "History", "LawOnSubMesh", "QuadratureFunction", "IdentityMap", "SubSpaceMap",
     "build_subspace_map", "Mesh", "FunctionSpace", "Function", "Constant", "DirichletBC", "ElementTables",
     "create_unit_interval", "create_unit_square", "create_rectangle", "create_unit_cube", "create_box",
-    "functionspace", "dirichletbc", "locate_dofs_geometrical", "MeshPartition",
+    "functionspace", "dirichletbc", "locate_dofs_geometrical", "MeshPartition", "surface_load",
 ]

@@ -246,6 +246,50 @@ def locate_dofs_geometrical(V, marker) -> np.ndarray:
     return np.flatnonzero(marker(x)).astype(np.int64)
 
 
+def surface_load(V, marker, traction) -> np.ndarray:
+    """Consistent nodal load vector of a constant traction on the boundary facets whose vertices all
+    satisfy ``marker`` -- what the reference's tests add to the residual as
+    ``problem.R_form -= inner(t, v) * ds(tag)`` (tests/models/test_viscoelasticity.py:452-470).
+    Assign it to ``problem.f_ext``.  P1: a facet's load is split equally among its vertices; P2: a
+    triangular facet loads its three edge midpoints with a third each (vertices get nothing), an edge
+    facet its ends with 1/6 and its midpoint with 2/3."""
+    space = V.parent if isinstance(V, _SubSpace) else V
+    mesh, g = space.mesh, space.mesh.gdim
+    if g == 1:
+        raise NotImplementedError("point loads in 1D: set f_ext directly")
+    t = np.asarray(traction, dtype=np.float64).ravel()
+    assert t.size == g
+    x = np.zeros((3, mesh.coords.shape[0]))
+    x[:g] = mesh.coords.T
+    on = np.asarray(marker(x), dtype=bool)
+    f = np.zeros((space.num_nodes, g))
+    nv = g + 1
+    edges = _EDGES[g]
+    for skip in range(nv):  # facet opposite to local vertex `skip`
+        loc = [i for i in range(nv) if i != skip]
+        hit = np.flatnonzero(on[mesh.cells[:, loc]].all(axis=1))
+        if hit.size == 0:
+            continue
+        X = mesh.coords[mesh.cells[hit][:, loc]]  # [nf][g][g]
+        if g == 2:
+            area = np.linalg.norm(X[:, 1] - X[:, 0], axis=1)
+        else:
+            area = 0.5 * np.linalg.norm(np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), axis=1)
+        if space.degree == 1:
+            for i in loc:
+                np.add.at(f, space.dofmap[hit, i], (area / g)[:, None] * t[None, :])
+        else:
+            mids = [nv + e for e, (a, b) in enumerate(edges) if a in loc and b in loc]
+            if g == 2:
+                for i in loc:
+                    np.add.at(f, space.dofmap[hit, i], (area / 6.0)[:, None] * t[None, :])
+                np.add.at(f, space.dofmap[hit, mids[0]], (area * 2.0 / 3.0)[:, None] * t[None, :])
+            else:
+                for m in mids:
+                    np.add.at(f, space.dofmap[hit, m], (area / 3.0)[:, None] * t[None, :])
+    return f.ravel()
+
+
 class ElementTables:
     """Reference tables of the (degree, q_degree) pair on the mesh's simplex and
     the per-cell affine geometry, as numpy arrays (moved to HBM by the problem).

@@ -429,3 +429,142 @@ def test_relaxation_3d_visco(cls, ocls):
         assert abs(s0 - (E0 + E1) * eps) < 1e-8 and abs(s_inf - E0 * eps) < 1e-8
     assert rel_err(problem.stress_0.numpy(), opb.stress_0, 6) < 1e-9
     assert problem._time == pytest.approx(1e-8 + 200.0)
+
+
+y1b = lambda x: np.isclose(x[1], 1.0)   # noqa: E731
+z1b = lambda x: np.isclose(x[2], 1.0)   # noqa: E731
+
+
+def test_mises_uniaxial_cyclic_strain_3d():
+    """reference tests/models/test_plasticity.py:140-287 on the device stand-in: one full sine cycle of the
+    right-face displacement; the reference's own assertions (tests/test_solver_oracle.py::cyclic_checks) and
+    step-by-step parity with the CPU oracle."""
+    from test_solver_oracle import cyclic_checks
+
+    mesh = S.create_unit_cube(1, 1, 1)
+    V = S.functionspace(mesh, ("CG", 1, (3,)))
+    u = S.Function(V)
+    scalar_x, zero = S.Constant(mesh, 0.0), S.Constant(mesh, 0.0)
+    bcs = gpu_bcs(V, [(left, 0, zero), (right, 0, scalar_x), (y0b, 1, zero), (z0b, 2, zero)])
+    problem = S.IncrSmallStrainProblem(VonMises3D(MISES), u, bcs, q_degree=1)
+    solver = S.NewtonSolver(None, problem)
+    opb = F.OracleProblem(om.VonMises3D(MISES), oracle_for(problem), problem.bc_dofs_values)
+    nT, max_disp = 100, 0.05
+    displacement, load, worst = [0.0], [0.0], 0.0
+    for time in np.linspace(np.pi, -np.pi, num=nT + 1):
+        scalar_x.value = np.sin(time) * max_disp
+        n, converged = solver.solve(u)
+        assert converged
+        problem.update()
+        on, ook = opb.solve()
+        assert ook
+        opb.update()
+        worst = max(worst, rel_err(problem.stress_0.numpy(), opb.stress_0, 6))
+        displacement.append(scalar_x.value)
+        load.append(problem.stress_0.numpy()[::6][0])
+    cyclic_checks(np.array(displacement), np.array(load), nT)
+    assert worst < 1e-8
+    assert rel_err(problem._history_0[0]["eps_n"].numpy(), opb.history_0[0]["eps_n"], 6) < 1e-8
+
+
+@pytest.mark.parametrize("cls,ocls", [(SpringKelvinModel, om.SpringKelvinModel), (SpringMaxwellModel, om.SpringMaxwellModel)])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_creep_under_traction(dim, cls, ocls):
+    """reference tests/models/test_viscoelasticity.py:369-526: constant traction on the right face
+    (``problem.f_ext`` = the consistent nodal load, ``S.surface_load``), nearly elastic first step, then
+    dt = 2 up to 20 tau; 1D chain formulas for the initial and final strain, oracle parity at the end."""
+    import torch
+
+    f_max = 0.1
+    if dim == 2:
+        mesh, cons, load = S.create_unit_square(2, 2), C.PLANE_STRESS, (f_max, 0.0)
+    else:
+        mesh, cons, load = S.create_unit_cube(2, 2, 2), C.FULL, (f_max, 0.0, 0.0)
+    V = S.functionspace(mesh, ("CG", 1, (dim,)))
+    u = S.Function(V)
+    zero = S.Constant(mesh, 0.0)
+    specs = [(left, 0, zero), (y0b, 1, zero)] + ([(z0b, 2, zero)] if dim == 3 else [])
+    problem = S.IncrSmallStrainProblem(cls(VISCO, cons), u, gpu_bcs(V, specs), 1, del_t=1e-8)
+    fl = S.surface_load(V, right, load)
+    problem.f_ext.copy_(torch.from_numpy(fl).to(problem.f_ext.device))
+    solver = S.NewtonSolver(None, problem)
+    opb = F.OracleProblem(ocls(VISCO, cons), oracle_for(problem), problem.bc_dofs_values, del_t=1e-8)
+    opb.f_ext[:] = fl
+    solver.solve(u)
+    problem.update()
+    opb.solve()
+    opb.update()
+    strain = [problem._history_1[0]["strain"].numpy().max()]
+    visco = [problem._history_1[0]["strain_visco"].numpy().max()]
+    stress = [problem.stress_1.numpy().max()]
+    problem._del_t = 2.0
+    opb.dt = 2.0
+    while problem._time < 20 * VISCO["tau"]:
+        n, converged = solver.solve(u)
+        assert converged
+        problem.update()
+        opb.solve()
+        opb.update()
+        strain.append(problem._history_1[0]["strain"].numpy().max())
+        visco.append(problem._history_1[0]["strain_visco"].numpy().max())
+        stress.append(problem.stress_1.numpy().max())
+    E0, E1 = VISCO["E0"], VISCO["E1"]
+    if cls is SpringKelvinModel:
+        s0, s_inf = f_max / E0, f_max / E0 + f_max / E1
+    else:
+        s0, s_inf = f_max / (E0 + E1), f_max / E0
+    assert abs(strain[0] - s0) < 1e-8 and abs(strain[-1] - s_inf) < 1e-8
+    assert abs(stress[0] - f_max) < 1e-8
+    assert np.sum(np.diff(stress)) < 1e-8 and abs(visco[0]) < 1e-8 and visco[-1] > 0
+    assert np.abs(u.numpy() - opb.u).max() <= 1e-9 * np.abs(opb.u).max()
+    assert rel_err(problem.stress_0.numpy(), opb.stress_0, cons.stress_strain_dim) < 1e-8
+
+
+@pytest.mark.parametrize("cls", [SpringKelvinModel, SpringMaxwellModel])
+def test_visco_plane_strain_equals_3d(cls):
+    """reference tests/models/test_viscoelasticity.py:550-696: 2D PLANE_STRAIN against 3D with the z faces
+    held, dt = 5 up to 20 tau, compared at every step."""
+    runs = []
+    for dim in (2, 3):
+        if dim == 2:
+            mesh, cons = S.create_unit_square(1, 1), C.PLANE_STRAIN
+        else:
+            mesh, cons = S.create_unit_cube(1, 1, 1), C.FULL
+        V = S.functionspace(mesh, ("CG", 1, (dim,)))
+        u = S.Function(V)
+        zero = S.Constant(mesh, 0.0)
+        specs = [(left, c, zero) for c in range(dim)] + [(y1b, 1, zero), (y0b, 1, zero), (right, 0, S.Constant(mesh, 0.01))]
+        if dim == 3:
+            specs += [(z0b, 2, zero), (z1b, 2, zero)]
+        problem = S.IncrSmallStrainProblem(cls(VISCO, cons), u, gpu_bcs(V, specs), 1, del_t=5.0)
+        runs.append((u, problem, S.NewtonSolver(None, problem)))
+    while runs[0][1]._time < 20 * VISCO["tau"]:
+        for u, problem, solver in runs:
+            solver.solve(u)
+            problem.update()
+        (u2, p2, _), (u3, p3, _) = runs
+        s2, s3 = p2.stress_1.numpy(), p3.stress_1.numpy()
+        assert abs(s2[0] - s3[0]) < 1e-8 and abs(s2[1] - s3[1]) < 1e-8
+        assert abs(u2.numpy().max() - u3.numpy().max()) < 1e-8
+
+
+def test_kelvin_vs_maxwell_1d():
+    """reference tests/models/test_viscoelasticity.py:291-366: Kelvin chain vs the Maxwell chain with
+    transferred parameters, uniaxial stress, ten steps of dt = 0.1."""
+    E0, E1, tau, nu = VISCO["E0"], VISCO["E1"], VISCO["tau"], VISCO["nu"]
+    maxwell = {"E0": E0 * E1 / (E0 + E1), "E1": E0**2 / (E0 + E1), "tau": E1 / (E0 + E1) * tau, "nu": nu}
+    hist = []
+    for law in (SpringKelvinModel(VISCO, C.UNIAXIAL_STRESS), SpringMaxwellModel(maxwell, C.UNIAXIAL_STRESS)):
+        mesh = S.create_unit_interval(2)
+        V = S.functionspace(mesh, ("CG", 1))
+        u = S.Function(V)
+        bcs = gpu_bcs(V, [(left, None, S.Constant(mesh, 0.0)), (right, None, S.Constant(mesh, 0.001))])
+        problem = S.IncrSmallStrainProblem(law, u, bcs, 2, del_t=0.1)
+        solver = S.NewtonSolver(None, problem)
+        stress = []
+        while problem._time < 10 * 0.1 - 1e-12:
+            solver.solve(u)
+            problem.update()
+            stress.append(problem.stress_1.numpy()[-1])
+        hist.append(np.array(stress))
+    assert len(hist[0]) == 10 and np.linalg.norm(hist[0] - hist[1]) < 1e-8

