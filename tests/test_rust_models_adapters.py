@@ -227,3 +227,40 @@ def test_linear_hardening_uniaxial_stress_through_solver():
     assert el.sum() >= 5 and np.abs(slopes[el] - E).max() < 1e-6
     pl = load[:-1] > y0 + 1.0
     assert pl.sum() >= 5 and np.abs(slopes[pl] - E * h / (E + h)).max() < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["host", "device"])
+@pytest.mark.parametrize("lname", ["elastic", "mises"])
+@pytest.mark.parametrize("aname", ["uniaxial_strain", "plane_strain"])
+def test_gpu_adapters_match_reference_goldens(aname, lname, mode):
+    """UniaxialStrainFrom3D / PlaneStrainFrom3D around the CUDA FULL models against fixtures produced by the
+    reference's own adapters around its own models (oracle/gen_golden_adapters.py), three consecutive calls
+    on one adapter object: the persistent 3D scratch arrays behave like the reference's
+    (models/utils.py:252-273, 341-359), on the numpy path and on the device path
+    (fcx_embed_3d / fcx_extract_from_3d)."""
+    import torch
+
+    from _util import TOL_ELASTIC, TOL_PLASTIC, assert_close, golden
+    from fenics_constitutive_b200.models import LinearElasticityModel, PlaneStrainFrom3D, UniaxialStrainFrom3D, VonMises3D
+
+    G = golden("adapters.npz")
+    n, ncalls = int(G["n"]), int(G["ncalls"])
+    cls, s = (UniaxialStrainFrom3D, 1) if aname == "uniaxial_strain" else (PlaneStrainFrom3D, 4)
+    inner = (LinearElasticityModel({"E": 42.0, "nu": 0.3}, C.FULL) if lname == "elastic"
+             else VonMises3D({"p_ka": 175000.0, "p_mu": 80769.0, "p_y0": 1200.0, "p_y00": 2500.0, "p_w": 200.0}))
+    wrap = cls(inner)
+    key = f"{aname}_{lname}"
+    to = (lambda a: torch.from_numpy(a).cuda()) if mode == "device" else (lambda a: a)
+    back = (lambda a: a.cpu().numpy()) if mode == "device" else (lambda a: a)
+    stress, tangent = to(np.zeros(n * s)), to(np.full(n * s * s, np.nan))
+    history = {"eps_n": to(np.zeros(n * 6)), "alpha": to(np.zeros(n))} if lname == "mises" else None
+    tol = TOL_ELASTIC if lname == "elastic" else TOL_PLASTIC
+    for k in range(ncalls):
+        wrap.evaluate(0.0, 1.0, to(G[f"{key}_grad{k}"].copy()), stress, tangent, history)
+        assert_close(back(stress), G[f"{key}_stress{k}"], s, tol, f"{key} stress call {k}")
+        assert_close(back(tangent), G[f"{key}_tangent{k}"], s * s, tol, f"{key} tangent call {k}")
+        if history is not None:
+            assert_close(back(history["eps_n"]), G[f"{key}_eps_n{k}"], 6, tol, f"{key} eps_n call {k}")
+            assert_close(back(history["alpha"]), G[f"{key}_alpha{k}"], 1, tol, f"{key} alpha call {k}")
+            assert np.array_equal(back(history["alpha"]) > 0, G[f"{key}_alpha{k}"] > 0)
