@@ -800,7 +800,8 @@ static void plastic_wire_expand(const PlasticWire &W, size_t q0, size_t cnt, con
 // arrays.  Default 1: on this pool's hosts the direct stores lose to the records (122-133 vs 150-177
 // M QP/s, profiles/r1zf_host_wire_stats.jsonl): the whole path is bound by what host memory and the
 // link move together (~51 GB/s of PCIe traffic in both wire modes while the host threads stream the
-// tangents), and the GPU's 288-byte runs share cache lines with the host threads' fills.
+// tangents); most likely the GPU's 288-byte runs and the host threads' fills of the neighbouring
+// elastic runs fight over the partial cache lines they share (not investigated further).
 // Tried and reverted (profiles/r1zg_*): packing the records in device memory and letting a second
 // drain stage DMA exactly `count` of them -- same link rate, one more host round trip per chunk.
 static int g_wire = 1;
