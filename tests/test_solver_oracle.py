@@ -234,6 +234,31 @@ def test_kelvin_vs_maxwell_1d():
     assert len(hist[0]) == 10 and np.linalg.norm(hist[0] - hist[1]) < 1e-8
 
 
+@pytest.mark.parametrize("degree,qd", [(1, 1), (2, 2)])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_surface_load_is_consistent(dim, degree, qd):
+    """`surface_load`: the nodal forces of a constant traction sum to traction x area, and under that load
+    a linear-elastic bar with symmetry BCs answers with the homogeneous uniaxial-stress state (patch test),
+    for P1 and P2 facets."""
+    f = 0.3
+    if dim == 2:
+        mesh, cons, load = M.create_unit_square(3, 2), C.PLANE_STRESS, (f, 0.0)
+        specs = [(left, 0, [0.0]), (y0b, 1, [0.0])]
+    else:
+        mesh, cons, load = M.create_unit_cube(2, 3, 2), C.FULL, (f, 0.0, 0.0)
+        specs = [(left, 0, [0.0]), (y0b, 1, [0.0]), (z0b, 2, [0.0])]
+    V, T, fem = make(mesh, degree, qd)
+    fl = M.surface_load(V, right, load)
+    assert abs(fl.reshape(-1, dim)[:, 0].sum() - f) < 1e-14 and np.abs(fl.reshape(-1, dim)[:, 1:]).max() == 0.0
+    pb = F.OracleProblem(om.LinearElasticityModel({"E": E, "nu": NU}, cons), fem, bcs_of(V, specs))
+    pb.f_ext[:] = fl
+    n, ok = pb.solve()
+    assert ok
+    s = pb.stress_1.reshape(-1, fem.s)
+    assert np.abs(s[:, 0] - f).max() < 1e-12 and np.abs(s[:, 1:]).max() < 1e-12
+    assert np.abs(pb.u.reshape(-1, dim)[:, 0] - f / E * V.node_coords[:, 0]).max() < 1e-13
+
+
 @pytest.mark.parametrize("name", ["kelvin", "maxwell"])
 @pytest.mark.parametrize("dim", [2, 3])
 def test_creep(dim, name):
