@@ -568,3 +568,36 @@ def test_kelvin_vs_maxwell_1d():
             stress.append(problem.stress_1.numpy()[-1])
         hist.append(np.array(stress))
     assert len(hist[0]) == 10 and np.linalg.norm(hist[0] - hist[1]) < 1e-8
+
+
+def test_partition_hooks_single_rank():
+    """NewtonSolver with a MeshPartition attached (solver/partitioned.py) on ONE rank: every node is owned,
+    there is nothing to exchange, and the solve is the plain one (the multi-rank exchange itself is covered by
+    tests/test_mesh_partition.py on gloo and scripts/check_partitioned_newton.py on 2 GPUs)."""
+    mesh = S.create_unit_cube(4, 3, 2)
+    sols = []
+    for use_partition in (False, True):
+        part = S.MeshPartition(mesh, 2, 0, 1) if use_partition else None
+        V = part.V if use_partition else S.functionspace(mesh, ("CG", 2, (3,)))
+        u = S.Function(V)
+        zero, ux = S.Constant(mesh, 0.0), S.Constant(mesh, 0.0)
+        bcs = gpu_bcs(V, [(left, 0, zero), (left, 1, zero), (left, 2, zero), (right, 0, ux)])
+        problem = S.IncrSmallStrainProblem(VonMises3D(MISES), u, bcs, q_degree=2)
+        solver = S.NewtonSolver(None, problem)
+        solver.linear_solver = "cg"
+        if use_partition:
+            part.attach(solver)
+            assert part.num_owned_nodes == V.num_nodes and part.neighbours == [] and not solver.reduce_over_ranks
+        its = []
+        for k in (1, 2):
+            ux.value = 0.006 * k
+            n, converged = solver.solve(u)
+            assert converged
+            problem.update()
+            its.append(n)
+        x = u.numpy() if not use_partition else part.gather_global(u.numpy())
+        sols.append((x, its, problem.stress_0.numpy()))
+    assert sols[0][1] == sols[1][1]
+    assert np.abs(sols[0][0] - sols[1][0]).max() <= 1e-9 * np.abs(sols[0][0]).max()
+    assert rel_err(sols[1][2], sols[0][2], 6) <= 1e-8
+    assert float(np.abs(sols[0][2]).max()) > 1200.0  # the second step went plastic
