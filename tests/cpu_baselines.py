@@ -4,7 +4,9 @@
              exists, i.e. the build container), one process, small sample -- it is a per-point CPython loop;
   c_port     oracle/fcx_oracle.c (gcc -O2, OpenMP), all host threads;
   numba      oracle/numba_models.py (@njit(parallel=True)), all numba threads.
-One JSON line per baseline.  Test infrastructure: nothing here is part of the product path."""
+One JSON line per baseline.  Test infrastructure (it lives under tests/ because only tests/, smoke() and
+bench.py's CPU legs may use oracle/): nothing here is part of the product path.
+    python tests/cpu_baselines.py [--qps N --seconds S]"""
 from __future__ import annotations
 
 import argparse
