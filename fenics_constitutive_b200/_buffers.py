@@ -34,6 +34,15 @@ class Buf:
         self.device_index = device_index
 
 
+class NullBuf(Buf):
+    """An absent optional array (``tangent=None``): a NULL address on the side of ``like``."""
+
+    __slots__ = ()
+
+    def __init__(self, like: Buf):
+        super().__init__(like.kind, None, 0, None, like.device_index)
+
+
 def as_buf(a, name: str, writable: bool = False, dtype=np.float64) -> Buf:
     """Classify one array argument and return its address and element count."""
     if isinstance(a, np.ndarray):

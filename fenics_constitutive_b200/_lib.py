@@ -37,7 +37,9 @@ SIGNATURES = {
     "fcx_mises_linear_hardening_evaluate_host": (_ci, [_dp, _sz, _dp, _dp, _dp, _dp, _vp]),
     "fcx_drucker_prager_evaluate": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp, _dp, _vp, _vp, _vp]),
     "fcx_drucker_prager_evaluate_host": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp, _dp, _vp]),
-    "fcx_mises_form": (_ci, [_dp, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
+    "fcx_map_rows_to_sub": (_ci, [_sz, _sz, _vp, _dp, _dp, _vp]),
+    "fcx_map_rows_to_parent": (_ci, [_sz, _sz, _vp, _dp, _dp, _vp]),
+    "fcx_mises_form": (_ci, [_dp, _sz, _vp, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
                              _dp, _dp, _vp, _vp, _vp]),
     "fcx_tangent_apply_rec": (_ci, [_ci, _ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp]),
     "fcx_fe_stride": (_ci, [_ci]),

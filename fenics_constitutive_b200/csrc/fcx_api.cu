@@ -27,18 +27,19 @@ int note_cuda_error(cudaError_t e, const char *where)
     return FCX_ERR_CUDA;
 }
 
-static int g_sm_count = 0;
+static int g_sm_count[FCX_MAX_DEVICES] = {};  // per device index, 0 = not queried yet
 int sm_count()
 {
-    if (g_sm_count == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            g_sm_count = n;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FCX_MAX_DEVICES)
+        return 148;  // B200
+    if (g_sm_count[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_sm_count[dev] = n;
         else
-            return 148;  // B200
+            return 148;
     }
-    return g_sm_count;
+    return g_sm_count[dev];
 }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -114,17 +115,10 @@ static int launch_tile_t(const typename M::Params &prm, const SegPtrs<M::nseg()>
 {
     auto kern = fcx_tile_kernel<M, TILE>;
     constexpr size_t smem = tile_smem_bytes<M, TILE>();
-    static int occ = -1;  // per instantiation
-    if (occ < 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaFuncSetAttribute");
-        int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, TILE, smem);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-        occ = o > 0 ? o : 1;
-    }
+    static OccCache cache;  // per instantiation and device
+    int occ = 1;
+    if (int rc = kernel_occupancy(cache, kern, TILE, smem, "occupancy(fcx_tile_kernel)", &occ))
+        return rc;
     const int per_sm = g_ctas_per_sm > 0 ? g_ctas_per_sm : occ;
     const unsigned long long ntiles = (n + TILE - 1) / TILE;
     unsigned long long grid = (unsigned long long)sm_count() * per_sm;
@@ -153,25 +147,18 @@ static int launch_tile(const typename M::Params &prm, const SegPtrs<M::nseg()> &
 }
 
 // Output-staged Mises kernel (fcx_mises_ostage.cuh) over `ntiles` full tiles.
-template <int TILE, int MINCTAS>
+template <int TILE, int MINCTAS, bool WITH_TANGENT>
 static int launch_mises_ostage(const MisesParams &P, const double *grad, double *stress,
                                double *tangent, double *eps_n, double *alpha,
                                unsigned long long ntiles, unsigned char *flag, int *status,
                                cudaStream_t stream)
 {
-    auto kern = fcx_mises_ostage_kernel<TILE, MINCTAS>;
-    constexpr size_t smem = mises_ostage_smem_bytes<TILE>();
-    static int occ = -1;
-    if (occ < 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaFuncSetAttribute(mises_ostage)");
-        int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, TILE, smem);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaOccupancy(mises_ostage)");
-        occ = o > 0 ? o : 1;
-    }
+    auto kern = fcx_mises_ostage_kernel<TILE, MINCTAS, WITH_TANGENT>;
+    constexpr size_t smem = mises_ostage_smem_bytes<TILE, WITH_TANGENT>();
+    static OccCache cache;  // per instantiation and device
+    int occ = 1;
+    if (int rc = kernel_occupancy(cache, kern, TILE, smem, "occupancy(mises_ostage)", &occ))
+        return rc;
     const int per_sm = g_ctas_per_sm > 0 ? g_ctas_per_sm : occ;
     unsigned long long grid = (unsigned long long)sm_count() * per_sm;
     if (grid > ntiles)
@@ -190,17 +177,10 @@ static int launch_mises_form(const MisesParams &P, MisesFormArgs A, cudaStream_t
     constexpr int TILE = 64;
     auto kern = fcx_mises_form_kernel<ND, NQ, TILE, 8>;
     constexpr size_t smem = mises_form_smem_bytes<ND, NQ, TILE>();
-    static int occ = -1;
-    if (occ < 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaFuncSetAttribute(mises_form)");
-        int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, TILE, smem);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaOccupancy(mises_form)");
-        occ = o > 0 ? o : 1;
-    }
+    static OccCache cache;  // per instantiation and device
+    int occ = 1;
+    if (int rc = kernel_occupancy(cache, kern, TILE, smem, "occupancy(mises_form)", &occ))
+        return rc;
     constexpr int CPT = TILE / NQ;
     const unsigned long long ntiles = (A.ncells + CPT - 1) / CPT;
     const int per_sm = g_ctas_per_sm > 0 ? g_ctas_per_sm : occ;
@@ -519,7 +499,6 @@ long long fcx_diag_stream_mix(const double *src, double *dst, size_t n_qps, void
 
 int fcx_set_device(int device)
 {
-    g_sm_count = 0;
     return note_cuda_error(cudaSetDevice(device), "cudaSetDevice");
 }
 
@@ -528,7 +507,7 @@ int fcx_elastic_evaluate(int constraint, const double *D, size_t n, const double
 {
     if (n == 0)
         return FCX_OK;
-    if (!D || !grad || !stress || !tangent)
+    if (!D || !grad || !stress)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (constraint) {
@@ -547,7 +526,7 @@ int fcx_mises_evaluate(const double *params, size_t n, const double *grad, doubl
 {
     if (n == 0)
         return FCX_OK;
-    if (!params || !grad || !stress || !tangent || !eps_n || !alpha)
+    if (!params || !grad || !stress || !eps_n || !alpha)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MisesParams P{params[0], params[1], params[2], params[3], params[4], g_mises_nmax};
@@ -567,17 +546,23 @@ int fcx_mises_evaluate(const double *params, size_t n, const double *grad, doubl
         const unsigned long long ntiles = n / T;
         const size_t nfull = (size_t)ntiles * T;
         int rc = FCX_OK;
-        if (ntiles > 0)
+        if (ntiles > 0 && tangent != nullptr)
             rc = (g_mises_tile == 64)
-                     ? launch_mises_ostage<64, 8>(P, grad, stress, tangent, eps_n, alpha, ntiles,
-                                                  plastic_flag, status, st)
-                     : launch_mises_ostage<128, 4>(P, grad, stress, tangent, eps_n, alpha, ntiles,
-                                                   plastic_flag, status, st);
+                     ? launch_mises_ostage<64, 8, true>(P, grad, stress, tangent, eps_n, alpha, ntiles,
+                                                        plastic_flag, status, st)
+                     : launch_mises_ostage<128, 4, true>(P, grad, stress, tangent, eps_n, alpha, ntiles,
+                                                         plastic_flag, status, st);
+        else if (ntiles > 0)  // stress-only: no tangent staging, no tangent store (280 B/QP)
+            rc = (g_mises_tile == 64)
+                     ? launch_mises_ostage<64, 8, false>(P, grad, stress, nullptr, eps_n, alpha, ntiles,
+                                                         plastic_flag, status, st)
+                     : launch_mises_ostage<128, 4, false>(P, grad, stress, nullptr, eps_n, alpha, ntiles,
+                                                          plastic_flag, status, st);
         if (rc != FCX_OK || nfull == n)
             return rc;
         SegPtrs<4> tail{{const_cast<double *>(grad) + nfull * 9, stress + nfull * 6,
                          eps_n + nfull * 6, alpha + nfull}};
-        return launch_tile<MisesModel<false>>(P, tail, tangent + nfull * 36, n - nfull, al,
+        return launch_tile<MisesModel<false>>(P, tail, tangent ? tangent + nfull * 36 : nullptr, n - nfull, al,
                                               plastic_flag ? plastic_flag + nfull : nullptr,
                                               status, st, nfull);
     }
@@ -590,7 +575,7 @@ int fcx_mises_linear_hardening_evaluate(const double *params, size_t n, const do
 {
     if (n == 0)
         return FCX_OK;
-    if (!params || !grad || !stress || !tangent || !history)
+    if (!params || !grad || !stress || !history)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     MisesLinParams P{params[0], params[1], params[2], params[3]};
     SegPtrs<3> io{{const_cast<double *>(grad), stress, history}};
@@ -605,7 +590,7 @@ int fcx_drucker_prager_evaluate(int hyperbolic, const double *params, size_t n, 
 {
     if (n == 0)
         return FCX_OK;
-    if (!params || !grad || !stress || !tangent || !history)
+    if (!params || !grad || !stress || !history)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     DruckerPragerParams P;
     P.mu = params[0];
@@ -623,7 +608,7 @@ int fcx_drucker_prager_evaluate(int hyperbolic, const double *params, size_t n, 
     return launch_tile<DruckerPragerModel<false>>(P, io, tangent, n, al, plastic_flag, status, st);
 }
 
-int fcx_mises_form(const double *params, size_t ncells, int nq, int nd, const int *dofmap,
+int fcx_mises_form(const double *params, size_t ncells, const int *cells, int nq, int nd, const int *dofmap,
                    const double *u, const double *u_prev, const double *dphi_ref,
                    const double *Jinv, const double *stress_prev, double *stress_cur,
                    double *tangent, const double *eps_n0, double *eps_n1, const double *alpha0,
@@ -634,11 +619,12 @@ int fcx_mises_form(const double *params, size_t ncells, int nq, int nd, const in
         return FCX_OK;
     if (tangent_rec && !aligned16(tangent_rec))
         return FCX_ERR_ARG;
-    if (!params || !dofmap || !u || !dphi_ref || !Jinv || !stress_prev || !stress_cur || !tangent ||
-        !eps_n0 || !eps_n1 || !alpha0 || !alpha1)
+    if (!params || !dofmap || !u || !dphi_ref || !Jinv || !stress_prev || !stress_cur ||
+        !eps_n0 || !eps_n1 || !alpha0 || !alpha1)  // tangent == NULL: stress-only
         return FCX_ERR_NULL;
     MisesParams P{params[0], params[1], params[2], params[3], params[4], g_mises_nmax};
     MisesFormArgs A;
+    A.cells = cells;
     A.dofmap = dofmap;
     A.u = u;
     A.u_prev = u_prev;
@@ -678,7 +664,7 @@ int fcx_kelvin_evaluate(int constraint, const double *D0, const double *I2, doub
         return FCX_ERR_TIMESTEP;
     if (n == 0)
         return FCX_OK;
-    if (!D0 || !I2 || !grad || !stress || !tangent || !ev || !et)
+    if (!D0 || !I2 || !grad || !stress || !ev || !et)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (constraint) {
@@ -702,7 +688,7 @@ int fcx_maxwell_evaluate(int constraint, const double *D0, const double *D1, dou
         return FCX_ERR_TIMESTEP;
     if (n == 0)
         return FCX_OK;
-    if (!D0 || !D1 || !grad || !stress || !tangent || !ev || !et)
+    if (!D0 || !D1 || !grad || !stress || !ev || !et)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (constraint) {

@@ -505,18 +505,10 @@ static int launch_qp_cell(const CellArgs &A0, cudaStream_t st)
 {
     using Cfg = CellCfg<G, S, ND, NQ, MODE>;
     auto kern = qp_cell_kernel<G, S, ND, NQ, MODE>;
-    static int occ = -1;
-    if (occ < 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)Cfg::smem_bytes);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaFuncSetAttribute(qp_cell)");
-        int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, Cfg::TILE, Cfg::smem_bytes);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaOccupancy(qp_cell)");
-        occ = o > 0 ? o : 1;
-    }
+    static OccCache cache;  // per device
+    int occ = 1;
+    if (int rc = kernel_occupancy(cache, kern, Cfg::TILE, Cfg::smem_bytes, "occupancy(qp_cell)", &occ))
+        return rc;
     CellArgs A = A0;
     const unsigned long long ntiles = (A.ncells + Cfg::CPT - 1) / Cfg::CPT;
     const int per_sm = tuned_ctas_per_sm() > 0 ? tuned_ctas_per_sm() : occ;

@@ -350,18 +350,10 @@ static int launch_gather_plain(size_t ncells, const int *dofmap, const double *u
 {
     using Cfg = GatherCfg<G, ND, NQ>;
     auto kern = gather_kernel<G, ND, NQ>;
-    static int occ = -1;
-    if (occ < 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)Cfg::smem_bytes);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaFuncSetAttribute(gather)");
-        int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, Cfg::THREADS, Cfg::smem_bytes);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaOccupancy(gather)");
-        occ = o > 0 ? o : 1;
-    }
+    static OccCache cache;  // per device
+    int occ = 1;
+    if (int rc = kernel_occupancy(cache, kern, Cfg::THREADS, Cfg::smem_bytes, "occupancy(gather)", &occ))
+        return rc;
     const unsigned long long ntiles = (ncells + Cfg::CPT - 1) / Cfg::CPT;
     const int per_sm = tuned_ctas_per_sm() > 0 ? tuned_ctas_per_sm() : occ;
     unsigned long long grid = (unsigned long long)sm_count() * per_sm;
@@ -383,18 +375,10 @@ static int launch_gather_staged(size_t nfull_cells, const int *dofmap, const dou
     using Cfg = GatherCfg<G, ND, NQ>;
     using SC = StagedCfg<G, ND, NQ, PREV>;
     auto kern = gather_staged_kernel<G, ND, NQ, PREV>;
-    static int occ = -1;
-    if (occ < 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)SC::smem_bytes);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaFuncSetAttribute(gather staged)");
-        int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, Cfg::THREADS, SC::smem_bytes);
-        if (e != cudaSuccess)
-            return note_cuda_error(e, "cudaOccupancy(gather staged)");
-        occ = o > 0 ? o : 1;
-    }
+    static OccCache cache;  // per device
+    int occ = 1;
+    if (int rc = kernel_occupancy(cache, kern, Cfg::THREADS, SC::smem_bytes, "occupancy(gather staged)", &occ))
+        return rc;
     const unsigned long long ntiles = nfull_cells / Cfg::CPT;
     const int per_sm = tuned_ctas_per_sm() > 0 ? tuned_ctas_per_sm() : occ;
     unsigned long long grid = (unsigned long long)sm_count() * per_sm;

@@ -760,10 +760,12 @@ static void plastic_wire_expand(const PlasticWire &W, size_t q0, size_t cnt, con
                 tm[k] = _mm_loadu_pd(W.tmpl + 2 * k);
             size_t rr = r0;
             for (size_t q = a; q < b; ++q) {
-                double *T = W.tangent + (q0 + q) * 36;
+                // W.tangent == nullptr: stress-only call, the records carry the history alone
+                double *T = W.tangent ? W.tangent + (q0 + q) * 36 : nullptr;
                 if (flag[q]) {
                     const double *P = rec + rr * R;
-                    if (W.nt == 21) {
+                    if (T == nullptr) {
+                    } else if (W.nt == 21) {
                         double full[36];
                         int k = 0;
                         for (int i = 0; i < 6; ++i)
@@ -781,6 +783,7 @@ static void plastic_wire_expand(const PlasticWire &W, size_t q0, size_t cnt, con
                         H += W.hw[h];
                     }
                     ++rr;
+                } else if (T == nullptr) {
                 } else if (nts) {
                     for (int m = 0; m < 18; ++m)
                         _mm_stream_pd(T + 2 * m, tm[m]);
@@ -905,6 +908,10 @@ static int run_pipeline_const_tangent(HostArr *arr, int narr, int tangent_idx, i
                                       Launch &&launch)
 {
     double *tangent = (double *)arr[tangent_idx].dst;
+    if (tangent == nullptr) {  // stress-only call: the tangent has no device slot either
+        arr[tangent_idx].bpq = 0;
+        return run_pipeline(arr, narr, n, launch);
+    }
     if (!g_wire || n < 4096 || ss > 36)
         return run_pipeline(arr, narr, n, launch);
     double tmpl[36];
@@ -993,7 +1000,8 @@ template <class Launch>
 static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
 {
     const size_t d = sizeof(double);
-    const size_t bpq[6] = {d * 9, d * 6, d * 36, d * H.hw[0], H.nh > 1 ? d * H.hw[1] : 0, 1};
+    // H.tangent == nullptr (stress-only call): no tangent slot on the device, none on the wire
+    const size_t bpq[6] = {d * 9, d * 6, H.tangent ? d * 36 : 0, d * H.hw[0], H.nh > 1 ? d * H.hw[1] : 0, 1};
     if (g_wire && n >= 4096) {
         // elastic tangent as the kernel produces it: one virgin point with a zero increment
         // (elastic for any sensible parameter set; otherwise fall through to the plain path)
@@ -1020,7 +1028,7 @@ static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
             if (rc != FCX_OK)
                 return rc;
             unsigned char f0 = 1;
-            e = cudaMemcpyAsync(W.tmpl, dev[2], sizeof W.tmpl, cudaMemcpyDeviceToHost, st);
+            e = H.tangent ? cudaMemcpyAsync(W.tmpl, dev[2], sizeof W.tmpl, cudaMemcpyDeviceToHost, st) : cudaSuccess;
             if (e == cudaSuccess)
                 e = cudaMemcpyAsync(&f0, dev[5], 1, cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess)
@@ -1041,8 +1049,8 @@ static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
                 W.hw[h] = h < H.nh ? H.hw[h] : 0;
             }
             W.user_flag = H.flag;
-            W.nt = H.symmetric ? 21 : 36;
-            if (g_wire >= 2 && (reinterpret_cast<uintptr_t>(H.tangent) & 15u) == 0) {
+            W.nt = H.tangent == nullptr ? 0 : (H.symmetric ? 21 : 36);
+            if (g_wire >= 2 && H.tangent != nullptr && (reinterpret_cast<uintptr_t>(H.tangent) & 15u) == 0) {
                 W.tangent_dev = (double *)device_alias(H.tangent, n * 36 * d);
                 if (W.tangent_dev != nullptr && (reinterpret_cast<uintptr_t>(W.tangent_dev) & 15u) == 0)
                     W.nt = 0;
@@ -1226,13 +1234,13 @@ int fcx_elastic_evaluate_host(int constraint, const double *D, size_t n, const d
         return FCX_ERR_CONSTRAINT;
     if (n == 0)
         return FCX_OK;
-    if (!D || !grad || !stress || !tangent)
+    if (!D || !grad || !stress)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     const size_t d = sizeof(double);
     HostArr arr[3] = {{grad, nullptr, d * g * g}, {stress, stress, d * s}, {nullptr, tangent, d * s * s}};
     return run_pipeline_const_tangent(arr, 3, 2, s * s, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
         return fcx_elastic_evaluate(constraint, D, cnt, (const double *)dev[0], (double *)dev[1],
-                                    (double *)dev[2], st);
+                                    tangent ? (double *)dev[2] : nullptr, st);
     });
 }
 
@@ -1242,12 +1250,12 @@ int fcx_mises_evaluate_host(const double *params, size_t n, const double *grad, 
 {
     if (n == 0)
         return FCX_OK;
-    if (!params || !grad || !stress || !tangent || !eps_n || !alpha)
+    if (!params || !grad || !stress || !eps_n || !alpha)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     const PlasticHost H{grad, stress, tangent, 2, {eps_n, alpha}, {6, 1}, plastic_flag, true};
     return run_plastic_host(H, n, [&](void **dev, size_t cnt, cudaStream_t st, int *status) {
         return fcx_mises_evaluate(params, cnt, (const double *)dev[0], (double *)dev[1],
-                                  (double *)dev[2], (double *)dev[3], (double *)dev[4],
+                                  tangent ? (double *)dev[2] : nullptr, (double *)dev[3], (double *)dev[4],
                                   FCX_LAYOUT_AOS, (unsigned char *)dev[5], status, st);
     });
 }
@@ -1258,14 +1266,14 @@ int fcx_mises_linear_hardening_evaluate_host(const double *params, size_t n, con
 {
     if (n == 0)
         return FCX_OK;
-    if (!params || !grad || !stress || !tangent || !history)
+    if (!params || !grad || !stress || !history)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     // full 36-entry records on the slot wire: kappa*1(x)1 + c*P_dev + c'*n n^T is symmetric too, but
     // nothing pins that bit for bit for this model, so the triangle shortcut is not taken
     const PlasticHost H{grad, stress, tangent, 1, {history, nullptr}, {7, 0}, plastic_flag, false};
     return run_plastic_host(H, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
         return fcx_mises_linear_hardening_evaluate(params, cnt, (const double *)dev[0], (double *)dev[1],
-                                                   (double *)dev[2], (double *)dev[3],
+                                                   tangent ? (double *)dev[2] : nullptr, (double *)dev[3],
                                                    (unsigned char *)dev[5], st);
     });
 }
@@ -1276,13 +1284,13 @@ int fcx_drucker_prager_evaluate_host(int hyperbolic, const double *params, size_
 {
     if (n == 0)
         return FCX_OK;
-    if (!params || !grad || !stress || !tangent || !history)
+    if (!params || !grad || !stress || !history)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     // non-associated flow makes the tangent non-symmetric: full records
     const PlasticHost H{grad, stress, tangent, 1, {history, nullptr}, {7, 0}, plastic_flag, false};
     return run_plastic_host(H, n, [&](void **dev, size_t cnt, cudaStream_t st, int *status) {
         return fcx_drucker_prager_evaluate(hyperbolic, params, cnt, (const double *)dev[0],
-                                           (double *)dev[1], (double *)dev[2], (double *)dev[3],
+                                           (double *)dev[1], tangent ? (double *)dev[2] : nullptr, (double *)dev[3],
                                            (unsigned char *)dev[5], status, st);
     });
 }
@@ -1299,14 +1307,14 @@ int fcx_kelvin_evaluate_host(int constraint, const double *D0, const double *I2,
         return FCX_ERR_TIMESTEP;
     if (n == 0)
         return FCX_OK;
-    if (!D0 || !I2 || !grad || !stress || !tangent || !ev || !et)
+    if (!D0 || !I2 || !grad || !stress || !ev || !et)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     const size_t d = sizeof(double);
     HostArr arr[5] = {{grad, nullptr, d * g * g}, {stress, stress, d * s},
                       {nullptr, tangent, d * s * s}, {ev, ev, d * s}, {et, et, d * s}};
     return run_pipeline_const_tangent(arr, 5, 2, s * s, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
         return fcx_kelvin_evaluate(constraint, D0, I2, mu0, lam0, mu1, tau, del_t, cnt,
-                                   (const double *)dev[0], (double *)dev[1], (double *)dev[2],
+                                   (const double *)dev[0], (double *)dev[1], tangent ? (double *)dev[2] : nullptr,
                                    (double *)dev[3], (double *)dev[4], st);
     });
 }
@@ -1322,14 +1330,14 @@ int fcx_maxwell_evaluate_host(int constraint, const double *D0, const double *D1
         return FCX_ERR_TIMESTEP;
     if (n == 0)
         return FCX_OK;
-    if (!D0 || !D1 || !grad || !stress || !tangent || !ev || !et)
+    if (!D0 || !D1 || !grad || !stress || !ev || !et)  // tangent == NULL: stress-only evaluate
         return FCX_ERR_NULL;
     const size_t d = sizeof(double);
     HostArr arr[5] = {{grad, nullptr, d * g * g}, {stress, stress, d * s},
                       {nullptr, tangent, d * s * s}, {ev, ev, d * s}, {et, et, d * s}};
     return run_pipeline_const_tangent(arr, 5, 2, s * s, n, [&](void **dev, size_t cnt, cudaStream_t st, int *) {
         return fcx_maxwell_evaluate(constraint, D0, D1, mu1, tau, del_t, cnt,
-                                    (const double *)dev[0], (double *)dev[1], (double *)dev[2],
+                                    (const double *)dev[0], (double *)dev[1], tangent ? (double *)dev[2] : nullptr,
                                     (double *)dev[3], (double *)dev[4], st);
     });
 }

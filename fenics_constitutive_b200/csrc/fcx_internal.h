@@ -18,4 +18,44 @@ int tuned_ctas_per_sm();
 int fem_variant();
 // fcx_tune "gather_variant": 1 = gather_staged_kernel (cp.async-staged nodal values), 0 = gather_kernel.
 int gather_variant();
+
+// Resident CTAs per SM of `kern` at (threads, smem), with the opt-in to > 48 KB of dynamic shared
+// memory set first.  Both are properties of (kernel, DEVICE): a process may drive several GPUs (the
+// Python layer binds every call to the device that owns the tensors), so the cache is per device
+// index, one OccCache per kernel instantiation (a function-local static of its launcher).
+constexpr int FCX_MAX_DEVICES = 64;
+struct OccCache {
+    int v[FCX_MAX_DEVICES];
+    OccCache()
+    {
+        for (int i = 0; i < FCX_MAX_DEVICES; ++i)
+            v[i] = -1;
+    }
+};
+template <class Kern>
+static inline int kernel_occupancy(OccCache &cache, Kern kern, int threads, size_t smem, const char *what,
+                                   int *occ_out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return note_cuda_error(e, what);
+    const bool cached = dev >= 0 && dev < FCX_MAX_DEVICES;
+    if (cached && cache.v[dev] > 0) {
+        *occ_out = cache.v[dev];
+        return 0;
+    }
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return note_cuda_error(e, what);
+    int o = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, smem);
+    if (e != cudaSuccess)
+        return note_cuda_error(e, what);
+    o = o > 0 ? o : 1;
+    if (cached)
+        cache.v[dev] = o;
+    *occ_out = o;
+    return 0;
+}
 }  // namespace fcx

@@ -12,6 +12,13 @@
 // and WRITES the trial arrays (stress_cur, eps_n1, alpha1, tangent), and
 // grad_del_u never goes to memory unless the caller asks for it.
 //
+// A law that owns only part of the mesh (reference LawOnSubMesh with a SubSpaceMap,
+// solver/maps.py:62-123, _lawonsubmesh.py:58-70) passes its cell list `cells`: dofmap / Jinv / the
+// history arrays are then indexed by the law's LOCAL cell number (they live on the sub-mesh), while
+// stress_prev / stress_cur / tangent / tangent_rec are rows cells[c] of the PARENT arrays -- the
+// map_to_sub / map_to_parent passes (a read and a write of every stress and tangent byte) are
+// folded into the bulk copies, one per cell row instead of one per tile.
+//
 // Same staging as fcx_mises_ostage.cuh: thread t owns QP t of a tile of TILE
 // QPs (= TILE/NQ whole cells); committed state comes in with bulk async copies
 // while the threads gather their cell's nodal increments (L1/L2-resident) and
@@ -30,6 +37,7 @@ constexpr size_t mises_form_smem_bytes()
 }
 
 struct MisesFormArgs {
+    const int *cells;           // [ncells] parent cell of local cell c, or nullptr (law on every cell)
     const int *dofmap;          // [ncells][ND]
     const double *u;            // [nnodes][3]
     const double *u_prev;       // [nnodes][3] or nullptr
@@ -39,7 +47,7 @@ struct MisesFormArgs {
     const double *eps0;         // [n][6]
     const double *alpha0;       // [n]
     double *stress_cur;         // [n][6]
-    double *tangent;            // [n][36]
+    double *tangent;            // [n][36] or nullptr (stress-only: residual evaluations, or J from the records)
     double *eps1;               // [n][6]
     double *alpha1;             // [n]
     double *grad_out;           // [n][9] or nullptr
@@ -91,7 +99,15 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
             if (bulk) {
                 bulk_wait_read_all();  // previous tile's stores have left shared memory
                 mbar_arrive_expect_tx(bar, (uint32_t)(13 * TILE * sizeof(double)));
-                bulk_g2s(s_sig, A.stress_prev + q0 * 6, TILE * 6 * sizeof(double), bar);
+                if (A.cells == nullptr) {
+                    bulk_g2s(s_sig, A.stress_prev + q0 * 6, TILE * 6 * sizeof(double), bar);
+                } else {
+                    const int *pc = A.cells + q0 / NQ;
+#pragma unroll 4
+                    for (int lc = 0; lc < CPT; ++lc)
+                        bulk_g2s(s_sig + lc * NQ * 6, A.stress_prev + (size_t)pc[lc] * NQ * 6,
+                                 NQ * 6 * sizeof(double), bar);
+                }
                 bulk_g2s(s_eps, A.eps0 + q0 * 6, TILE * 6 * sizeof(double), bar);
                 bulk_g2s(s_alp, A.alpha0 + q0, TILE * sizeof(double), bar);
             }
@@ -100,10 +116,12 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
         // ---- grad_del_u of this thread's QP, in registers (overlaps the loads) ----
         double g[9];
         const bool active = tid < cnt;
+        unsigned long long qp_parent;  // this thread's QP in the parent arrays
         {
             // idle lanes of the ragged last tile clamp to the last cell; nothing of theirs is stored
             unsigned long long c = q0 / NQ + tid / NQ;
             c = c < A.ncells ? c : A.ncells - 1;
+            qp_parent = (A.cells != nullptr ? (unsigned long long)A.cells[c] : c) * NQ + tid % NQ;
             const int q = tid % NQ;
             double K[9];
 #pragma unroll
@@ -144,7 +162,7 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
             } else {
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
-                    sig[i] = A.stress_prev[qg * 6 + i];
+                    sig[i] = A.stress_prev[qp_parent * 6 + i];
                     ep[i] = A.eps0[qg * 6 + i];
                 }
                 al = A.alpha0[qg];
@@ -169,13 +187,13 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
             } else {
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
-                    A.stress_cur[qg * 6 + i] = sig[i];
+                    A.stress_cur[qp_parent * 6 + i] = sig[i];
                     A.eps1[qg * 6 + i] = ep[i];
                 }
                 A.alpha1[qg] = al;
             }
             if (A.trec != nullptr) {  // 80 B instead of 288: what the matrix-free Jacobian action reads
-                double *r = A.trec + qg * 10;
+                double *r = A.trec + qp_parent * 10;
                 *reinterpret_cast<double2 *>(r + 0) = make_double2(coef[0], coef[1]);
                 *reinterpret_cast<double2 *>(r + 2) = make_double2(coef[2], coef[3]);
                 *reinterpret_cast<double2 *>(r + 4) = make_double2(xn[0], xn[1]);
@@ -191,7 +209,9 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
                                                 : ((i == j) ? coef[2] : 0.0);
                     c[i][j] = base + coef[3] * (xn[i] * xn[j]);  // (:170-175)
                 }
-            if (bulk) {
+            if (A.tangent == nullptr) {
+                // stress-only call
+            } else if (bulk) {
                 double *row = s_tan + tid * 36;
 #pragma unroll
                 for (int i = 0; i < 6; ++i)
@@ -202,7 +222,7 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
                         *reinterpret_cast<double2 *>(row + i * 6 + j) = make_double2(a, b);
                     }
             } else {
-                double *row = A.tangent + qg * 36;
+                double *row = A.tangent + qp_parent * 36;
 #pragma unroll
                 for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -214,8 +234,20 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
             fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0 && bulk) {
-            bulk_s2g(A.tangent + q0 * 36, s_tan, TILE * 36 * sizeof(double));
-            bulk_s2g(A.stress_cur + q0 * 6, s_sig, TILE * 6 * sizeof(double));
+            if (A.cells == nullptr) {
+                if (A.tangent != nullptr)
+                    bulk_s2g(A.tangent + q0 * 36, s_tan, TILE * 36 * sizeof(double));
+                bulk_s2g(A.stress_cur + q0 * 6, s_sig, TILE * 6 * sizeof(double));
+            } else {
+                const int *pc = A.cells + q0 / NQ;
+#pragma unroll 4
+                for (int lc = 0; lc < CPT; ++lc) {
+                    const size_t pq = (size_t)pc[lc] * NQ;
+                    if (A.tangent != nullptr)
+                        bulk_s2g(A.tangent + pq * 36, s_tan + lc * NQ * 36, NQ * 36 * sizeof(double));
+                    bulk_s2g(A.stress_cur + pq * 6, s_sig + lc * NQ * 6, NQ * 6 * sizeof(double));
+                }
+            }
             bulk_s2g(A.eps1 + q0 * 6, s_eps, TILE * 6 * sizeof(double));
             bulk_s2g(A.alpha1 + q0, s_alp, TILE * sizeof(double));
             bulk_commit();

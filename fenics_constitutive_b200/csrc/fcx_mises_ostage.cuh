@@ -25,13 +25,16 @@
 
 namespace fcx {
 
-template <int TILE>
+// WITH_TANGENT = false: stress-only evaluate (the reference's `tangent: Option<..>`,
+// comfe-rs/src/interfaces.rs:368, bindings/src/lib.rs:83,109-113): region B shrinks to the
+// grad_del_u slots [T][9], nothing of the tangent is formed or stored (280 instead of 568 B/QP).
+template <int TILE, bool WITH_TANGENT = true>
 constexpr size_t mises_ostage_smem_bytes()
 {
-    return sizeof(double) * 49 * TILE + sizeof(uint64_t);
+    return sizeof(double) * (WITH_TANGENT ? 49 : 22) * TILE + sizeof(uint64_t);
 }
 
-template <int TILE, int MINCTAS>
+template <int TILE, int MINCTAS, bool WITH_TANGENT = true>
 __global__ void __launch_bounds__(TILE, MINCTAS)
     fcx_mises_ostage_kernel(const __grid_constant__ MisesParams P, const double *__restrict__ grad,
                             double *__restrict__ stress, double *__restrict__ tangent,
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
     double *s_eps = smem + 6 * TILE;   // [TILE][6]
     double *s_alp = smem + 12 * TILE;  // [TILE]
     double *s_tan = smem + 13 * TILE;  // [TILE][36]; grad [TILE][9] at its head on load
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 49 * TILE);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (WITH_TANGENT ? 49 : 22) * TILE);
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
         }
         s_alp[tid] = al;
 
+        if constexpr (WITH_TANGENT) {
         // aah = ka*xioi + cpp*xpp + cnn*outer(xn, xn)   (:170-175), symmetric:
         // 21 unique entries, evaluated as base + cnn*(xn_i*xn_j) like the reference.
         double c[6][6];
@@ -129,11 +133,13 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
                 const double b = (i <= j + 1) ? c[i][j + 1] : c[j + 1][i];
                 *reinterpret_cast<double2 *>(row + i * 6 + j) = make_double2(a, b);
             }
+        }
 
         fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0) {
-            bulk_s2g(tangent + q0 * 36, s_tan, TILE * 36 * sizeof(double));
+            if constexpr (WITH_TANGENT)
+                bulk_s2g(tangent + q0 * 36, s_tan, TILE * 36 * sizeof(double));
             bulk_s2g(stress + q0 * 6, s_sig, TILE * 6 * sizeof(double));
             bulk_s2g(eps_n + q0 * 6, s_eps, TILE * 6 * sizeof(double));
             bulk_s2g(alpha + q0, s_alp, TILE * sizeof(double));

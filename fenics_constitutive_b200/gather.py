@@ -58,7 +58,12 @@ def lagrange_gradients(gdim: int, degree: int, points: np.ndarray) -> np.ndarray
 
 
 def simplex_quadrature(gdim: int, degree: int) -> tuple[np.ndarray, np.ndarray]:
-    """(points [nq][gdim], weights [nq]) exact to `degree` (1 or 2) on the reference simplex."""
+    """(points [nq][gdim], weights [nq]) exact to `degree` (1 or 2) on the reference simplex.
+    The reference takes any degree basix offers (_incrementalunknowns.py:21-22); only the rules the
+    fused kernels are specialised for exist here, and a higher degree is refused rather than
+    silently integrated with the degree-2 rule (the QP count would differ from the reference's)."""
+    if degree not in (0, 1, 2):
+        raise NotImplementedError(f"simplex_quadrature: q_degree must be 1 or 2 (got {degree})")
     if gdim == 1:
         if degree <= 1:
             return np.array([[0.5]]), np.array([1.0])

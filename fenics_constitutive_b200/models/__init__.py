@@ -14,7 +14,10 @@ from .spring_maxwell_model import SpringMaxwellModel
 from .utils import *  # noqa: F401,F403
 
 __all__ = [
+    "DruckerPrager3D",
+    "DruckerPragerHyperbolic3D",
     "IncrSmallStrainModel",
+    "LinearElasticity3D",
     "LinearElasticityModel",
     "MisesPlasticityLinearHardening3D",
     "SpringKelvinModel",

@@ -18,8 +18,10 @@ class CudaModel(IncrSmallStrainModel):
         g, s = self.geometric_dim, self.stress_strain_dim
         bg = B.as_buf(grad_del_u, "grad_del_u")
         bs = B.as_buf(stress, "stress", writable=True)
-        bt = B.as_buf(tangent, "tangent", writable=True)
-        assert bg.size // (g**2) == bs.size // s == bt.size // (s**2), (
+        # tangent=None: stress-only evaluate, as the reference's compiled models allow
+        # (`tangent: Option<..>`, bindings/src/lib.rs:83,109-113; comfe-rs/src/interfaces.rs:368)
+        bt = B.as_buf(tangent, "tangent", writable=True) if tangent is not None else B.NullBuf(bg)
+        assert bg.size // (g**2) == bs.size // s and (tangent is None or bs.size // s == bt.size // (s**2)), (
             "grad_del_u, stress and tangent disagree on the number of quadrature points"
         )
         n = bg.size // (g**2)

@@ -54,7 +54,7 @@ class VonMises3D(CudaModel):
         self.plastic_flag = None
         self.defer_errors = False
         self.eps_layout = "aos"
-        self._status = {}  # device index -> (int32[2] tensor, failures already reported)
+        self._status = {}  # device index -> int32[2] tensor [failed points, first failing index]
 
     def _params(self) -> np.ndarray:
         return np.array([self.p_ka, self.p_mu, self.p_y0, self.p_y00, self.p_w], dtype=np.float64)
@@ -63,19 +63,20 @@ class VonMises3D(CudaModel):
         import torch
 
         if dev not in self._status:
-            st = torch.tensor([0, _INT_MAX], dtype=torch.int32, device=f"cuda:{dev}")
-            self._status[dev] = [st, 0]
-        return self._status[dev][0]
+            self._status[dev] = torch.tensor([0, _INT_MAX], dtype=torch.int32, device=f"cuda:{dev}")
+        return self._status[dev]
 
     def check_converged(self) -> None:
-        """Raise RuntimeError if any Newton iteration launched so far failed
-        (synchronises the device)."""
-        for dev, entry in self._status.items():
-            st, seen = entry
+        """Raise RuntimeError if any Newton iteration launched since the last check failed
+        (synchronises the device).  The device status word is reset when a failure is reported,
+        so the count and the first index of the next report belong to later calls only."""
+        import torch
+
+        for dev, st in self._status.items():
             count, first = (int(v) for v in st.cpu())
-            if count > seen:
-                entry[1] = count
-                raise RuntimeError(f"{_NEWTON_MSG} ({count - seen} point(s), first index {first})")
+            if count > 0:
+                st.copy_(torch.tensor([0, _INT_MAX], dtype=torch.int32))
+                raise RuntimeError(f"{_NEWTON_MSG} ({count} point(s), first index {first})")
 
     def evaluate(self, time, del_t, grad_del_u, mandel_stress, tangent, history) -> None:
         n, kind, bufs, dev = self._collect(

@@ -178,6 +178,12 @@ class _DruckerPragerBase(CudaModel):
     def history_dim(self) -> dict[str, int]:
         return {"history": 7}
 
+    @property
+    def symmetric_tangent(self) -> bool:
+        """Non-associated flow (b_flow != b) makes the consistent tangent non-symmetric."""
+        b = self.parameters[self._keys.index("b")]
+        return bool(b == self.parameters[self._keys.index("b_flow")])
+
 
 class DruckerPrager3D(_DruckerPragerBase):
     """Classic Drucker-Prager, f = sqrt(J2) + b I1 - a, flow potential slope ``b_flow``

@@ -4,7 +4,7 @@ it needs (mesh, function space, Dirichlet BCs, Newton solver).  dolfinx/PETSc
 are absent from the build image; see DESIGN.md "stand-in driver"."""
 from __future__ import annotations
 
-from ._newton import NewtonSolver
+from ._newton import KrylovError, NewtonSolver
 from ._problem import (
     History,
     IncrementalDisplacement,
@@ -35,7 +35,7 @@ from .mesh import (
 )
 
 __all__ = [
-    "IncrSmallStrainProblem", "NewtonSolver", "SimulationTime", "IncrementalDisplacement",
+    "IncrSmallStrainProblem", "KrylovError", "NewtonSolver", "SimulationTime", "IncrementalDisplacement",
     "IncrementalStress", "History", "LawOnSubMesh", "QuadratureFunction", "IdentityMap", "SubSpaceMap",
     "build_subspace_map", "Mesh", "FunctionSpace", "Function", "Constant", "DirichletBC", "ElementTables",
     "create_unit_interval", "create_unit_square", "create_rectangle", "create_unit_cube", "create_box",

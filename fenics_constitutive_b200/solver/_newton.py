@@ -16,17 +16,31 @@ on the constrained ones; J gets identity rows/columns there.
 
 Linear solver: the Jacobian is applied matrix-free from the stored tangents
 (``problem.J_apply``).  "cg": Jacobi-preconditioned conjugate gradients on the
-free dofs (the consistent tangents of the built-in laws are symmetric);
-"dense": the operator is materialised column by column and solved with LU --
-the analogue of the reference tests' default PETSc LU -- for small problems;
-"auto" picks dense up to 3000 dofs.  With several ranks (torchrun), every dot
-product and norm is summed over ranks (NCCL all-reduce of one double).
+free dofs, for SYMMETRIC tangents (every built-in law except the Drucker-Prager
+models with non-associated flow, b_flow != b); "bicgstab": Jacobi-preconditioned
+BiCGStab for non-symmetric tangents; "dense": the operator is materialised column
+by column and solved with LU -- the analogue of the reference tests' default
+PETSc LU -- for small single-rank problems.  "auto" picks dense up to 3000 dofs
+on one rank, otherwise cg or (``problem.symmetric_tangent`` False) bicgstab; on a
+partitioned mesh or with several ranks it never picks dense (a rank-local LU would
+ignore the coupling across ranks), and asking for it explicitly raises.  With
+several ranks (torchrun), every dot product and norm is summed over ranks (NCCL
+all-reduce of one double).  Every Krylov solve records whether it converged
+(``krylov_converged``, ``krylov_relres``); hitting ``cg_max_it`` or a CG breakdown
+(p.Ap <= 0: the operator is not positive definite on the free dofs) raises
+``KrylovError`` unless ``error_on_krylov_failure`` is False (then it warns).
 """
 from __future__ import annotations
 
 import numpy as np
 
+import warnings
+
 from ..partition import sum_over_ranks
+
+
+class KrylovError(RuntimeError):
+    """The linear solve of a Newton step did not converge (or CG broke down)."""
 
 
 class NewtonSolver:
@@ -40,7 +54,10 @@ class NewtonSolver:
         self.convergence_criterion = "residual"
         self.error_on_nonconvergence = True
         self.report = False
-        self.linear_solver = "auto"  # "cg" | "dense" | "auto"
+        self.linear_solver = "auto"  # "cg" | "bicgstab" | "dense" | "auto"
+        self.error_on_krylov_failure = True
+        self.krylov_converged: list[bool] = []
+        self.krylov_relres: list[float] = []
         self.cg_rtol = 1e-12
         # Inexact Newton: None = every linear solve to cg_rtol; "eisenstat-walker" = forcing term
         # eta_k = gamma (|r_k| / |r_{k-1}|)^2 (choice 2 of Eisenstat & Walker 1996 with their
@@ -157,6 +174,7 @@ class NewtonSolver:
         rz.copy_(self._rsum(torch.dot(r, p)).reshape(1))
         r0 = float(torch.sqrt(self._rsum(torch.dot(r, r))).item())
         if r0 == 0.0:
+            self._krylov_report(True, 0.0, 0, "cg")
             return x, 0
         tol2 = ((self.cg_rtol if rtol is None else rtol) * r0) ** 2
         K = max(1, int(self.cg_check_every))
@@ -177,20 +195,101 @@ class NewtonSolver:
             halo(p)
             rz.copy_(sc[2:3])
 
+        state = {"rr": r0 * r0, "pAp": 1.0}
+
         def converged():
-            return float(sc[3].item()) <= tol2  # one host synchronisation
+            vals = sc.tolist()  # one host synchronisation: [rz, pAp, rz_new, rr]
+            state["rr"], state["pAp"] = vals[3], vals[1]
+            return vals[3] <= tol2
 
         # Tried and removed (profiles/r1zr_*): the K iterations between two host checks captured as a CUDA
         # graph (kernels, all-reduces and ghost exchange included).  On one GPU the loop is GPU-bound and the
         # replayed graph was SLOWER (0.76 vs 0.48 ms per iteration); with the mesh split over two GPUs the
         # replays, interleaved with eager NCCL calls on another stream, deadlocked on the 1 M-cell problem.
         it = 0
+        ok = False
         while it < self.cg_max_it:
             for _ in range(K):
                 iteration()
             it += K
             if converged():
+                ok = True
                 break
+            if not state["pAp"] > 0.0:
+                # fcx_pcg_update_xr sets alpha = 0 for p.Ap <= 0: the iteration would stall silently
+                self._krylov_report(False, float(np.sqrt(max(state["rr"], 0.0))) / r0, it, "cg",
+                                    "breakdown: p.Ap <= 0 (operator not symmetric positive definite on the "
+                                    "free dofs; use linear_solver='bicgstab' or 'dense')")
+                return x, it
+        self._krylov_report(ok, float(np.sqrt(max(state["rr"], 0.0))) / r0, it, "cg",
+                            None if ok else f"no convergence in cg_max_it = {self.cg_max_it} iterations")
+        return x, it
+
+    def _krylov_report(self, ok: bool, relres: float, it: int, name: str, why: str | None = None) -> None:
+        self.krylov_converged.append(bool(ok))
+        self.krylov_relres.append(float(relres))
+        if ok:
+            return
+        msg = f"{name}: linear solve failed after {it} iterations (|r|/|r0| = {relres:.3e}): {why}"
+        if self.error_on_krylov_failure:
+            raise KrylovError(msg)
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
+    def _solve_bicgstab(self, apply, rhs, free_mask, diag, rtol=None):
+        """Jacobi-preconditioned BiCGStab on the free (owned) dofs for NON-symmetric tangents
+        (Drucker-Prager with non-associated flow).  Plain torch vector operations with one host
+        synchronisation per dot product: a correctness path for the unusual laws, not a tuned one."""
+        import torch
+
+        own = self._owned(rhs)
+        halo = self.partition.halo_update if self.partition is not None else (lambda v: None)
+        fm = (free_mask if own is None else free_mask & own).to(torch.float64)
+        minv = fm / torch.where(diag.abs() > 0, diag, torch.ones_like(diag))
+        x = torch.zeros_like(rhs)
+        r = rhs * fm
+        r0n = self._norm(r)
+        if r0n == 0.0:
+            self._krylov_report(True, 0.0, 0, "bicgstab")
+            return x, 0
+        tol = (self.cg_rtol if rtol is None else rtol) * r0n
+        rhat = r.clone()
+        rho = alpha = omega = 1.0
+        v = torch.zeros_like(rhs)
+        p = torch.zeros_like(rhs)
+        y, z, s, t = (torch.empty_like(rhs) for _ in range(4))
+        it, rn = 0, r0n
+        while it < self.cg_max_it:
+            rho_new = self._dot(rhat, r)
+            if rho_new == 0.0 or omega == 0.0:
+                self._krylov_report(False, rn / r0n, it, "bicgstab", "breakdown (rho or omega = 0)")
+                return x, it
+            beta = (rho_new / rho) * (alpha / omega)
+            p = r + beta * (p - omega * v)
+            torch.mul(minv, p, out=y)
+            halo(y)
+            apply(y, v)
+            v.mul_(fm)
+            alpha = rho_new / self._dot(rhat, v)
+            s = r - alpha * v
+            it += 1
+            if self._norm(s) <= tol:
+                x.add_(y, alpha=alpha)
+                rn = self._norm(s)
+                break
+            torch.mul(minv, s, out=z)
+            halo(z)
+            apply(z, t)
+            t.mul_(fm)
+            tt = self._dot(t, t)
+            omega = self._dot(t, s) / tt if tt > 0 else 0.0
+            x.add_(y, alpha=alpha).add_(z, alpha=omega)
+            r = s - omega * t
+            rho = rho_new
+            rn = self._norm(r)
+            if rn <= tol:
+                break
+        self._krylov_report(rn <= tol, rn / r0n, it, "bicgstab",
+                            None if rn <= tol else f"no convergence in cg_max_it = {self.cg_max_it} iterations")
         return x, it
 
     # -------------------------------------------------------------- solve
@@ -224,6 +323,14 @@ class NewtonSolver:
             return self._norm(b)
 
         self.residual_history, self.krylov_iterations = [], []
+        self.krylov_converged, self.krylov_relres = [], []
+        multi_rank = self.partition is not None or self.reduce_over_ranks
+        if self.linear_solver == "dense" and multi_rank:
+            raise ValueError("linear_solver='dense' builds a rank-local matrix and cannot be used on a "
+                             "partitioned mesh / with several ranks: use 'cg' or 'bicgstab'")
+        if self.linear_solver not in ("auto", "cg", "bicgstab", "dense"):
+            raise ValueError(f"unknown linear_solver {self.linear_solver!r}")
+        symmetric = bool(getattr(pb, "symmetric_tangent", True))
         r = residual()
         r0 = r
         self.residual_history.append(r)
@@ -235,10 +342,14 @@ class NewtonSolver:
         if self.convergence_criterion == "residual" and r0 > 0 and r / r0 < self.rtol:
             converged = True
         while not converged and it < self.max_it:
-            use_dense = self.linear_solver == "dense" or (self.linear_solver == "auto" and n <= 3000)
+            use_dense = self.linear_solver == "dense" or (
+                self.linear_solver == "auto" and n <= 3000 and not multi_rank)
+            use_bicgstab = self.linear_solver == "bicgstab" or (self.linear_solver == "auto" and not symmetric)
             rhs = b.clone()
             if use_dense:
                 dx, kit = self._solve_dense(pb.J_apply, rhs, free)
+            elif use_bicgstab:
+                dx, kit = self._solve_bicgstab(pb.J_apply, rhs, free, pb.J_diag(), None)
             else:
                 if self.profile:
                     import time

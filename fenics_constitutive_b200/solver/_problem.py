@@ -132,7 +132,7 @@ class History:
 class LawOnSubMesh:
     """reference solver/_lawonsubmesh.py:48-100"""
 
-    def __init__(self, law, cells: np.ndarray, problem: "IncrSmallStrainProblem"):
+    def __init__(self, law, cells: np.ndarray, problem: "IncrSmallStrainProblem", fused: bool = False):
         s, g = law.stress_strain_dim, law.geometric_dim
         T = problem.tables
         dev = problem.device
@@ -149,6 +149,9 @@ class LawOnSubMesh:
         if self.identity:  # alias the global arrays instead of copying through an IdentityMap
             self.stress = None
             self.local_tangent = problem.tangent
+        elif fused:  # the fused form() kernel reads / writes the parent rows directly (no local copies)
+            self.stress = None
+            self.local_tangent = None
         else:
             self.stress = QuadratureFunction(nqp * s, dev)
             self.local_tangent = QuadratureFunction(nqp * s * s, dev)
@@ -184,7 +187,7 @@ class IncrSmallStrainProblem:
     ``q_degree`` 1 or 2; ``del_t`` the time increment."""
 
     def __init__(self, laws, u: Function, bcs: list[DirichletBC], q_degree: int, del_t: float = 1.0,
-                 form_compiler_options=None, jit_options=None) -> None:
+                 form_compiler_options=None, jit_options=None, fused: bool | None = None) -> None:
         import torch
 
         self.V = u.function_space
@@ -226,21 +229,36 @@ class IncrSmallStrainProblem:
         self.tangent = QuadratureFunction(self.nqp * self.sdim**2, dev)
         self.sim_time = SimulationTime(dt=del_t)
         self.incr_disp = IncrementalDisplacement(u, q_degree)
-        self._law_on_submeshs = [LawOnSubMesh(law, cells, self) for law, cells in laws]
+        # fused form() kernel: every law a VonMises3D (each on its own cell list: the sub-mesh maps
+        # are folded into the kernel's bulk copies), supported element
+        # (``fused=False`` forces the generic path: gather, map kernels, law.evaluate, map kernels)
+        self.fused = (
+            fused is not False
+            and all(type(law) is VonMises3D and law.eps_layout == "aos" for law, _ in laws)
+            and (T.nd, T.nq) in ((10, 4), (4, 1), (4, 4))
+        )
+        if fused and not self.fused:
+            raise ValueError("fused=True needs VonMises3D laws (AoS history) on P1/P2 tetrahedra")
+        self._law_on_submeshs = [LawOnSubMesh(law, cells, self, self.fused) for law, cells in laws]
         self._bcs = list(bcs)
         self.f_ext = torch.zeros(self.V.num_dofs, dtype=torch.float64, device=dev)  # Neumann loads (nodal)
-        # fused form() kernel: one VonMises3D law on the whole mesh, supported element
-        l0 = self._law_on_submeshs[0]
-        self.fused = (
-            len(self._law_on_submeshs) == 1 and l0.identity and type(l0.law) is VonMises3D
-            and l0.law.eps_layout == "aos" and (T.nd, T.nq) in ((10, 4), (4, 1), (4, 4))
-        )
         self.keep_del_grad_u = True  # fused path: also store grad_del_u (72 B/QP) for inspection
         # fused path: form() also emits the tangent as 10-double records (4 coefficients + flow
         # direction) and J_apply reads those -- 80 instead of 288 B per QP per Krylov iteration
         self.use_tangent_records = True
-        self._trec = torch.empty(self.nqp * 10, dtype=torch.float64, device=dev) if self.fused else None
+        # fused path: also write the dense [nqp][36] tangent (the reference's `tangent` Function).
+        # J_diag reads it; switch off only with use_tangent_records (the Jacobian then lives in the
+        # records alone and form() moves 288 B/QP less)
+        self.dense_tangent = True
+        # (zeros: cells that no law owns keep a zero tangent, like the dense array)
+        self._trec = torch.zeros(self.nqp * 10, dtype=torch.float64, device=dev) if self.fused else None
         self._trec_valid = False
+
+    @property
+    def symmetric_tangent(self) -> bool:
+        """False if a law's consistent tangent is not symmetric (``law.symmetric_tangent`` False: the
+        Drucker-Prager models with non-associated flow) -- NewtonSolver then avoids CG."""
+        return all(getattr(ctx.law, "symmetric_tangent", True) for ctx in self._law_on_submeshs)
 
     # ------------------------------------------------------------------ form
     def form(self, x=None) -> None:
@@ -255,38 +273,44 @@ class IncrSmallStrainProblem:
             law.evaluate(self.sim_time, self.incr_disp, self.stress, self.tangent)
 
     def _form_fused(self) -> None:
-        ctx = self._law_on_submeshs[0]
-        law: VonMises3D = ctx.law
         T = self.tables
         L = lib()
         dev = self.device.index
         check(L.fcx_set_device(dev), "fcx_set_device")
         stream = B.current_stream_ptr(dev)
-        h0, h1 = ctx.history.history_0, ctx.history.history_1
-        P = law._params()
-        status = law._status_tensor(dev)
-        flag = None
-        if law.record_plastic_flag:
-            import torch
+        for ctx in self._law_on_submeshs:
+            law: VonMises3D = ctx.law
+            ncl = int(ctx.cells.size)
+            if ncl == 0:
+                continue
+            h0, h1 = ctx.history.history_0, ctx.history.history_1
+            P = law._params()
+            status = law._status_tensor(dev)
+            flag = None
+            if law.record_plastic_flag:
+                import torch
 
-            flag = torch.zeros(self.nqp, dtype=torch.uint8, device=self.device)
-        rc = L.fcx_mises_form(
-            P.ctypes.data, self.num_cells, T.nq, T.nd, self._dofmap.data_ptr(),
-            self.incr_disp.current.x.array.data_ptr(), self.incr_disp.previous.x.array.data_ptr(),
-            self._dphi.data_ptr(), self._Jinv.data_ptr(),
-            self.stress.previous.x.array.data_ptr(), self.stress.current.x.array.data_ptr(),
-            self.tangent.x.array.data_ptr(),
-            h0["eps_n"].x.array.data_ptr(), h1["eps_n"].x.array.data_ptr(),
-            h0["alpha"].x.array.data_ptr(), h1["alpha"].x.array.data_ptr(),
-            ctx.displacement_gradient_fn.x.array.data_ptr() if self.keep_del_grad_u else None,
-            self._trec.data_ptr() if self.use_tangent_records else None,
-            flag.data_ptr() if flag is not None else None, status.data_ptr(), stream,
-        )
+                flag = torch.zeros(ncl * T.nq, dtype=torch.uint8, device=self.device)
+            op = ctx.gather_op  # dofmap / Jinv rows of the law's cells (sliced once at set-up)
+            rc = L.fcx_mises_form(
+                P.ctypes.data, ncl, None if ctx.identity else ctx.submesh_map.cells_ptr(), T.nq, T.nd,
+                op.dofmap.data_ptr(),
+                self.incr_disp.current.x.array.data_ptr(), self.incr_disp.previous.x.array.data_ptr(),
+                self._dphi.data_ptr(), op.Jinv.data_ptr(),
+                self.stress.previous.x.array.data_ptr(), self.stress.current.x.array.data_ptr(),
+                self.tangent.x.array.data_ptr() if self.dense_tangent else None,
+                h0["eps_n"].x.array.data_ptr(), h1["eps_n"].x.array.data_ptr(),
+                h0["alpha"].x.array.data_ptr(), h1["alpha"].x.array.data_ptr(),
+                ctx.displacement_gradient_fn.x.array.data_ptr() if self.keep_del_grad_u else None,
+                self._trec.data_ptr() if self.use_tangent_records else None,
+                flag.data_ptr() if flag is not None else None, status.data_ptr(), stream,
+            )
+            law.plastic_flag = flag
+            check(rc, "IncrSmallStrainProblem.form (fcx_mises_form)")
         self._trec_valid = self.use_tangent_records
-        law.plastic_flag = flag
-        check(rc, "IncrSmallStrainProblem.form (fcx_mises_form)")
-        if not law.defer_errors:
-            law.check_converged()
+        for ctx in self._law_on_submeshs:
+            if not ctx.law.defer_errors:
+                ctx.law.check_converged()
 
     # -------------------------------------------------------- residual / Jacobian
     def _tables_args(self):

@@ -27,28 +27,51 @@ class IdentityMap:
 
 
 class SubSpaceMap:
-    """Rows ``cells`` of the parent <-> all rows of the sub array (device index ops)."""
+    """Rows ``cells`` of the parent <-> all rows of the sub array: the row gather / scatter
+    kernels of csrc/fcx_maps.cu (``fcx_map_rows_to_sub`` / ``fcx_map_rows_to_parent``).  CUDA
+    tensors only -- there is no CPU fallback."""
 
     def __init__(self, cells: np.ndarray, num_parent_cells: int, device):
         import torch
 
         self.cell_map = np.asarray(cells, dtype=np.int64)
         self.num_parent_cells = int(num_parent_cells)
-        self._idx = torch.as_tensor(self.cell_map, dtype=torch.int64, device=device)
+        assert self.cell_map.size == 0 or (0 <= self.cell_map.min() and self.cell_map.max() < self.num_parent_cells)
+        self._cells = torch.as_tensor(self.cell_map, dtype=torch.int32, device=device).contiguous()
+
+    def cells_ptr(self) -> int:
+        """Device address of the int32 cell list (the ``cells`` argument of fcx_mises_form)."""
+        return self._cells.data_ptr()
+
+    def _rows(self, sub, parent, to_parent: bool) -> None:
+        from .. import _buffers as B
+        from .._lib import check, lib
+
+        n = self.cell_map.size
+        if n == 0:
+            return
+        bs, bp = B.as_buf(sub, "sub", writable=not to_parent), B.as_buf(parent, "parent", writable=to_parent)
+        if B.common_kind([bs, bp]) != B.DEVICE:
+            raise ValueError("SubSpaceMap needs CUDA tensors")
+        assert bs.size % n == 0, "sub array is not a whole number of rows"
+        row = bs.size // n
+        assert bp.size == row * self.num_parent_cells, "Shapes do not match"
+        L = lib()
+        check(L.fcx_set_device(bs.device_index), "fcx_set_device")
+        stream = B.current_stream_ptr(bs.device_index)
+        if to_parent:
+            rc = L.fcx_map_rows_to_parent(n, row, self._cells.data_ptr(), bs.ptr, bp.ptr, stream)
+        else:
+            rc = L.fcx_map_rows_to_sub(n, row, self._cells.data_ptr(), bp.ptr, bs.ptr, stream)
+        check(rc, "SubSpaceMap")
 
     def map_to_parent(self, sub, parent) -> None:
-        n = self.cell_map.size
-        if n == 0:
-            return
-        parent.view(self.num_parent_cells, -1).index_copy_(0, self._idx, sub.view(n, -1))
+        """reference solver/maps.py:104-123"""
+        self._rows(sub, parent, True)
 
     def map_to_sub(self, parent, sub) -> None:
-        import torch
-
-        n = self.cell_map.size
-        if n == 0:
-            return
-        torch.index_select(parent.view(self.num_parent_cells, -1), 0, self._idx, out=sub.view(n, -1))
+        """reference solver/maps.py:82-102"""
+        self._rows(sub, parent, False)
 
 
 def build_subspace_map(cells: np.ndarray, num_parent_cells: int, device):

@@ -19,6 +19,12 @@
  * Mandel order [xx, yy, zz, xy, xz, yz], shear scaled by Python's 1/2**0.5
  * (reference: models/utils.py:199-204).
  *
+ * `tangent` may be NULL in every fcx_<model>_evaluate[_host] call and in
+ * fcx_mises_form: a STRESS-ONLY evaluate, the reference's `tangent: Option<..>`
+ * (bindings/src/lib.rs:83,109-113; comfe-rs/src/interfaces.rs:368,441-455).
+ * Stress and history are updated exactly as with a tangent; no tangent byte is
+ * formed, stored or sent over PCIe (VonMises3D: 280 instead of 568 B per QP).
+ *
  * Two families of entry points:
  *   fcx_<model>_evaluate       DEVICE pointers; enqueue-only on `stream`
  *                              (a cudaStream_t passed as void*, NULL = default
@@ -50,7 +56,7 @@
 extern "C" {
 #endif
 
-#define FCX_VERSION 100 /* 0.1.0 */
+#define FCX_VERSION 200 /* 0.2.0 */
 
 /* StressStrainConstraint values, reference models/interfaces.py:23-27 */
 enum fcx_constraint {
@@ -188,9 +194,16 @@ int fcx_gather_grad(int gdim, size_t ncells, int nq, int nd, const int *dofmap,
  * arrays (stress_cur, eps_n1, alpha1, tangent) only written; a pair may alias
  * (in-place).  grad_out: optional [ncells*nq][3][3] copy of grad_del_u.
  * (nd, nq) in {(10,4), (4,1), (4,4)}; FCX_ERR_ARG otherwise (use
- * fcx_gather_grad + fcx_mises_evaluate).  * tangent_rec: optional [ncells*nq][10], 16-byte aligned: the tangent of each point as
+ * fcx_gather_grad + fcx_mises_evaluate).
+ * cells: NULL for a law that owns every cell (IdentityMap).  Otherwise the law's cell list
+ *   (DEVICE int32 [ncells], reference solver/maps.py:62-123 SubSpaceMap / _lawonsubmesh.py:58-70):
+ *   dofmap, Jinv, eps_n0/1, alpha0/1, grad_out and plastic_flag are indexed by the law's LOCAL cell
+ *   number (sub-mesh arrays), stress_prev / stress_cur / tangent / tangent_rec are rows cells[c] of the
+ *   PARENT arrays -- map_to_sub and map_to_parent happen inside the kernel's bulk copies.
+ * tangent_rec: optional [ncells*nq][10], 16-byte aligned: the tangent of each point as
  *   {ka + cpp*2/3, ka - cpp/3, cpp, cnn, xn[6]} (see fcx_tangent_apply_rec). */
-int fcx_mises_form(const double *params_host, size_t ncells, int nq, int nd, const int *dofmap,
+int fcx_mises_form(const double *params_host, size_t ncells, const int *cells, int nq, int nd,
+                   const int *dofmap,
                    const double *u, const double *u_prev, const double *dphi_ref,
                    const double *Jinv, const double *stress_prev, double *stress_cur,
                    double *tangent, const double *eps_n0, double *eps_n1, const double *alpha0,
@@ -239,6 +252,18 @@ int fcx_tangent_diag(int gdim, int sdim, size_t ncells, int nq, int nd, const do
                      const double *tangent, double *fe, const int *fe_pos, void *stream);
 int fcx_gather_sum(int gdim, size_t nnodes, const long long *adj_ptr, const int *adj_idx,
                    const double *fe, double *out, double alpha, double beta, void *stream);
+
+/* SubSpaceMap.map_to_sub / map_to_parent on the device -- reference solver/maps.py:62-123 (the
+ * index gather / scatter between the parent mesh's quadrature arrays and those of a law's sub-mesh,
+ * called from solver/_lawonsubmesh.py:58-70).  A quadrature array is [cell][row_doubles] flat
+ * (row_doubles = quadrature points per cell x entries per point, reference
+ * tests/solver/test_maps.py:119-121); cells: DEVICE int32 [nrows_sub], parent cell of sub cell i.
+ *   fcx_map_rows_to_sub     sub[i][:]           = parent[cells[i]][:]
+ *   fcx_map_rows_to_parent  parent[cells[i]][:] = sub[i][:]      (other parent rows untouched) */
+int fcx_map_rows_to_sub(size_t nrows_sub, size_t row_doubles, const int *cells, const double *parent,
+                        double *sub, void *stream);
+int fcx_map_rows_to_parent(size_t nrows_sub, size_t row_doubles, const int *cells, const double *sub,
+                           double *parent, void *stream);
 
 /* Fused vector kernels of one Jacobi-preconditioned CG iteration (the linear solve inside the
  * stand-in NewtonSolver; the reference leaves it to PETSc via dolfinx.nls.petsc.NewtonSolver).

@@ -88,7 +88,7 @@ def test_abi_exports_every_declared_symbol():
         assert hasattr(L, name), f"{name} declared in fcx.h but not exported"
     assert declared == set(_lib.SIGNATURES), "ctypes table out of sync with fcx.h"
     lib = _lib.lib()
-    assert lib.fcx_version() == 100
+    assert lib.fcx_version() == 200
     assert [lib.fcx_stress_strain_dim(c) for c in range(0, 7)] == [-1, 1, 1, 4, 4, 6, -1]
     assert [lib.fcx_geometric_dim(c) for c in range(0, 7)] == [-1, 1, 1, 2, 2, 3, -1]
     assert lib.fcx_strerror(-2).decode() == "Time step must be defined and positive."
