@@ -15,7 +15,11 @@ Prints ONE JSON line on rank 0.  `value` is device-resident throughput (inputs
 already in HBM); `e2e` is the same metric through the public host-array API
 (`VonMises3D.evaluate` with pinned numpy arrays: H2D + kernel + D2H inside the
 timed region).  `--impl reference` times the CPU oracle port (the reference is
-pure Python and cannot travel to the GPU box) with all host threads.
+pure Python and cannot travel to the GPU box) with all host threads, on the same
+16M QPs per step as the GPU arm.  Further keys of the native line: `e2e` holds the
+pageable-array result (what dolfinx hands over) as `value` next to `pinned`, per-step medians over
+>= 5 steps and a measured host roofline (`e2e.roofline`); `models` carries every other BASELINE
+config (scripts/bench_blocks.py); `newton` the full-Newton stand-in of config 5.
 """
 from __future__ import annotations
 
@@ -153,7 +157,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = args.cpu_sample
+    sample = args.ref_qps
     law, threads, grad, virgin, tangent = _cpu_law_and_inputs(sample)
     state = tuple(a.copy() for a in virgin)
     for _ in range(args.warmup):
@@ -167,7 +171,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample} QPs per step (bounded sample of the 16M workload)"},
+        "config": {"workload": WORKLOAD, "qps_per_gpu": sample,
+                   "sample": (f"{sample} QPs per step" + (" (the whole 16M workload)" if sample == N_QP
+                              else " (bounded sample of the 16M workload)"))},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} QPs x {args.steps} steps, C oracle port (gcc -O2, OpenMP {threads} threads)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -178,10 +184,59 @@ def run_reference(args):
 
 # ------------------------------------------------------------------ GPU arm
 
+def _e2e_leg(kind, law_h, ne, Ke, rank, world, device, dist, L):
+    """Ke timed `VonMises3D.evaluate` calls on host arrays of one memory kind (+ 1 warm-up call that
+    allocates the pipeline's buffers and faults the pages in).  Every call starts from the virgin
+    state (reset untimed); per-step time = max over ranks; reported value = median step."""
+    import torch
+
+    from fenics_constitutive_b200 import synthetic
+    from fenics_constitutive_b200.partition import max_over_ranks
+
+    reg_s = None
+    if kind == "pinned":
+        mk = lambda m: torch.empty(m, dtype=torch.float64).pin_memory()  # noqa: E731
+    else:  # ordinary (pageable) numpy memory, as dolfinx hands it over
+        mk = lambda m: torch.from_numpy(np.zeros(m))  # noqa: E731
+    h_grad, h_st, h_ep, h_al, h_tg = mk(ne * 9), mk(ne * 6), mk(ne * 6), mk(ne), mk(ne * 36)
+    arrays = (h_grad, h_st, h_ep, h_al, h_tg)
+    if kind == "registered":  # pageable arrays page-locked once with fcx_host_register (a solver's set-up step)
+        t0 = time.perf_counter()
+        for a in arrays:
+            rc = L.fcx_host_register(a.data_ptr(), a.numel() * 8)
+            assert rc == 0, f"fcx_host_register rc={rc}"
+        reg_s = time.perf_counter() - t0
+    rng = np.random.default_rng(99 + rank)
+    h_grad.numpy()[:] = rng.standard_normal(ne * 9) * synthetic.MISES_GRAD_STD
+    times = []
+    for i in range(Ke + 1):
+        for a in (h_st, h_ep, h_al):
+            a.zero_()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        law_h.evaluate(0.0, 1.0, h_grad.numpy(), h_st.numpy(), h_tg.numpy(),
+                       {"eps_n": h_ep.numpy(), "alpha": h_al.numpy()})
+        dt = time.perf_counter() - t0
+        if i > 0:
+            times.append(max_over_ranks(dt, device))
+    plastic = float((h_al.numpy() > 0).mean())
+    wire = int(L.fcx_host_wire_used())
+    if kind == "registered":
+        for a in arrays:
+            L.fcx_host_unregister(a.data_ptr())
+    med = float(np.median(times))
+    return {"value": world * ne / med, "best": world * ne / min(times), "steps": Ke,
+            "step_s": [round(t, 4) for t in times], "plastic_fraction": round(plastic, 4),
+            "wire": wire, "register_s": reg_s}
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
 
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import bench_blocks as BB
     from fenics_constitutive_b200 import synthetic
     from fenics_constitutive_b200._lib import lib
     from fenics_constitutive_b200.models import VonMises3D
@@ -243,41 +298,46 @@ def run_native(args):
     kernel_ms = ms_local / K  # one launch per step
     achieved = BYTES_PER_QP * n / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = hbm_peak()
-    del states
+    del states, grad, tangent
     torch.cuda.empty_cache()
 
-    # ---- end-to-end leg: public API, pinned host arrays, H2D + D2H in the timed region ----
-    ne = args.e2e_qps
-    Ke = args.e2e_steps
-    reg_s = None
-    if args.e2e_memory == "pinned":
-        pin = lambda m: torch.empty(m, dtype=torch.float64).pin_memory()  # noqa: E731
-    else:  # ordinary (pageable) numpy memory, as dolfinx hands it over
-        pin = lambda m: torch.from_numpy(np.zeros(m))  # noqa: E731
-    h_grad, h_st, h_ep, h_al, h_tg = pin(ne * 9), pin(ne * 6), pin(ne * 6), pin(ne), pin(ne * 36)
-    if args.e2e_memory == "registered":  # pageable arrays page-locked once with fcx_host_register
-        t0 = time.perf_counter()
-        for a in (h_grad, h_st, h_ep, h_al, h_tg):
-            rc = L.fcx_host_register(a.data_ptr(), a.numel() * 8)
-            assert rc == 0, f"fcx_host_register rc={rc}"
-        reg_s = time.perf_counter() - t0
-    rng = np.random.default_rng(99 + rank)
-    h_grad.numpy()[:] = rng.standard_normal(ne * 9) * synthetic.MISES_GRAD_STD
+    # ---- the other BASELINE configs, device-resident (rank 0 only: per-kernel numbers, not a scaling claim) ----
+    models = None
+    if rank == 0 and not args.no_models:
+        try:
+            models = BB.models_block(device, n, peak, steps=max(4, min(K, 10)))
+        except Exception as exc:  # a secondary block must never cost the headline line
+            models = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+
+    # ---- host roofline: what this box's memory system and PCIe link deliver (rank 0 probes alone) ----
+    roof = None
+    if rank == 0:
+        try:
+            roof = BB.host_roofline(L)
+        except Exception as exc:
+            roof = {"error": f"{type(exc).__name__}: {exc}"}
+    if world > 1:
+        dist.barrier()
+
+    # ---- end-to-end legs: public API, host arrays, H2D + D2H in the timed region ----
+    ne, Ke = args.e2e_qps, max(1, args.e2e_steps)
     law_h = VonMises3D(synthetic.MISES_PARAMS)
-    e2e_s = 0.0
-    for i in range(Ke + 1):  # first call is the warm-up (allocates the staging buffers)
-        for a in (h_st, h_ep, h_al):
-            a.zero_()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        law_h.evaluate(0.0, 1.0, h_grad.numpy(), h_st.numpy(), h_tg.numpy(),
-                       {"eps_n": h_ep.numpy(), "alpha": h_al.numpy()})
-        dt = time.perf_counter() - t0
-        if i > 0:
-            e2e_s += max_over_ranks(dt, device)
-    e2e_value = world * ne * Ke / e2e_s
-    e2e_plastic = float((h_al.numpy() > 0).mean())
+    legs = {}
+    for kind in args.e2e_memory.split(","):
+        legs[kind] = _e2e_leg(kind, law_h, ne, Ke, rank, world, device, dist, L)
+    head_kind = "pageable" if "pageable" in legs else next(iter(legs))
+    head = legs[head_kind]
+
+    # ---- full-Newton stand-in, BASELINE config 5: one mesh over all ranks ----
+    newton = None
+    if not args.no_newton:
+        try:
+            newton = BB.newton_block(rank, world, device, grid=args.newton_grid)
+        except Exception as exc:
+            newton = {"error": f"{type(exc).__name__}: {exc}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -287,6 +347,37 @@ def run_native(args):
                          f"C oracle port (gcc -O2, OpenMP, {threads} threads), {secs:.1f} s timed"}
 
     if rank == 0:
+        def leg_roofline(kind, leg):
+            """Aggregate ceilings of the host-array path for this leg's memory kind / wire, from the probes."""
+            if not roof or "error" in roof or not roof.get("pcie"):
+                return None
+            tr = BB.e2e_traffic("pinned" if kind in ("pinned", "registered") else "pageable", leg["wire"],
+                                leg["plastic_fraction"])
+            caps = {"host_dram": roof["host_memory"]["memcpy_rw_GBps"] * 1e9 / tr["host_dram"],
+                    "pcie_h2d": world * roof["pcie"]["h2d_concurrent_GBps"] * 1e9 / tr["pcie_h2d"],
+                    "pcie_d2h": world * roof["pcie"]["d2h_concurrent_GBps"] * 1e9 / tr["pcie_d2h"]}
+            bound = min(caps, key=caps.get)
+            return {"bound": bound, "ceiling_qp_per_s": {k: round(v) for k, v in caps.items()},
+                    "bytes_per_qp": tr, "achieved_host_bytes_per_s": leg["value"] * tr["host_dram"],
+                    "peak": roof["host_memory"]["memcpy_rw_GBps"] * 1e9,
+                    "peak_unit": "B/s, host memcpy read+write, measured at start-up",
+                    "frac": leg["value"] / caps[bound]}
+
+        e2e = {"value": head["value"], "unit": UNIT, "h2d_bytes_per_step": H2D_PER_QP * ne,
+               "d2h_bytes_per_step": D2H_PER_QP * ne,
+               # d2h_bytes_per_step: the result arrays delivered into host memory (392 B/QP);
+               # d2h_wire_bytes_per_step: what actually crosses PCIe (record wire: stress + flag byte for every
+               # point, 224 B only for plastic points; include/fcx.h fcx_host_wire)
+               "d2h_wire_bytes_per_step": int(ne * (49 + 224 * head["plastic_fraction"])) if head["wire"]
+               else D2H_PER_QP * ne,
+               "qps_per_gpu": ne, "steps": Ke, "statistic": "median step, max over ranks per step",
+               "host_memory": head_kind, "wire": head["wire"], "plastic_fraction": head["plastic_fraction"],
+               "step_s": head["step_s"], "best": head["best"],
+               "api": f"VonMises3D.evaluate(numpy {head_kind} host arrays) -> fcx_mises_evaluate_host",
+               "roofline": leg_roofline(head_kind, head), "host_probes": roof}
+        for kind, leg in legs.items():
+            if kind != head_kind:
+                e2e[kind] = {**leg, "roofline": leg_roofline(kind, leg)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
@@ -295,29 +386,15 @@ def run_native(args):
                        "history_layout": "aos (reference contract)",
                        "l2": "inputs (9.1 GB touched per step) larger than L2; fresh state set per step"
                              + ("" if K + W <= nsets else f" (recycled after {nsets} steps)"),
-                       "kernel": "fcx_mises_ostage_kernel<64,8>, atomic tile tickets",
+                       "kernel": "fcx_mises_ostage_kernel<64,8,true>, atomic tile tickets",
                        "parallelism": f"qp-shard x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_qp": BYTES_PER_QP, "kernel_ms": kernel_ms},
-            "cpu_baseline": cpu,
-            # d2h_bytes_per_step: the result arrays delivered into host memory (392 B/QP);
-            # d2h_wire_bytes_per_step: what actually crosses PCIe with the packed download wire
-            # (stress + flag byte for every point, 224 B only for plastic points; include/fcx.h fcx_host_wire)
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": H2D_PER_QP * ne,
-                    "d2h_bytes_per_step": D2H_PER_QP * ne,
-                    "d2h_wire_bytes_per_step": (int(ne * (49 + 224 * e2e_plastic)) if L.fcx_host_wire(-1)
-                                                else D2H_PER_QP * ne),
-                    "qps_per_gpu": ne, "steps": Ke,
-                    "plastic_fraction": round(e2e_plastic, 4),
-                    "host_memory": args.e2e_memory, "register_s": reg_s,
-                    "api": f"VonMises3D.evaluate(numpy {args.e2e_memory} host arrays) -> fcx_mises_evaluate_host"},
+            "cpu_baseline": cpu, "e2e": e2e, "models": models, "newton": newton,
             "gpu_launches": launches, "clocks": clocks, "host_cpus": os.cpu_count(),
         }
         print(json.dumps(line), flush=True)
-    if args.e2e_memory == "registered":
-        for a in (h_grad, h_st, h_ep, h_al, h_tg):
-            L.fcx_host_unregister(a.data_ptr())
     if world > 1:
         dist.destroy_process_group()
 
@@ -330,11 +407,16 @@ def main():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--qps", type=int, default=N_QP, help="QPs per GPU (default: the 16M workload)")
     ap.add_argument("--e2e-qps", type=int, default=N_QP)
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-memory", choices=["pinned", "pageable", "registered"], default="pinned",
-                    help="host memory of the e2e leg's arrays (default: page-locked)")
-    ap.add_argument("--cpu-sample", type=int, default=4_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-memory", default="pageable,pinned",
+                    help="comma list of host-memory kinds for the e2e legs: pageable (ordinary numpy arrays, the "
+                         "headline e2e), pinned (page-locked), registered (pageable + fcx_host_register)")
+    ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="QPs of the cpu_baseline leg of the native arm")
+    ap.add_argument("--ref-qps", type=int, default=N_QP, help="QPs per step of --impl reference (default: the 16M workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-models", action="store_true", help="skip the per-config `models` block")
+    ap.add_argument("--no-newton", action="store_true", help="skip the full-Newton stand-in block")
+    ap.add_argument("--newton-grid", type=int, default=55, help="cubes per direction (6 n^3 P2 tets; 55 = 998 250 cells)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps

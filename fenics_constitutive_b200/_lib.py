@@ -60,6 +60,11 @@ SIGNATURES = {
     "fcx_host_staging": (_ci, [_ci]),
     "fcx_host_threads": (_ci, [_ci]),
     "fcx_host_wire": (_ci, [_ci]),
+    "fcx_host_wire_used": (_ci, []),
+    "fcx_host_numa": (_ci, [_ci]),
+    "fcx_host_numa_info": (_ci, [_vp, _ci]),
+    "fcx_diag_host_bandwidth": (_ci, [_ci, _sz, _vp, _ci]),
+    "fcx_diag_pcie": (_ci, [_sz, _vp, _ci]),
     "fcx_host_trace": (_ci, [_ci]),
     "fcx_host_slots": (_ci, [_ci]),
     "fcx_host_debug_skip": (_ci, [_ci]),

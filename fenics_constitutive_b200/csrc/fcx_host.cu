@@ -19,6 +19,10 @@
 // arithmetic still happens only on the GPU.
 #include <cuda_runtime.h>
 #include <emmintrin.h>  // SSE2 streaming stores (x86-64 baseline) for the wire expansion
+#include <pthread.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <chrono>
@@ -26,6 +30,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -99,6 +104,124 @@ static inline double now_s()
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// ---- NUMA placement ----------------------------------------------------------
+// The pool threads touch every byte the DMA engines move, so they belong on the NUMA node the GPU
+// hangs off (and the pinned ring slots in that node's memory): a copy that crosses the socket
+// interconnect costs twice.  The node comes from sysfs (/sys/bus/pci/devices/<gpu>/numa_node), its
+// CPUs from /sys/devices/system/node/nodeN/cpulist, intersected with the CPUs this process may run
+// on (container cpuset).  A single-node host, a VM that hides the topology (numa_node = -1) or an
+// empty intersection leave everything unpinned.  fcx_host_numa(0) switches it off.
+static int g_numa = 1;
+struct NumaInfo {
+    int node = -1;       // NUMA node of the bound GPU, -1 = unknown / not applicable
+    int ncpus = 0;       // CPUs of that node this process may use
+    int allowed = 0;     // CPUs this process may use at all
+    cpu_set_t set;
+    bool valid = false;  // pin threads to `set`
+};
+static NumaInfo g_numa_info;
+static std::once_flag g_numa_once;
+
+static int allowed_cpus()
+{
+    cpu_set_t s;
+    CPU_ZERO(&s);
+    if (sched_getaffinity(0, sizeof s, &s) == 0) {
+        const int c = CPU_COUNT(&s);
+        if (c > 0)
+            return c;
+    }
+    const int hw = (int)std::thread::hardware_concurrency();
+    return hw > 0 ? hw : 1;
+}
+
+static void numa_probe()
+{
+    NumaInfo &N = g_numa_info;
+    CPU_ZERO(&N.set);
+    N.allowed = allowed_cpus();
+    int dev = 0;
+    char bus[32] = "";
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    for (char *p = bus; *p; ++p)
+        if (*p >= 'A' && *p <= 'Z')
+            *p += 'a' - 'A';
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f)
+        return;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1)
+        node = -1;
+    fclose(f);
+    N.node = node;
+    if (node < 0)
+        return;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f)
+        return;
+    char list[4096] = "";
+    if (!fgets(list, sizeof list, f))
+        list[0] = 0;
+    fclose(f);
+    cpu_set_t may;
+    CPU_ZERO(&may);
+    if (sched_getaffinity(0, sizeof may, &may) != 0)
+        return;
+    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k == 1)
+            b = a;
+        if (k < 1)
+            continue;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &may))
+                CPU_SET(c, &N.set);
+    }
+    N.ncpus = CPU_COUNT(&N.set);
+    // pin only if the node is a proper, non-empty subset of what we may use (otherwise nothing to gain)
+    N.valid = N.ncpus > 0 && N.ncpus < N.allowed;
+}
+
+static const NumaInfo &numa_info()
+{
+    std::call_once(g_numa_once, numa_probe);
+    return g_numa_info;
+}
+
+static void pin_this_thread_to_gpu_node()
+{
+    const NumaInfo &N = numa_info();
+    if (g_numa && N.valid)
+        pthread_setaffinity_np(pthread_self(), sizeof N.set, &N.set);
+}
+
+// Prefer the GPU's node for the pages of the next allocations of this thread (the pinned ring
+// slots); `restore` puts the default policy back.  Raw syscall: libnuma is not assumed.
+static void prefer_gpu_node_memory(bool restore)
+{
+#ifdef SYS_set_mempolicy
+    const NumaInfo &N = numa_info();
+    if (!g_numa || !N.valid || N.node < 0 || N.node >= 1024)
+        return;
+    if (restore) {
+        syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+        return;
+    }
+    unsigned long mask[16] = {};
+    mask[N.node / (8 * sizeof(unsigned long))] |= 1UL << (N.node % (8 * sizeof(unsigned long)));
+    syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof mask * 8);
+#else
+    (void)restore;
+#endif
+}
+
 // ---- host-thread pool (memcpy only) -----------------------------------------
 class Pool {
 public:
@@ -130,6 +253,7 @@ public:
 private:
     void work()
     {
+        pin_this_thread_to_gpu_node();
         for (;;) {
             std::function<void()> f;
             {
@@ -186,7 +310,7 @@ static int pool_threads(bool wide = false)
 {
     if (g_threads > 0)
         return g_threads;
-    int hw = (int)std::thread::hardware_concurrency();
+    int hw = allowed_cpus();  // the container's cpuset, not the machine's core count
     // one process per GPU (torchrun): the ranks of a node share its cores
     static const int local_world = [] {
         const char *e = getenv("LOCAL_WORLD_SIZE");
@@ -294,11 +418,15 @@ static int ensure_pin(size_t need)
     }
     g_ctx.pin_cap = 0;
     g_ctx.npin = 0;
+    prefer_gpu_node_memory(false);
     for (int s = 0; s < g_nslot; ++s) {
         cudaError_t e = cudaHostAlloc((void **)&g_ctx.pin[s], need, cudaHostAllocMapped);
-        if (e != cudaSuccess)
+        if (e != cudaSuccess) {
+            prefer_gpu_node_memory(true);
             return note_cuda_error(e, "cudaHostAlloc(ring slot)");
+        }
     }
+    prefer_gpu_node_memory(true);
     g_ctx.pin_cap = need;
     g_ctx.npin = g_nslot;
     return FCX_OK;
@@ -405,6 +533,7 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
 
     std::thread drain([&] {
         cudaSetDevice(device);
+        pin_this_thread_to_gpu_node();
         for (;;) {
             Item it;
             {
@@ -807,7 +936,50 @@ static void plastic_wire_expand(const PlasticWire &W, size_t q0, size_t cnt, con
 // elastic runs fight over the partial cache lines they share (not investigated further).
 // Tried and reverted (profiles/r1zg_*): packing the records in device memory and letting a second
 // drain stage DMA exactly `count` of them -- same link rate, one more host round trip per chunk.
-static int g_wire = 1;
+// 3 = AUTO (the default): the record wire (1) unless several ranks share the host's memory system AND
+// every result array of the call is page-locked -- then plain DMA (0), which costs no host-thread byte:
+// with 4-8 ranks per host the pool shrinks to a few threads per rank and the expansion, not the link,
+// bounds the record wire (SCALE_r01: 217 M QP/s for 8 GPUs).  Threshold: FCX_WIRE_AUTO_RANKS (default 4).
+static int g_wire = 3;
+
+static int local_world_size()
+{
+    static const int v = [] {
+        const char *e = getenv("LOCAL_WORLD_SIZE");
+        const int w = e ? atoi(e) : 1;
+        return w > 0 ? w : 1;
+    }();
+    return v;
+}
+
+static bool page_locked(const void *p)
+{
+    if (p == nullptr)
+        return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// The wire mode a plastic-model host call runs with (g_wire resolved for this call's arrays).
+static int effective_wire(const void *stress, const void *tangent, const void *h0, const void *h1)
+{
+    if (g_wire != 3)
+        return g_wire;
+    static const int ranks = [] {
+        const char *e = getenv("FCX_WIRE_AUTO_RANKS");
+        const int v = e ? atoi(e) : 4;
+        return v > 0 ? v : 4;
+    }();
+    if (local_world_size() >= ranks && page_locked(stress) && page_locked(tangent) && page_locked(h0) &&
+        page_locked(h1))
+        return 0;
+    return 1;
+}
+static int g_last_wire = -1;  // what the last plastic host call resolved to (fcx_host_wire_used)
 
 // Device alias of a page-locked host range (pinned allocation or cudaHostRegister), or nullptr.
 static void *device_alias(const void *p, size_t bytes)
@@ -1002,7 +1174,9 @@ static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
     const size_t d = sizeof(double);
     // H.tangent == nullptr (stress-only call): no tangent slot on the device, none on the wire
     const size_t bpq[6] = {d * 9, d * 6, H.tangent ? d * 36 : 0, d * H.hw[0], H.nh > 1 ? d * H.hw[1] : 0, 1};
-    if (g_wire && n >= 4096) {
+    const int wire = n >= 4096 ? effective_wire(H.stress, H.tangent, H.hist[0], H.nh > 1 ? H.hist[1] : nullptr) : 0;
+    g_last_wire = wire;
+    if (wire) {
         // elastic tangent as the kernel produces it: one virgin point with a zero increment
         // (elastic for any sensible parameter set; otherwise fall through to the plain path)
         PlasticWire W;
@@ -1050,7 +1224,7 @@ static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
             }
             W.user_flag = H.flag;
             W.nt = H.tangent == nullptr ? 0 : (H.symmetric ? 21 : 36);
-            if (g_wire >= 2 && H.tangent != nullptr && (reinterpret_cast<uintptr_t>(H.tangent) & 15u) == 0) {
+            if (wire >= 2 && H.tangent != nullptr && (reinterpret_cast<uintptr_t>(H.tangent) & 15u) == 0) {
                 W.tangent_dev = (double *)device_alias(H.tangent, n * 36 * d);
                 if (W.tangent_dev != nullptr && (reinterpret_cast<uintptr_t>(W.tangent_dev) & 15u) == 0)
                     W.nt = 0;
@@ -1129,8 +1303,29 @@ int fcx_host_wire(int on)
 {
     const int old = g_wire;
     if (on >= 0)
-        g_wire = on > 2 ? 2 : on;
+        g_wire = on > 3 ? 3 : on;
     return old;
+}
+
+int fcx_host_wire_used(void) { return g_last_wire; }
+
+int fcx_host_numa(int on)
+{
+    const int old = g_numa;
+    if (on >= 0)
+        g_numa = on ? 1 : 0;
+    return old;
+}
+
+int fcx_host_numa_info(int *out, int n)
+{
+    const NumaInfo &N = numa_info();
+    const int v[4] = {N.node, N.ncpus, N.allowed, (g_numa && N.valid) ? 1 : 0};
+    if (!out)
+        return FCX_ERR_NULL;
+    for (int i = 0; i < n && i < 4; ++i)
+        out[i] = v[i];
+    return 4;
 }
 
 int fcx_host_slots(int n)
@@ -1178,6 +1373,156 @@ int fcx_host_stats(double *out, int n)
     for (int i = 0; i < n && i < 12; ++i)
         out[i] = v[i];
     return 12;
+}
+
+/* Host-side roofline probes (bench.py's e2e.roofline): what the host memory system and the PCIe
+ * link of THIS box deliver, measured the way the host pipeline uses them. */
+int fcx_diag_host_bandwidth(int threads, size_t bytes, double *out, int nout)
+{
+    if (!out || nout < 3)
+        return FCX_ERR_NULL;
+    if (threads <= 0)
+        threads = pool_threads(true);
+    bytes &= ~(size_t)4095;
+    if (bytes < ((size_t)1 << 20))
+        return FCX_ERR_ARG;
+    char *a = (char *)aligned_alloc(4096, bytes), *b = (char *)aligned_alloc(4096, bytes);
+    if (!a || !b) {
+        free(a);
+        free(b);
+        return FCX_ERR_ARG;
+    }
+    Pool &pool = Pool::get();
+    pool.ensure(threads);
+    const size_t per = ((bytes / threads) + 4095) & ~(size_t)4095;
+    auto run = [&](int what) {  // 0 first touch, 1 memcpy b <- a, 2 streaming fill of b, 3 read a
+        Group g;
+        std::atomic<long long> sink{0};
+        const double t0 = now_s();
+        for (size_t off = 0; off < bytes; off += per) {
+            const size_t len = bytes - off < per ? bytes - off : per;
+            g.add();
+            pool.submit([=, &g, &sink] {
+                if (what == 0) {
+                    memset(a + off, 1, len);
+                    memset(b + off, 2, len);
+                } else if (what == 1) {
+                    memcpy(b + off, a + off, len);
+                } else if (what == 2) {
+                    const __m128d v = _mm_set1_pd(1.5);
+                    double *d = (double *)(b + off);
+                    for (size_t i = 0; i < len / 8; i += 2)
+                        _mm_stream_pd(d + i, v);
+                    _mm_sfence();
+                } else {
+                    const long long *s = (const long long *)(a + off);
+                    long long acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+                    for (size_t i = 0; i + 3 < len / 8; i += 4) {
+                        acc0 += s[i];
+                        acc1 += s[i + 1];
+                        acc2 += s[i + 2];
+                        acc3 += s[i + 3];
+                    }
+                    sink.fetch_add(acc0 + acc1 + acc2 + acc3, std::memory_order_relaxed);
+                }
+                g.done();
+            });
+        }
+        g.wait();
+        return now_s() - t0;
+    };
+    run(0);
+    double best[3] = {1e30, 1e30, 1e30};
+    for (int rep = 0; rep < 4; ++rep)
+        for (int w = 0; w < 3; ++w) {
+            const double t = run(w + 1);
+            if (t < best[w])
+                best[w] = t;
+        }
+    out[0] = 2.0 * bytes / best[0] / 1e9;  // memcpy: bytes read + bytes written per second
+    out[1] = (double)bytes / best[1] / 1e9;  // streaming (non-temporal) fill
+    out[2] = (double)bytes / best[2] / 1e9;  // read
+    if (nout > 3)
+        out[3] = threads;
+    free(a);
+    free(b);
+    return FCX_OK;
+}
+
+int fcx_diag_pcie(size_t bytes, double *out, int nout)
+{
+    if (!out || nout < 4)
+        return FCX_ERR_NULL;
+    bytes &= ~(size_t)255;
+    if (bytes < ((size_t)1 << 20))
+        return FCX_ERR_ARG;
+    char *h0 = nullptr, *h1 = nullptr, *d0 = nullptr, *d1 = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t ev[4] = {};
+    cudaError_t e = cudaHostAlloc((void **)&h0, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess)
+        e = cudaHostAlloc((void **)&h1, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&d0, bytes);
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&d1, bytes);
+    if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+        e = cudaEventCreate(&ev[i]);
+    if (e == cudaSuccess) {
+        memset(h0, 1, bytes);
+        memset(h1, 2, bytes);
+        auto timed = [&](bool up, bool down, float *ms_up, float *ms_down) {
+            cudaDeviceSynchronize();
+            if (up)
+                cudaEventRecord(ev[0], s0);
+            if (down)
+                cudaEventRecord(ev[2], s1);
+            for (int rep = 0; rep < 3; ++rep) {
+                if (up)
+                    cudaMemcpyAsync(d0, h0, bytes, cudaMemcpyHostToDevice, s0);
+                if (down)
+                    cudaMemcpyAsync(h1, d1, bytes, cudaMemcpyDeviceToHost, s1);
+            }
+            if (up)
+                cudaEventRecord(ev[1], s0);
+            if (down)
+                cudaEventRecord(ev[3], s1);
+            cudaDeviceSynchronize();
+            if (up)
+                cudaEventElapsedTime(ms_up, ev[0], ev[1]);
+            if (down)
+                cudaEventElapsedTime(ms_down, ev[2], ev[3]);
+        };
+        float a = 0, b = 0, c = 0, d = 0;
+        timed(true, false, &a, &b);  // warm-up
+        timed(true, false, &a, &b);
+        timed(false, true, &c, &b);
+        timed(true, true, &c, &d);
+        const double gb = 3.0 * bytes / 1e9;
+        out[0] = gb / (a * 1e-3);  // H2D alone
+        out[1] = gb / (b * 1e-3);  // D2H alone
+        out[2] = gb / (c * 1e-3);  // H2D while D2H runs
+        out[3] = gb / (d * 1e-3);  // D2H while H2D runs
+        e = cudaGetLastError();
+    }
+    for (int i = 0; i < 4; ++i)
+        if (ev[i])
+            cudaEventDestroy(ev[i]);
+    if (s0)
+        cudaStreamDestroy(s0);
+    if (s1)
+        cudaStreamDestroy(s1);
+    cudaFree(d0);
+    cudaFree(d1);
+    if (h0)
+        cudaFreeHost(h0);
+    if (h1)
+        cudaFreeHost(h1);
+    return note_cuda_error(e, "fcx_diag_pcie");
 }
 
 int fcx_host_threads(int n)

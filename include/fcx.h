@@ -329,12 +329,32 @@ int fcx_host_threads(int n);
  * every point, a flag byte, and for PLASTIC points only a compacted record; the host threads
  * scatter the records and copy the constant elastic tangent -- bit-identical arrays).
  * 1 = records carry tangent (VonMises3D: its 21 upper-triangle entries) + history;
- * 1 is the default;
+ * 1 was the default of version 0.1 (3 = auto is now);
  * 2 = additionally, a page-locked caller tangent array gets the plastic tangents stored in place by
  * a kernel through its device alias, records carry the history only (fewer host-thread bytes, but
  * slower on the hosts measured so far, profiles/r1zf_host_wire_stats.jsonl);
- * 0 = plain D2H of every array, -1 = query; returns the old value. */
+ * 0 = plain D2H of every array, 3 = auto (below), -1 = query; returns the old value. */
 int fcx_host_wire(int on);
+/* 3 = AUTO, the default since 0.2: wire 1, except that with several ranks per host
+ * (LOCAL_WORLD_SIZE >= FCX_WIRE_AUTO_RANKS, default 4) and every result array page-locked the call
+ * takes wire 0 -- plain DMA costs no host-thread byte, and with 4-8 ranks sharing one memory system the
+ * host-thread expansion is what bounds the record wire.  fcx_host_wire_used(): what the last plastic
+ * host call resolved to (0/1/2; -1 before the first call). */
+int fcx_host_wire_used(void);
+/* NUMA placement of the host pipeline (pool threads, drain thread, pinned ring slots) on the node
+ * the bound GPU hangs off; 1 = on (default), 0 = off, -1 = query; returns the old value.  A no-op on
+ * single-node hosts and where sysfs hides the topology.  fcx_host_numa_info: out[0..4) = GPU's NUMA
+ * node (-1 unknown), usable CPUs of that node, CPUs this process may use, 1 if threads are pinned. */
+int fcx_host_numa(int on);
+int fcx_host_numa_info(int *out, int n);
+/* Host-side roofline probes for the e2e path, measured on this box (GB/s, best of a few passes):
+ * fcx_diag_host_bandwidth: `threads` pool threads (0 = the pool's default) over two `bytes`-sized
+ *   buffers: out[0] memcpy (bytes read + bytes written per second), out[1] streaming-store fill,
+ *   out[2] read, out[3] threads used.
+ * fcx_diag_pcie: page-locked <-> device copies of `bytes`: out[0] H2D alone, out[1] D2H alone,
+ *   out[2] H2D and out[3] D2H while the other direction runs (two copy engines). */
+int fcx_diag_host_bandwidth(int threads, size_t bytes, double *out, int nout);
+int fcx_diag_pcie(size_t bytes, double *out, int nout);
 /* Chunks in flight in the *_host pipelines (streams / device buffers / pinned ring slots):
  * 2..8, default 6; 0 = query.  Returns the old value. */
 int fcx_host_slots(int n);
