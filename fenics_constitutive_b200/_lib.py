@@ -74,6 +74,7 @@ SIGNATURES = {
     "fcx_host_release": (None, []),
     "fcx_launch_count": (ctypes.c_ulonglong, []),
     "fcx_tune": (_ci, [ctypes.c_char_p, _ci]),
+    "fcx_diag_dfma_peak": (_cd, []),
     "fcx_diag_stream_mix": (ctypes.c_longlong, [_dp, _dp, _sz, _vp]),
 }
 

@@ -58,6 +58,10 @@ static int g_tile = 128;
 // warp-cooperative tangent store.
 static int g_mises_variant = 1;
 static int g_mises_tile = 64;  // QPs per tile of the output-staged kernel (64 or 128)
+// Stress-only Mises calls (tangent == NULL): 0 = double-buffered tile pipeline, stress-only instantiation
+// (fcx_tile_kernel<MisesModel, 128, false>), 1 = single-stage output-staged kernel without the tangent
+// region.  Measured on B200, 16 M QPs (profiles/r2a_tune_stress_only.jsonl): 0.75 vs 0.80 ms.
+static int g_mises_so_variant = 0;
 // Hand tiles out through an atomic ticket counter (all tile kernels).
 static int g_dynamic_tiles = 1;
 static int g_fem_variant = 1;
@@ -108,13 +112,13 @@ int tuned_ctas_per_sm() { return g_ctas_per_sm; }
 int fem_variant() { return g_fem_variant; }
 int gather_variant() { return g_gather_variant; }
 
-template <class M, int TILE>
+template <class M, int TILE, bool WT = true>
 static int launch_tile_t(const typename M::Params &prm, const SegPtrs<M::nseg()> &io,
                          double *tangent, size_t n, bool bulk_ok, unsigned char *flag,
                          int *status, cudaStream_t stream, unsigned long long qbase)
 {
-    auto kern = fcx_tile_kernel<M, TILE>;
-    constexpr size_t smem = tile_smem_bytes<M, TILE>();
+    auto kern = fcx_tile_kernel<M, TILE, WT>;
+    constexpr size_t smem = tile_smem_bytes<M, TILE, WT>();
     static OccCache cache;  // per instantiation and device
     int occ = 1;
     if (int rc = kernel_occupancy(cache, kern, TILE, smem, "occupancy(fcx_tile_kernel)", &occ))
@@ -142,7 +146,12 @@ static int launch_tile(const typename M::Params &prm, const SegPtrs<M::nseg()> &
     switch (g_tile) {
     case 64: return launch_tile_t<M, 64>(prm, io, tangent, n, bulk_ok, flag, status, stream, qbase);
     case 256: return launch_tile_t<M, 256>(prm, io, tangent, n, bulk_ok, flag, status, stream, qbase);
-    default: return launch_tile_t<M, 128>(prm, io, tangent, n, bulk_ok, flag, status, stream, qbase);
+    default:
+        // stress-only calls (tangent == NULL) have their own instantiation at the default tile size;
+        // the other tile sizes (tuning only) take the run-time branch of the full kernel
+        if (tangent == nullptr)
+            return launch_tile_t<M, 128, false>(prm, io, nullptr, n, bulk_ok, flag, status, stream, qbase);
+        return launch_tile_t<M, 128>(prm, io, tangent, n, bulk_ok, flag, status, stream, qbase);
     }
 }
 
@@ -393,11 +402,67 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Diagnostic: fp64 FMA peak of the device -- 8 independent DFMA chains per thread, no memory traffic.
+// BASELINE.md section 2 asks for this number next to any fp64-pipe utilisation that is quoted.
+__global__ void __launch_bounds__(256) diag_dfma_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll 8
+        for (int k = 0; k < 8; ++k) {
+            x0 = fma(x0, a, b);
+            x1 = fma(x1, a, b);
+            x2 = fma(x2, a, b);
+            x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b);
+            x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b);
+            x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456)  // never true: keeps the chains alive
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace fcx
 
 using namespace fcx;
 
 extern "C" {
+
+/* DFMA-chain peak of the current device in TFLOP/s (2 flops per DFMA); < 0 on error. */
+double fcx_diag_dfma_peak(void)
+{
+    const int iters = 4096, blocks = sm_count() * 8;
+    double *out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * 256 * blocks) != cudaSuccess)
+        return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    diag_dfma_kernel<<<blocks, 256>>>(out, 64, 0.999999, 1e-9);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        diag_dfma_kernel<<<blocks, 256>>>(out, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = ms < best ? ms : best;
+    }
+    g_launches.fetch_add(4, std::memory_order_relaxed);
+    const cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (e != cudaSuccess)
+        return -1.0;
+    const double dfma = (double)blocks * 256 * iters * 64;
+    return 2.0 * dfma / (best * 1e-3) / 1e12;
+}
 
 int fcx_version(void) { return FCX_VERSION; }
 
@@ -466,6 +531,13 @@ int fcx_tune(const char *key, int value)
             return FCX_ERR_ARG;
         const int old = g_mises_variant;
         g_mises_variant = value;
+        return old;
+    }
+    if (key && strcmp(key, "mises_so_variant") == 0) {
+        if (value != 0 && value != 1)
+            return FCX_ERR_ARG;
+        const int old = g_mises_so_variant;
+        g_mises_so_variant = value;
         return old;
     }
     if (key && strcmp(key, "dynamic_tiles") == 0) {
@@ -539,6 +611,8 @@ int fcx_mises_evaluate(const double *params, size_t n, const double *grad, doubl
     }
     if (eps_layout != FCX_LAYOUT_AOS)
         return FCX_ERR_ARG;
+    if (tangent == nullptr && g_mises_so_variant == 0)
+        return launch_tile<MisesModel<false>>(P, io, nullptr, n, al, plastic_flag, status, st);
     if (g_mises_variant == 1 && al) {
         // full tiles through the output-staged kernel, the tail (< one tile)
         // through the generic pipeline

@@ -116,12 +116,12 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
         // ---- grad_del_u of this thread's QP, in registers (overlaps the loads) ----
         double g[9];
         const bool active = tid < cnt;
-        unsigned long long qp_parent;  // this thread's QP in the parent arrays
+        unsigned pcell;  // this thread's cell in the parent arrays
         {
             // idle lanes of the ragged last tile clamp to the last cell; nothing of theirs is stored
             unsigned long long c = q0 / NQ + tid / NQ;
             c = c < A.ncells ? c : A.ncells - 1;
-            qp_parent = (A.cells != nullptr ? (unsigned long long)A.cells[c] : c) * NQ + tid % NQ;
+            pcell = A.cells != nullptr ? (unsigned)A.cells[c] : (unsigned)c;
             const int q = tid % NQ;
             double K[9];
 #pragma unroll
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(TILE, MINCTAS)
 
         if (active) {
             const unsigned long long qg = q0 + tid;
+            const unsigned long long qp_parent = (unsigned long long)pcell * NQ + tid % NQ;
             double sig[6], ep[6], al;
             if (bulk) {
 #pragma unroll

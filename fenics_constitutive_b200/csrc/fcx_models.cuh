@@ -489,6 +489,8 @@ struct MisesModel {
             v.template st<2>(i, ep[i]);
         }
         v.template st<3>(0, alpha);
+        if (aux == nullptr)  // stress-only instantiation: no tangent record
+            return;
         double *rec = aux + t * REC;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -631,6 +633,8 @@ struct MisesLinModel {
 #pragma unroll
         for (int i = 0; i < 7; ++i)
             v.template st<2>(i, hist[i]);
+        if (aux == nullptr)  // stress-only instantiation: no tangent record
+            return;
         // kappa*1(x)1 + (2mu theta)*P_dev + (2mu theta_bar)*n n^T   (:98-100, :118-120)
         const double c = two_mu * theta;
         const double third = (1.0 * (1.0 / 3.0)) * -1.0;  // consts.rs:106-115
@@ -778,7 +782,8 @@ struct DruckerPragerModel {
         state(P, sigtr, bfe, S);
         failed = S.apex;
         plastic = !(S.f <= 0.0);  // :133
-        double *rec = aux + t * REC;
+        double no_rec[REC];  // stress-only instantiation (aux == nullptr): the record is dead code
+        double *rec = aux != nullptr ? aux + t * REC : no_rec;
         rec[0] = P.kappa + two_mu * (2.0 / 3.0);  // elastic tangent 3 kappa P_vol + 2 mu P_dev
         rec[1] = P.kappa - two_mu / 3.0;          // (also what a failed point reports)
         rec[2] = two_mu;

@@ -53,14 +53,27 @@ struct QpView {
     }
 };
 
-template <class M, int TILE>
+// WT = false: the stress-only instantiation (tangent == nullptr, the reference's
+// `tangent: Option<..>`): no tangent record / constant block in shared memory, nothing of the
+// tangent computed or stored -- the smaller footprint buys one more resident CTA per SM.
+template <class M, int TILE, bool WT = true>
 constexpr size_t tile_smem_bytes()
 {
-    return sizeof(double) * (2 * M::wsum() * TILE + M::aux_doubles(TILE)) + 2 * sizeof(uint64_t);
+    return sizeof(double) * (2 * M::wsum() * TILE + (WT ? M::aux_doubles(TILE) : 0)) + 2 * sizeof(uint64_t);
 }
 
-template <class M, int TILE>
-__global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
+template <class M, int TILE, bool WT>
+constexpr int tile_min_ctas()
+{
+    if (WT || M::min_ctas(TILE) * TILE < 512)  // register-hungry models (Drucker-Prager) keep their budget
+        return M::min_ctas(TILE);
+    const int by_smem = (int)((227 * 1024) / (tile_smem_bytes<M, TILE, false>() + 1024));
+    const int want = M::min_ctas(TILE) + 1;
+    return want < by_smem ? want : (by_smem > M::min_ctas(TILE) ? by_smem : M::min_ctas(TILE));
+}
+
+template <class M, int TILE, bool WT = true>
+__global__ void __launch_bounds__(TILE, tile_min_ctas<M, TILE, WT>())
     fcx_tile_kernel(const __grid_constant__ typename M::Params prm,
                     const __grid_constant__ SegPtrs<M::nseg()> io, double *__restrict__ tangent,
                     const unsigned long long n, const int flags,
@@ -82,25 +95,26 @@ __global__ void __launch_bounds__(TILE, M::min_ctas(TILE))
     //       stores from a constant shared-memory block instead of thread stores
     // tangent == nullptr: stress-only evaluate (the reference's `tangent: Option<..>`,
     //       comfe-rs/src/interfaces.rs:368): no tangent traffic at all
-    const bool want_tan = tangent != nullptr;
+    const bool want_tan = WT && tangent != nullptr;
     const bool ct_bulk = (flags & 8) != 0 && M::const_tangent_qps() > 0 && want_tan;
     const uint64_t pol = policy_evict_first();
     constexpr int NSEG = M::nseg();
     constexpr int WSUM = M::wsum();
     constexpr int SS = M::sdim() * M::sdim();
     extern __shared__ __align__(128) double smem[];
-    double *aux = smem + 2 * WSUM * TILE;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(aux + M::aux_doubles(TILE));
+    double *aux = WT ? smem + 2 * WSUM * TILE : nullptr;  // nullptr: Model::qp leaves no tangent record
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * WSUM * TILE + (WT ? M::aux_doubles(TILE) : 0));
 
     const int tid = threadIdx.x;
     const unsigned long long ntiles = (n + TILE - 1) / TILE;
 
     __shared__ unsigned long long s_ticket;
-    M::init_aux(prm, aux, tid, TILE);
+    if (WT)
+        M::init_aux(prm, aux, tid, TILE);
     if (tid == 0)
         s_ticket = (ticket != nullptr) ? gridDim.x + atomicAdd(ticket, 1ULL)
                                        : (unsigned long long)blockIdx.x + gridDim.x;
-    if (M::const_tangent_qps() > 0)
+    if (WT && M::const_tangent_qps() > 0)
         fence_proxy_async_smem();  // aux is a bulk-store source (constant tangent block)
     if (tid == 0) {
         mbar_init(&bars[0], 1);

@@ -391,6 +391,9 @@ int fcx_tune(const char *key, int value);
  * DRAM ceiling for that mix.  src holds >= 22*n doubles, dst >= 49*n doubles
  * (DEVICE).  Returns the QP-equivalents actually processed (<= n_qps). */
 long long fcx_diag_stream_mix(const double *src, double *dst, size_t n_qps, void *stream);
+/* fp64 peak of the current device from chains of independent DFMAs (no memory traffic), in TFLOP/s
+ * (2 flops per DFMA): the denominator for any fp64-pipe utilisation that is quoted.  < 0 on error. */
+double fcx_diag_dfma_peak(void);
 
 #ifdef __cplusplus
 }

