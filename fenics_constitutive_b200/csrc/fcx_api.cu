@@ -65,7 +65,8 @@ static int g_mises_so_variant = 0;
 // Hand tiles out through an atomic ticket counter (all tile kernels).
 static int g_dynamic_tiles = 1;
 static int g_fem_variant = 1;
-static int g_gather_variant = 1;  // 1 = nodal values staged by cp.async one tile ahead (gather_staged_kernel)
+static int g_gather_variant = 2;  // 2 = thread per cell + constant-bank table (gather_cell_kernel, 3-D 4-point rules),
+                                  // 1 = nodal values staged by cp.async one tile ahead (gather_staged_kernel), 0 = register loads
 static int g_hints = 8;  // bit1: evict_first on bulk loads, bit2: on bulk stores,
                          // bit3: constant tangents written by bulk stores from shared memory
 

@@ -21,6 +21,8 @@
 // (double-buffered) and leaves as one bulk async store.
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "../../include/fcx.h"
 #include "fcx_fem.cuh"
 #include "fcx_internal.h"
@@ -308,6 +310,196 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
         bulk_wait_read_all();
 }
 
+// ---------------------------------------------------------------------------
+// gather_cell_kernel: ONE THREAD PER CELL, basis-gradient table in the constant bank.
+//
+// ncu on gather_staged_kernel (profiles/r1zh_gather_ncu_full.json) shows the shared-memory data
+// pipe as its limiter: per 32-cell tile 255 LDS + 78 STS + 144 LDGSTS + 180 bulk-copy wavefronts,
+// of which 120 LDS wavefronts only re-read the basis-gradient table and another 120 read every
+// nodal value twice (two threads per cell).  Here
+//   * a thread owns a whole cell (all NQ = 4 quadrature points): every nodal value is read from
+//     shared memory once, as 16-byte loads whose 240-byte lane stride is bank-conflict free;
+//   * the table dphi_ref sits in __constant__ memory (copied device-to-device on the launch
+//     stream), so with the quadrature-point and node loops unrolled its entries are constant-bank
+//     operands of the DFMAs: no load instruction, no register, no wavefront;
+//   * each thread writes its cell's 36 results as one 288-byte row with a padded row stride
+//     (38 doubles: conflict-free 16-byte stores) and ships it with its own bulk async store --
+//     rows are thread-private, so the output needs no CTA barrier.
+// Staging of dofmap / Jinv rows (bulk copies, two tiles ahead) and of the nodal values (8-byte
+// cp.async, one tile ahead) is gather_staged_kernel's.  Same fma chains in the same order as
+// grad_at_qp (a ascending, then the Jinv contraction), hence the same bits as the other kernels.
+// 3-D cells with 4-point rules only (P2 / P1 tetrahedra, q_degree 2); whole tiles of 64 cells.
+// ---------------------------------------------------------------------------
+constexpr int GC_MAX_TAB = 4 * 10 * 3;
+__constant__ double c_gather_tab[GC_MAX_TAB];  // dphi_ref [NQ][ND][3] of the launch in flight
+
+template <int ND, bool PREV>
+struct CellGatherCfg {
+    static constexpr int NQ = 4, G = 3, GG = 9;
+    static constexpr int CPT = 64;              // cells per tile = threads per CTA
+    static constexpr int ROW = 38;              // doubles per staged output row (36 used)
+    static constexpr int NDU = CPT * ND * G;    // nodal doubles per tile
+    static constexpr int NVEC = PREV ? 2 : 1;
+    static constexpr int DOF_DBL = (CPT * ND + 1) / 2;
+    static constexpr size_t smem_bytes =
+        sizeof(double) * ((size_t)CPT * ROW + 2 * NVEC * NDU + 3 * CPT * GG + 3 * DOF_DBL + 4);
+};
+
+template <int ND, bool PREV>
+__global__ void __launch_bounds__(64)
+    gather_cell_kernel(const __grid_constant__ GatherArgs A)
+{
+    using SC = CellGatherCfg<ND, PREV>;
+    constexpr int NQ = 4, G = 3, GG = 9, CPT = SC::CPT, NT = SC::CPT, NDU = SC::NDU, NVEC = SC::NVEC, ROW = SC::ROW;
+    static_assert((ND * G) % 2 == 0, "a cell's nodal block must be a whole number of 16-byte pairs");
+    extern __shared__ __align__(128) double smem[];
+    double *s_out = smem;                          // [CPT][ROW]
+    double *s_du = s_out + CPT * ROW;              // [2][NVEC][NDU]
+    double *s_jinv = s_du + 2 * NVEC * NDU;        // [3][CPT][GG]
+    double *s_dofd = s_jinv + 3 * CPT * GG;        // [3][CPT][ND] ints
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_dofd + 3 * SC::DOF_DBL);  // [3]
+    __shared__ unsigned long long s_tile[4];
+    auto dof_slot = [&](int s) { return reinterpret_cast<int *>(s_dofd + s * SC::DOF_DBL); };
+
+    const int tid = threadIdx.x;
+    const unsigned long long ntiles = A.ncells / CPT;  // whole tiles only
+    auto issue_A = [&](unsigned long long t, int s) {
+        const unsigned long long c0 = t * CPT;
+        mbar_arrive_expect_tx(bar + s, (uint32_t)(sizeof(double) * CPT * GG + sizeof(int) * CPT * ND));
+        bulk_g2s(s_jinv + s * CPT * GG, A.Jinv + c0 * GG, (uint32_t)(sizeof(double) * CPT * GG), bar + s);
+        bulk_g2s(dof_slot(s), A.dofmap + c0 * ND, (uint32_t)(sizeof(int) * CPT * ND), bar + s);
+    };
+    auto next_ticket = [&]() -> unsigned long long { return gridDim.x + atomicAdd(A.ticket, 1ULL); };
+    auto issue_B = [&](int s, int b) {
+        const int *dm = dof_slot(s);
+        double *dst = s_du + b * NVEC * NDU;
+        for (int e = tid; e < NDU; e += NT) {
+            const int cn = e / G, j = e - cn * G;
+            const size_t src = (size_t)dm[cn] * G + j;
+            cp_async_8(dst + e, A.u + src);
+            if (PREV)
+                cp_async_8(dst + NDU + e, A.u_prev + src);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < 3; ++s)
+            mbar_init(bar + s, 1);
+        fence_mbar_init();
+        const unsigned long long t0 = blockIdx.x, t1 = next_ticket();
+        s_tile[0] = t0;
+        s_tile[1] = t1;
+        issue_A(t0, 0);  // grid <= ntiles: the first tile always exists
+        if (t1 < ntiles)
+            issue_A(t1, 1);
+    }
+    __syncthreads();
+    uint32_t phase = 0;  // bit s = parity of the next completion of bar[s]
+    mbar_wait(bar + 0, 0);
+    phase ^= 1u;
+    issue_B(0, 0);
+    cp_async_commit();
+
+    for (int i = 0;; ++i) {
+        const unsigned long long tile = s_tile[i & 3];
+        if (tile >= ntiles)
+            break;
+        const int s0 = i % 3, s1 = (i + 1) % 3, s2 = (i + 2) % 3;
+        if (tid == 0) {
+            const unsigned long long t2 = next_ticket();
+            s_tile[(i + 2) & 3] = t2;
+            if (t2 < ntiles)
+                issue_A(t2, s2);
+        }
+        const unsigned long long tile1 = s_tile[(i + 1) & 3];
+        if (tile1 < ntiles) {
+            mbar_wait(bar + s1, (phase >> s1) & 1u);
+            phase ^= 1u << s1;
+            issue_B(s1, (i + 1) & 1);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();    // this thread's share of B(i) has landed
+        bulk_wait_read_all();  // this thread's previous row has left shared memory
+        __syncthreads();       // B(i) complete for every thread
+        {
+            double K[GG];
+            const double *kin = s_jinv + s0 * CPT * GG + tid * GG;
+#pragma unroll
+            for (int k = 0; k < GG; ++k)
+                K[k] = kin[k];
+            const double2 *du2 = reinterpret_cast<const double2 *>(s_du + (i & 1) * NVEC * NDU + tid * ND * G);
+            double T[NQ][G][G];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                for (int k = 0; k < G; ++k)
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+                        T[q][k][j] = 0.0;
+            // two nodes (six doubles, three 16-byte loads) at a time
+#pragma unroll
+            for (int a2 = 0; a2 < ND / 2; ++a2) {
+                double v[6];
+#pragma unroll
+                for (int h = 0; h < 3; ++h) {
+                    double2 x = du2[a2 * 3 + h];
+                    if (PREV) {
+                        const double2 y = du2[NDU / 2 + a2 * 3 + h];
+                        x.x -= y.x;
+                        x.y -= y.y;
+                    }
+                    v[2 * h] = x.x;
+                    v[2 * h + 1] = x.y;
+                }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int a = 2 * a2 + half;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                        for (int k = 0; k < G; ++k) {
+                            const double d = c_gather_tab[(q * ND + a) * G + k];
+#pragma unroll
+                            for (int j = 0; j < G; ++j)
+                                T[q][k][j] = fma(d, v[3 * half + j], T[q][k][j]);
+                        }
+                }
+            }
+            double *o = s_out + tid * ROW;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                double g[GG];
+#pragma unroll
+                for (int ii = 0; ii < G; ++ii)
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < G; ++k)
+                            acc = fma(K[k * G + ii], T[q][k][j], acc);
+                        g[ii * G + j] = acc;
+                    }
+                // 9 doubles per point: written as pairs across the point boundaries below
+#pragma unroll
+                for (int k = 0; k < GG; ++k)
+                    T[q][k / G][k % G] = g[k];  // reuse the accumulators as the result
+            }
+#pragma unroll
+            for (int p = 0; p < NQ * GG / 2; ++p) {
+                const int e0 = 2 * p, e1 = 2 * p + 1;
+                *reinterpret_cast<double2 *>(o + e0) =
+                    make_double2(T[e0 / GG][(e0 % GG) / G][e0 % G], T[e1 / GG][(e1 % GG) / G][e1 % G]);
+            }
+        }
+        fence_proxy_async_smem();
+        // the row is this thread's own: no barrier before its bulk store
+        bulk_s2g(A.grad + (tile * CPT + tid) * (NQ * GG), s_out + tid * ROW, (uint32_t)(sizeof(double) * NQ * GG));
+        bulk_commit();
+        __syncthreads();  // s_du[i & 1] and Jinv / dofmap slot s0 consumed by every thread
+    }
+    cp_async_wait<0>();
+    bulk_wait_read_all();
+}
+
 // Generic fallback for element/quadrature combinations without a compiled
 // specialisation: one thread per (cell, qp), runtime loops.
 __global__ void gather_generic_kernel(int G, int nq, int nd, const int *__restrict__ dofmap,
@@ -393,12 +585,72 @@ static int launch_gather_staged(size_t nfull_cells, const int *dofmap, const dou
     return note_cuda_error(cudaGetLastError(), "gather_staged_kernel launch");
 }
 
+// One launch of gather_cell_kernel over `nfull_cells` (a multiple of 64).  The table is copied
+// device-to-device into c_gather_tab on the launch stream; launches on other streams are ordered
+// behind the previous user of the symbol with an event (no host synchronisation).
+template <int ND, bool PREV>
+static int launch_gather_cell(size_t nfull_cells, const int *dofmap, const double *u, const double *u_prev,
+                              const double *dphi, const double *Jinv, double *grad, cudaStream_t st)
+{
+    using SC = CellGatherCfg<ND, PREV>;
+    auto kern = gather_cell_kernel<ND, PREV>;
+    static OccCache cache;  // per device
+    int occ = 1;
+    if (int rc = kernel_occupancy(cache, kern, SC::CPT, SC::smem_bytes, "occupancy(gather cell)", &occ))
+        return rc;
+    unsigned long long *ticket = tile_ticket(st);
+    if (ticket == nullptr)
+        return -1;  // dynamic tiles switched off: caller falls back
+    static std::mutex mu;
+    static cudaEvent_t last_use[FCX_MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= FCX_MAX_DEVICES)
+        return -1;
+    std::lock_guard<std::mutex> lock(mu);
+    cudaError_t e = cudaSuccess;
+    if (last_use[dev] == nullptr)
+        e = cudaEventCreateWithFlags(&last_use[dev], cudaEventDisableTiming);
+    else
+        e = cudaStreamWaitEvent(st, last_use[dev], 0);
+    if (e == cudaSuccess)
+        e = cudaMemcpyToSymbolAsync(c_gather_tab, dphi, sizeof(double) * 4 * ND * 3, 0, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess)
+        return note_cuda_error(e, "gather table -> constant bank");
+    const unsigned long long ntiles = nfull_cells / SC::CPT;
+    const int per_sm = tuned_ctas_per_sm() > 0 ? tuned_ctas_per_sm() : occ;
+    unsigned long long grid = (unsigned long long)sm_count() * per_sm;
+    if (grid > ntiles)
+        grid = ntiles;
+    GatherArgs A{dofmap, u, u_prev, dphi, Jinv, grad, (unsigned long long)nfull_cells, ticket, 1};
+    kern<<<(unsigned)grid, SC::CPT, SC::smem_bytes, st>>>(A);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaEventRecord(last_use[dev], st);
+    return note_cuda_error(e, "gather_cell_kernel launch");
+}
+
 template <int G, int ND, int NQ>
 static int launch_gather(size_t ncells, const int *dofmap, const double *u, const double *u_prev,
                          const double *dphi, const double *Jinv, double *grad, cudaStream_t st)
 {
     using Cfg = GatherCfg<G, ND, NQ>;
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    // thread-per-cell kernel (fcx_tune "gather_variant" 2): 3-D cells with 4-point rules, whole 64-cell tiles
+    if constexpr (G == 3 && NQ == 4) {
+        const size_t nfull64 = ncells / 64 * 64;
+        if (gather_variant() >= 2 && nfull64 >= 64 * 4 && al16(dofmap) && al16(Jinv) && al16(grad) && al16(dphi)) {
+            int rc = u_prev ? launch_gather_cell<ND, true>(nfull64, dofmap, u, u_prev, dphi, Jinv, grad, st)
+                            : launch_gather_cell<ND, false>(nfull64, dofmap, u, u_prev, dphi, Jinv, grad, st);
+            if (rc != -1) {
+                if (rc != FCX_OK || nfull64 == ncells)
+                    return rc;
+                return launch_gather_plain<G, ND, NQ>(ncells - nfull64, dofmap + nfull64 * ND, u, u_prev, dphi,
+                                                      Jinv + nfull64 * G * G, grad + nfull64 * NQ * G * G, st);
+            }
+        }
+    }
     const size_t nfull = ncells / Cfg::CPT * Cfg::CPT;
     // staged kernel (fcx_tune "gather_variant" 1): whole aligned tiles
     if (gather_variant() >= 1 && nfull >= (size_t)Cfg::CPT * 4 && al16(dofmap) && al16(Jinv) && al16(grad)) {

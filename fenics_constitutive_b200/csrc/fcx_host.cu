@@ -69,6 +69,13 @@ static HostCtx g_ctx;
 static std::mutex g_mu;
 static size_t g_chunk = (size_t)1 << 18;
 static size_t g_chunk_staged = (size_t)1 << 16;  // smaller chunks: the ring slots are pinned memory
+// Pageable callers: the pool also copies every input into the ring slots, so it wants more threads and
+// finer chunks than the page-locked path (16-core host, 16 M QPs, profiles/r2b_e2e_sweep_*.jsonl:
+// pageable 105 -> 118-121 M QP/s with 12-14 threads and 32 Ki-point chunks; page-locked arrays are
+// best at 4-8 threads, 152-160 M QP/s, and lose 5-10 % with 12-16).
+static size_t g_chunk_pageable = (size_t)1 << 15;
+static bool g_chunk_user = false;     // fcx_host_chunk_qps was called: it rules both
+static bool g_call_pageable = false;  // the call being served stages pageable arrays (set under g_mu)
 static int g_staging = 1;                        // stage pageable arrays with the host-thread pool
 static int g_threads = 0;                        // 0 = auto
 // Chunks in flight.  The pipeline is a closed loop of stations (upload engine, kernels + download,
@@ -322,7 +329,7 @@ static int pool_threads(bool wide = false)
         t = hw / local_world;
         t = t < 4 ? (hw > 3 ? 4 : 1) : t;
     }
-    const int cap = wide ? 16 : 8;
+    const int cap = wide ? 16 : (g_call_pageable ? 14 : 8);
     return t > cap ? cap : t;
 }
 
@@ -452,6 +459,11 @@ static int run_pipeline_staged(const HostArr *arr, int narr, const bool *pageabl
                                Launch &&launch, const Packer *packer = nullptr)
 {
     size_t chunk = g_chunk_staged < g_chunk ? g_chunk_staged : g_chunk;  // fcx_host_chunk_qps caps both
+    g_call_pageable = false;
+    for (int a = 0; a < narr; ++a)
+        g_call_pageable = g_call_pageable || pageable[a];
+    if (g_call_pageable && !g_chunk_user && g_chunk_pageable < chunk)
+        chunk = g_chunk_pageable;
     chunk = chunk < n ? chunk : n;
     chunk = (chunk + 127) & ~(size_t)127;
     size_t off[MAXARR], total = 0, pin_in[MAXARR], pin_out[MAXARR], pin_total = 0;
@@ -969,6 +981,8 @@ static int effective_wire(const void *stress, const void *tangent, const void *h
 {
     if (g_wire != 3)
         return g_wire;
+    if (tangent == nullptr)  // stress-only call: 104 B per point come back, plain DMA beats the record wire
+        return 0;            // (page-locked 250 vs 224 M QP/s, pageable 152 vs 148; profiles/r2b_e2e_sweep_so.jsonl)
     static const int ranks = [] {
         const char *e = getenv("FCX_WIRE_AUTO_RANKS");
         const int v = e ? atoi(e) : 4;
@@ -1286,8 +1300,10 @@ extern "C" {
 size_t fcx_host_chunk_qps(size_t v)
 {
     const size_t old = g_chunk;
-    if (v > 0)
+    if (v > 0) {
         g_chunk = v;
+        g_chunk_user = true;
+    }
     return old;
 }
 

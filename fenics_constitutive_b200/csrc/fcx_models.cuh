@@ -782,8 +782,16 @@ struct DruckerPragerModel {
         state(P, sigtr, bfe, S);
         failed = S.apex;
         plastic = !(S.f <= 0.0);  // :133
-        double no_rec[REC];  // stress-only instantiation (aux == nullptr): the record is dead code
-        double *rec = aux != nullptr ? aux + t * REC : no_rec;
+        // the tangent record is built in registers and leaves for shared memory at every exit
+        // (stress-only instantiation, aux == nullptr: dead code)
+        double rec[REC];
+        auto flush = [&]() {
+            if (aux != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k)
+                    aux[t * REC + k] = rec[k];
+            }
+        };
         rec[0] = P.kappa + two_mu * (2.0 / 3.0);  // elastic tangent 3 kappa P_vol + 2 mu P_dev
         rec[1] = P.kappa - two_mu / 3.0;          // (also what a failed point reports)
         rec[2] = two_mu;
@@ -796,6 +804,7 @@ struct DruckerPragerModel {
                 for (int i = 0; i < 6; ++i)
                     v.template st<1>(i, sigtr[i]);
             }
+            flush();
             return;
         }
         const double alpha_0 = hist[0];
@@ -873,8 +882,10 @@ struct DruckerPragerModel {
                 break;
             }
         }
-        if (failed)
+        if (failed) {
+            flush();
             return;  // the Rust code panics; nothing is written for this point
+        }
         // ---- commit: stress, alpha, plastic strain += de - C^-1 (sigma_1 - sigma_0)  (:249-252) ----
         double x[6];
 #pragma unroll
@@ -913,6 +924,7 @@ struct DruckerPragerModel {
             for (int k = 0; k < 6; ++k)
                 rec[6 + k] = S.s[k];
         }
+        flush();
     }
 
     // M_ij = [vol block] + m1 delta_ij + A3 s_i s_j + A4 1_i s_j + A5 s_i 1_j

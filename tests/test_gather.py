@@ -124,12 +124,14 @@ def test_gpu_gather_feeds_evaluate():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gdim,degree,qdeg,ncells", [(3, 2, 2, 40_007), (3, 2, 2, 4 * 32), (3, 1, 1, 9_001), (3, 1, 2, 5_000),
+@pytest.mark.parametrize("gdim,degree,qdeg,ncells", [(3, 2, 2, 40_007), (3, 2, 2, 4 * 32), (3, 2, 2, 4 * 64), (3, 2, 2, 200_000),
+                                                      (3, 1, 1, 9_001), (3, 1, 2, 5_000),
                                                       (2, 2, 2, 7_777), (2, 1, 2, 3_333), (1, 2, 2, 2_049), (1, 1, 1, 1_000)])
 @pytest.mark.parametrize("with_prev", [True, False])
 def test_gpu_gather_staged_kernel_bitwise(gdim, degree, qdeg, ncells, with_prev):
     """gather_staged_kernel (nodal values staged by cp.async one tile ahead, fcx_tune
-    "gather_variant" 1, the default) runs the same fma chains as gather_kernel: bit-identical
+    "gather_variant" 1) and gather_cell_kernel (thread per cell, table in the constant bank, variant 2,
+    the default for 3-D 4-point rules) run the same fma chains as gather_kernel: bit-identical
     output, ragged tails and many tiles per CTA included; and both match the oracle."""
     import torch
 
@@ -149,13 +151,13 @@ def test_gpu_gather_staged_kernel_bitwise(gdim, degree, qdeg, ncells, with_prev)
     outs = []
     old = L.fcx_tune(b"gather_variant", -1)
     try:
-        for variant in (0, 1, 1):
+        for variant in (0, 1, 2, 2):  # 2 = gather_cell_kernel (thread per cell, 3-D 4-point rules; else as 1)
             L.fcx_tune(b"gather_variant", variant)
             out = torch.full((op.num_qps * gdim * gdim,), float("nan"), dtype=torch.float64, device="cuda")
             op.evaluate(torch.from_numpy(u).cuda(), torch.from_numpy(u_prev).cuda() if with_prev else None, out)
             outs.append(out.cpu().numpy())
     finally:
         L.fcx_tune(b"gather_variant", old)
-    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2])
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])
     ref = om.gather_grad(gdim, dofmap, u, u_prev, dphi, Jinv)
     assert np.max(np.abs(outs[1] - ref)) <= 1e-12 * np.abs(ref).max()
