@@ -51,6 +51,15 @@ SIGNATURES = {
     "fcx_pcg_pap": (_ci, [_sz, _dp, _dp, _dp, _dp, _vp, _dp, _vp]),
     "fcx_pcg_update_xr": (_ci, [_sz, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _dp, _vp]),
     "fcx_pcg_update_p": (_ci, [_sz, _dp, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_krylov_create": (_ci, [_ci, _ci, _ci, _sz, _vp, _vp, _vp]),
+    "fcx_krylov_connect": (_ci, [_vp, _vp]),
+    "fcx_krylov_set_halo": (_ci, [_vp, _ci, _vp, _vp, _vp, _vp]),
+    "fcx_krylov_set_operator": (_ci, [_vp, _ci, _ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp, _vp]),
+    "fcx_krylov_begin": (_ci, [_vp, _dp, _dp, _vp]),
+    "fcx_krylov_iterate": (_ci, [_vp, _ci, _vp]),
+    "fcx_krylov_status": (_ci, [_vp, _vp]),
+    "fcx_krylov_solution": (_ci, [_vp, _dp, _vp]),
+    "fcx_krylov_destroy": (None, [_vp]),
     "fcx_elastic_evaluate_host": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp]),
     "fcx_mises_evaluate_host": (_ci, [_dp, _sz, _dp, _dp, _dp, _dp, _dp, _vp]),
     "fcx_kelvin_evaluate_host": (_ci, [_ci, _dp, _dp, _cd, _cd, _cd, _cd, _cd, _sz, _dp, _dp, _dp, _dp, _dp]),

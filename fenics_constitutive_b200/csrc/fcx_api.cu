@@ -65,8 +65,12 @@ static int g_mises_so_variant = 0;
 // Hand tiles out through an atomic ticket counter (all tile kernels).
 static int g_dynamic_tiles = 1;
 static int g_fem_variant = 1;
-static int g_gather_variant = 2;  // 2 = thread per cell + constant-bank table (gather_cell_kernel, 3-D 4-point rules),
-                                  // 1 = nodal values staged by cp.async one tile ahead (gather_staged_kernel), 0 = register loads
+// 1 = nodal values staged by cp.async one tile ahead (gather_staged_kernel, the default), 0 = register loads
+// (gather_kernel), 2 = thread per cell with the basis-gradient table in the constant bank (gather_cell_kernel,
+// 3-D 4-point rules): bit-identical, but measured SLOWER on B200 (0.139 vs 0.104 ms for 998 250 P2 tets,
+// profiles/r2c_gather_ab.jsonl): its 1.1 KB of shared memory per cell caps an SM at 6 warps (ncu: 9 % occupancy,
+// issue slots 34 %, every stall a fixed-latency wait with nothing else to issue).
+static int g_gather_variant = 1;
 static int g_hints = 8;  // bit1: evict_first on bulk loads, bit2: on bulk stores,
                          // bit3: constant tangents written by bulk stores from shared memory
 

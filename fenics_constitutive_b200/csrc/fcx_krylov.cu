@@ -1,0 +1,639 @@
+// fcx_krylov.cu -- device-resident Krylov loop of the stand-in NewtonSolver: single-reduction
+// (Chronopoulos-Gear) Jacobi-preconditioned conjugate gradients whose reduction and ghost exchange
+// run over NVLink PEER MEMORY from inside the kernels -- no NCCL call, no host round trip and no
+// Python in the iteration.
+//
+// Where this sits: the reference leaves the linear solve of every Newton step to PETSc through
+// dolfinx.nls.petsc.NewtonSolver (third-party); with the mesh partitioned over MPI
+// ranks (solver/_solver.py:64-68, tests/solver/test_solver_mpi.py:93-121) PETSc exchanges the ghost
+// values of the Krylov vectors and all-reduces the dot products.  The stand-in did the same with
+// NCCL issued from Python: two all-reduces + one send/recv per iteration, 0.43 ms per iteration on
+// two GPUs against 0.18 ms of kernels.  Here one iteration is
+//     K1  element kernel        fe = B^T C B u_e             (fcx_tangent_apply[_rec], unchanged)
+//     K2  gsum_dots_kernel      w = sum fe (node-wise, fixed order);  partial (r.u, w.u, r.r) over
+//                               owned free dofs; the last CTA adds the CTA partials in index order
+//                               and STORES the three sums into every rank's reduction slot
+//     K3  cg_update_kernel      waits for all ranks' slots, adds them in RANK order (every rank gets
+//                               the same bits), alpha / beta, then  p = u + beta p;  s = w + beta s;
+//                               x += alpha p;  r -= alpha s;  u = minv r
+//     K4  halo_push_kernel      u of the nodes that are ghosts elsewhere is stored straight into the
+//                               neighbours' vectors; a system-scope flag tells them; then waits for
+//                               the neighbours' flags (so K1 of the next iteration reads fresh ghosts)
+// with  gamma = r.u, delta = w.u:  beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)
+// -- ONE reduction per iteration instead of two, one fused vector pass instead of three kernels.
+// fcx_krylov_iterate enqueues a block of iterations from C; the host looks at the residual history
+// once per block.  One process per GPU: peers' buffers come from CUDA IPC handles.
+//
+// Ordering between ranks: a reduction slot / flag pair is double-buffered by iteration parity; a rank
+// can only run ahead to iteration i+2's K2 after every rank has finished iteration i's K3 (it needs
+// their i+1 sums), so a slot is never overwritten while someone still reads it.  Ghost values for
+// iteration i+1 are pushed after K3 of iteration i, which every neighbour can only reach after its own
+// K1 of iteration i has finished reading (the reduction is a barrier) -- no write-after-read hazard.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/fcx.h"
+#include "fcx_fem.cuh"
+#include "fcx_internal.h"
+
+namespace fcx {
+
+constexpr int KR_THREADS = 256;
+constexpr int KR_MAX_WORLD = 16;
+constexpr int KR_HIST = 1 << 16;  // residual history entries (ring)
+
+// One rank's communication block (a single cudaMalloc, exported through an IPC handle):
+//   [ u vector: n doubles, padded to 256 B | red[2][W][4] doubles | redflag[2][W] u64 | haloflag[W] u64 ]
+struct CommLayout {
+    size_t n_pad, off_red, off_redflag, off_haloflag, bytes;
+    __host__ __device__ CommLayout() : n_pad(0), off_red(0), off_redflag(0), off_haloflag(0), bytes(0) {}
+    __host__ CommLayout(size_t n, int world)
+    {
+        n_pad = (n * sizeof(double) + 255) & ~(size_t)255;
+        off_red = n_pad;
+        off_redflag = off_red + sizeof(double) * 2 * world * 4;
+        off_haloflag = off_redflag + sizeof(unsigned long long) * 2 * world;
+        bytes = (off_haloflag + sizeof(unsigned long long) * world + 255) & ~(size_t)255;
+    }
+};
+
+struct PeerPtrs {
+    char *base[KR_MAX_WORLD];  // comm block of every rank (own block included), device-visible
+};
+
+struct Krylov {
+    int rank = 0, world = 1, gdim = 3;
+    size_t n = 0, nnodes = 0;
+    CommLayout lay;
+    char *comm = nullptr;  // own comm block
+    PeerPtrs peers{};
+    bool peer_open[KR_MAX_WORLD] = {};
+    // vectors (own allocations); u lives at the head of the comm block
+    double *x = nullptr, *r = nullptr, *w = nullptr, *p = nullptr, *s = nullptr, *minv = nullptr;
+    double *partials = nullptr;          // [3][grid]
+    unsigned *ticket = nullptr;          // [2]: K2 reduction, K4 completion
+    double *state = nullptr;             // [2][4]: gamma, alpha, rr, breakdown flag per parity
+    double *hist = nullptr;              // [KR_HIST]: r.r at the start of iteration it
+    // halo plan (device): flattened send entries over all neighbours
+    int n_nbr = 0, n_send = 0;
+    int nbr_rank[KR_MAX_WORLD] = {};
+    int *send_src = nullptr, *send_dst = nullptr, *send_nbr = nullptr;  // [n_send]: my node, peer's node, slot
+    // operator
+    int op_mode = 0;  // 3 = tangent records, 1 = dense tangents
+    int sdim = 6, nq = 0, nd = 0;
+    size_t ncells = 0;
+    const int *dofmap = nullptr, *fe_pos = nullptr, *adj_idx = nullptr;
+    const long long *adj_ptr = nullptr;
+    const double *dphi = nullptr, *weights = nullptr, *Jinv = nullptr, *detJ = nullptr, *tang = nullptr;
+    double *fe = nullptr;
+    // progress
+    unsigned long long epoch = 0;  // reductions / pushes done since creation (same on every rank)
+    unsigned long long it = 0;     // iterations of the current solve
+    unsigned grid = 1;
+};
+
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile(const double *p)
+{
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ double kr_block_sum(double v, double *sh)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        v += __shfl_down_sync(0xffffffffu, v, d);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0)
+        sh[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < KR_THREADS / 32; ++k)
+            t += sh[k];
+    }
+    __syncthreads();
+    return t;  // valid in thread 0
+}
+
+// x = 0, r = rhs on free owned dofs (minv != 0) else 0, u = minv r, p = s = 0
+__global__ void __launch_bounds__(KR_THREADS)
+    kr_begin_kernel(size_t n, const double *__restrict__ rhs, const double *__restrict__ minv_in,
+                    double *__restrict__ minv, double *__restrict__ x, double *__restrict__ r,
+                    double *__restrict__ u, double *__restrict__ p, double *__restrict__ s)
+{
+    const size_t stride = (size_t)gridDim.x * KR_THREADS;
+    for (size_t i = (size_t)blockIdx.x * KR_THREADS + threadIdx.x; i < n; i += stride) {
+        const double m = minv_in[i];
+        const double rv = m != 0.0 ? rhs[i] : 0.0;
+        minv[i] = m;
+        x[i] = 0.0;
+        r[i] = rv;
+        u[i] = m * rv;
+        p[i] = 0.0;
+        s[i] = 0.0;
+    }
+}
+
+// K2: w = node-wise sum of the element vectors (fixed order: deterministic, no atomics) and the
+// three dot products of the iteration over the free owned dofs.
+template <int G>
+__global__ void __launch_bounds__(KR_THREADS)
+    gsum_dots_kernel(const long long *__restrict__ adj_ptr, const int *__restrict__ adj_idx,
+                     const double *__restrict__ fe, const double *__restrict__ r, const double *__restrict__ u,
+                     const double *__restrict__ minv, double *__restrict__ w, unsigned long long nnodes,
+                     double *partials, unsigned *ticket, PeerPtrs peers, CommLayout lay, int rank, int world,
+                     unsigned long long epoch)
+{
+    __shared__ double sh[KR_THREADS / 32];
+    __shared__ bool last;
+    double g = 0.0, d = 0.0, q = 0.0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < nnodes; v += stride) {
+        double acc[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j)
+            acc[j] = 0.0;
+        const long long e0 = adj_ptr[v], e1 = adj_ptr[v + 1];
+        for (long long e = e0; e < e1; ++e) {
+            const double *src = fe + (size_t)(adj_idx != nullptr ? adj_idx[e] : e) * FeStride<G>::v;
+            if (G == 3) {
+                const double2 xy = *reinterpret_cast<const double2 *>(src);
+                acc[0] += xy.x;
+                acc[1 % G] += xy.y;
+                acc[2 % G] += src[2];
+            } else {
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    acc[j] += src[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const size_t i = v * G + j;
+            w[i] = acc[j];
+            if (minv[i] != 0.0) {
+                const double rv = r[i], uv = u[i];
+                g = fma(rv, uv, g);
+                d = fma(acc[j], uv, d);
+                q = fma(rv, rv, q);
+            }
+        }
+    }
+    const double bg = kr_block_sum(g, sh), bd = kr_block_sum(d, sh), bq = kr_block_sum(q, sh);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = bg;
+        partials[gridDim.x + blockIdx.x] = bd;
+        partials[2 * gridDim.x + blockIdx.x] = bq;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 3) {
+        __threadfence();
+        double acc = 0.0;
+        const volatile double *src = partials + (size_t)threadIdx.x * gridDim.x;
+        for (unsigned b = 0; b < gridDim.x; ++b)
+            acc += src[b];
+        // all-gather of the local sums: one slot per (parity, source rank) in EVERY rank's block
+        const int par = (int)(epoch & 1ULL);
+        for (int t = 0; t < world; ++t) {
+            double *slot = reinterpret_cast<double *>(peers.base[t] + lay.off_red) + ((size_t)par * world + rank) * 4;
+            slot[threadIdx.x] = acc;
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence_system();
+        const int par = (int)(epoch & 1ULL);
+        for (int t = 0; t < world; ++t) {
+            unsigned long long *flag =
+                reinterpret_cast<unsigned long long *>(peers.base[t] + lay.off_redflag) + (size_t)par * world + rank;
+            st_flag(flag, epoch);
+        }
+        *ticket = 0;
+    }
+}
+
+// K3: finish the reduction (rank order), alpha / beta, fused vector update.
+__global__ void __launch_bounds__(KR_THREADS)
+    cg_update_kernel(size_t n, double *__restrict__ x, double *__restrict__ r, double *__restrict__ u,
+                     const double *__restrict__ w, double *__restrict__ p, double *__restrict__ s,
+                     const double *__restrict__ minv, char *comm, CommLayout lay, int world,
+                     unsigned long long epoch, int first, double *state, double *hist, unsigned long long it)
+{
+    __shared__ double sc[2];
+    if (threadIdx.x == 0) {
+        const int par = (int)(epoch & 1ULL);
+        const unsigned long long *flags =
+            reinterpret_cast<const unsigned long long *>(comm + lay.off_redflag) + (size_t)par * world;
+        const double *red = reinterpret_cast<const double *>(comm + lay.off_red) + (size_t)par * world * 4;
+        double g = 0.0, d = 0.0, q = 0.0;
+        for (int t = 0; t < world; ++t) {
+            while (ld_flag(flags + t) != epoch) {
+            }
+            g += ld_volatile(red + t * 4 + 0);
+            d += ld_volatile(red + t * 4 + 1);
+            q += ld_volatile(red + t * 4 + 2);
+        }
+        const double *prev = state + (size_t)(par ^ 1) * 4;  // written by the previous iteration's launch
+        double beta = 0.0, den = d;
+        if (!first) {
+            beta = prev[0] > 0.0 ? g / prev[0] : 0.0;
+            den = prev[1] != 0.0 ? d - beta * g / prev[1] : d;
+        }
+        // den <= 0: the operator is not positive definite on the free dofs (or the solve has converged to
+        // round-off): stop moving and flag it; the host decides
+        const double alpha = den > 0.0 ? g / den : 0.0;
+        sc[0] = alpha;
+        sc[1] = beta;
+        if (blockIdx.x == 0) {
+            double *cur = state + (size_t)par * 4;
+            cur[0] = g;
+            cur[1] = alpha;
+            cur[2] = q;
+            cur[3] = den > 0.0 ? (first ? 0.0 : prev[3]) : 1.0;  // sticky breakdown flag of this solve
+            hist[it % KR_HIST] = q;
+        }
+    }
+    __syncthreads();
+    const double alpha = sc[0], beta = sc[1];
+    const size_t n2 = n / 2;
+    double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
+    double2 *u2 = reinterpret_cast<double2 *>(u), *p2 = reinterpret_cast<double2 *>(p);
+    double2 *s2 = reinterpret_cast<double2 *>(s);
+    const double2 *w2 = reinterpret_cast<const double2 *>(w), *m2 = reinterpret_cast<const double2 *>(minv);
+    auto one = [&](double m, double uv, double wv, double &pv, double &sv, double &xv, double &rv, double &un) {
+        const double al = m != 0.0 ? alpha : 0.0;
+        pv = fma(beta, pv, uv);
+        sv = fma(beta, sv, wv);
+        xv = fma(al, pv, xv);
+        rv = fma(-al, sv, rv);
+        un = m * rv;
+    };
+    const size_t stride = (size_t)gridDim.x * KR_THREADS;
+    for (size_t i = (size_t)blockIdx.x * KR_THREADS + threadIdx.x; i < n2; i += stride) {
+        const double2 m = m2[i], uv = u2[i], wv = w2[i];
+        double2 pv = p2[i], sv = s2[i], xv = x2[i], rv = r2[i], un;
+        one(m.x, uv.x, wv.x, pv.x, sv.x, xv.x, rv.x, un.x);
+        one(m.y, uv.y, wv.y, pv.y, sv.y, xv.y, rv.y, un.y);
+        p2[i] = pv;
+        s2[i] = sv;
+        x2[i] = xv;
+        r2[i] = rv;
+        u2[i] = un;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const size_t i = n - 1;
+        double un;
+        one(minv[i], u[i], w[i], p[i], s[i], x[i], r[i], un);
+        u[i] = un;
+    }
+}
+
+// K4: owned values that are ghosts elsewhere -> the neighbours' u vectors (peer stores), then the
+// epoch flag; finally wait for every neighbour's flag of the same epoch.
+template <int G>
+__global__ void __launch_bounds__(KR_THREADS)
+    halo_push_kernel(const double *__restrict__ u, const int *__restrict__ send_src, const int *__restrict__ send_dst,
+                     const int *__restrict__ send_nbr, int n_send, PeerPtrs nbr_base, CommLayout lay, int n_nbr,
+                     int rank, char *comm, const int *__restrict__ nbr_rank_dev, unsigned *ticket,
+                     unsigned long long epoch)
+{
+    __shared__ bool last;
+    const int stride = gridDim.x * blockDim.x;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_send; e += stride) {
+        double *dst = reinterpret_cast<double *>(nbr_base.base[send_nbr[e]]) + (size_t)send_dst[e] * G;
+        const double *src = u + (size_t)send_src[e] * G;
+#pragma unroll
+        for (int j = 0; j < G; ++j)
+            dst[j] = src[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence_system();
+        for (int k = 0; k < n_nbr; ++k)
+            st_flag(reinterpret_cast<unsigned long long *>(nbr_base.base[k] + lay.off_haloflag) + rank, epoch);
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(comm + lay.off_haloflag);
+        for (int k = 0; k < n_nbr; ++k)
+            while (ld_flag(mine + nbr_rank_dev[k]) < epoch) {
+            }
+        *ticket = 0;
+    }
+}
+
+static unsigned kr_grid(size_t work)
+{
+    size_t g = (work + KR_THREADS - 1) / KR_THREADS;
+    const size_t cap = (size_t)sm_count() * 8;
+    return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+static int kr_push(Krylov *K, cudaStream_t st)
+{
+    if (K->world == 1 || K->n_nbr == 0)
+        return FCX_OK;
+    PeerPtrs nb{};
+    for (int k = 0; k < K->n_nbr; ++k)
+        nb.base[k] = K->peers.base[K->nbr_rank[k]];
+    const unsigned grid = kr_grid(K->n_send > 0 ? (size_t)K->n_send : 1);
+    double *u = reinterpret_cast<double *>(K->comm);
+    // nbr ranks on the device: kept right behind the send plan
+    const int *nbr_rank_dev = K->send_nbr + K->n_send;
+#define FCX_PUSH(G) \
+    halo_push_kernel<G><<<grid, KR_THREADS, 0, st>>>(u, K->send_src, K->send_dst, K->send_nbr, K->n_send, nb, K->lay, \
+                                                     K->n_nbr, K->rank, K->comm, nbr_rank_dev, K->ticket + 1, K->epoch)
+    if (K->gdim == 1)
+        FCX_PUSH(1);
+    else if (K->gdim == 2)
+        FCX_PUSH(2);
+    else
+        FCX_PUSH(3);
+#undef FCX_PUSH
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "halo_push_kernel launch");
+}
+
+}  // namespace fcx
+
+using namespace fcx;
+
+extern "C" {
+
+int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, void **handle_out, void **comm_out,
+                      unsigned char *ipc_handle_out /* 64 bytes */)
+{
+    if (!handle_out || !comm_out || !ipc_handle_out)
+        return FCX_ERR_NULL;
+    if (world < 1 || world > KR_MAX_WORLD || rank < 0 || rank >= world || gdim < 1 || gdim > 3 || nnodes == 0)
+        return FCX_ERR_ARG;
+    Krylov *K = new Krylov();
+    K->rank = rank;
+    K->world = world;
+    K->gdim = gdim;
+    K->nnodes = nnodes;
+    K->n = nnodes * (size_t)gdim;
+    K->lay = CommLayout(K->n, world);
+    K->grid = kr_grid(K->n / 2 + 1);
+    cudaError_t e = cudaMalloc((void **)&K->comm, K->lay.bytes);
+    if (e == cudaSuccess)
+        e = cudaMemset(K->comm, 0, K->lay.bytes);
+    double **vecs[6] = {&K->x, &K->r, &K->w, &K->p, &K->s, &K->minv};
+    for (int k = 0; k < 6 && e == cudaSuccess; ++k)
+        e = cudaMalloc((void **)vecs[k], sizeof(double) * K->n);
+    const unsigned gmax = (unsigned)sm_count() * 8;
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&K->partials, sizeof(double) * 3 * gmax);
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&K->ticket, sizeof(unsigned) * 2);
+    if (e == cudaSuccess)
+        e = cudaMemset(K->ticket, 0, sizeof(unsigned) * 2);
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&K->state, sizeof(double) * 8);
+    if (e == cudaSuccess)
+        e = cudaMemset(K->state, 0, sizeof(double) * 8);
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&K->hist, sizeof(double) * KR_HIST);
+    if (e == cudaSuccess) {
+        cudaIpcMemHandle_t h;
+        memset(&h, 0, sizeof h);
+        if (world > 1)
+            e = cudaIpcGetMemHandle(&h, K->comm);
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        memcpy(ipc_handle_out, &h, 64);
+    }
+    if (e != cudaSuccess) {
+        delete K;
+        return note_cuda_error(e, "fcx_krylov_create");
+    }
+    K->peers.base[rank] = K->comm;
+    *handle_out = K;
+    *comm_out = K->comm;
+    return FCX_OK;
+}
+
+/* ipc_handles: world x 64 bytes (rank order, own entry ignored).  Opens the peers' comm blocks. */
+int fcx_krylov_connect(void *handle, const unsigned char *ipc_handles)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K || (K->world > 1 && !ipc_handles))
+        return FCX_ERR_NULL;
+    for (int t = 0; t < K->world; ++t) {
+        if (t == K->rank)
+            continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_handles + (size_t)t * 64, 64);
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "cudaIpcOpenMemHandle");
+        K->peers.base[t] = static_cast<char *>(ptr);
+        K->peer_open[t] = true;
+    }
+    return FCX_OK;
+}
+
+/* Halo plan: for neighbour slot k (rank nbr_rank[k]) the entries [send_ptr[k], send_ptr[k+1]) of
+ * send_src (my local node) / send_dst (the neighbour's local node of the same mesh node).  HOST arrays. */
+int fcx_krylov_set_halo(void *handle, int n_nbr, const int *nbr_rank, const int *send_ptr, const int *send_src,
+                        const int *send_dst)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K)
+        return FCX_ERR_NULL;
+    if (n_nbr < 0 || n_nbr >= KR_MAX_WORLD)
+        return FCX_ERR_ARG;
+    K->n_nbr = n_nbr;
+    if (n_nbr == 0)
+        return FCX_OK;
+    if (!nbr_rank || !send_ptr || !send_src || !send_dst)
+        return FCX_ERR_NULL;
+    const int total = send_ptr[n_nbr];
+    std::vector<int> nbr((size_t)total + n_nbr);
+    for (int k = 0; k < n_nbr; ++k) {
+        K->nbr_rank[k] = nbr_rank[k];
+        for (int e = send_ptr[k]; e < send_ptr[k + 1]; ++e)
+            nbr[e] = k;
+        nbr[(size_t)total + k] = nbr_rank[k];
+    }
+    K->n_send = total;
+    cudaError_t e = cudaMalloc((void **)&K->send_src, sizeof(int) * (size_t)(total > 0 ? total : 1));
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&K->send_dst, sizeof(int) * (size_t)(total > 0 ? total : 1));
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&K->send_nbr, sizeof(int) * ((size_t)total + n_nbr));
+    if (e == cudaSuccess && total > 0)
+        e = cudaMemcpy(K->send_src, send_src, sizeof(int) * (size_t)total, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && total > 0)
+        e = cudaMemcpy(K->send_dst, send_dst, sizeof(int) * (size_t)total, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(K->send_nbr, nbr.data(), sizeof(int) * nbr.size(), cudaMemcpyHostToDevice);
+    return note_cuda_error(e, "fcx_krylov_set_halo");
+}
+
+/* The Jacobian action: the arguments of fcx_tangent_apply_rec (mode 3, `tangent` = the 10-double
+ * records) or fcx_tangent_apply (mode 1, dense tangents) + the node adjacency of fcx_gather_sum. */
+int fcx_krylov_set_operator(void *handle, int mode, int sdim, size_t ncells, int nq, int nd, const int *dofmap,
+                            const double *dphi_ref, const double *weights, const double *Jinv, const double *detJ,
+                            const double *tangent, double *fe, const int *fe_pos, const long long *adj_ptr,
+                            const int *adj_idx)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K || !dofmap || !dphi_ref || !weights || !Jinv || !detJ || !tangent || !fe || !adj_ptr)
+        return FCX_ERR_NULL;
+    if (mode != 1 && mode != 3)
+        return FCX_ERR_ARG;
+    K->op_mode = mode;
+    K->sdim = sdim;
+    K->ncells = ncells;
+    K->nq = nq;
+    K->nd = nd;
+    K->dofmap = dofmap;
+    K->dphi = dphi_ref;
+    K->weights = weights;
+    K->Jinv = Jinv;
+    K->detJ = detJ;
+    K->tang = tangent;
+    K->fe = fe;
+    K->fe_pos = fe_pos;
+    K->adj_ptr = adj_ptr;
+    K->adj_idx = fe_pos != nullptr ? nullptr : adj_idx;
+    return FCX_OK;
+}
+
+/* Start a solve: x = 0, r = rhs on the dofs with minv != 0 (free AND owned), u = minv r; pushes the
+ * ghost values of u.  rhs, minv: DEVICE vectors of n doubles. */
+int fcx_krylov_begin(void *handle, const double *rhs, const double *minv, void *stream)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K || !rhs || !minv)
+        return FCX_ERR_NULL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double *u = reinterpret_cast<double *>(K->comm);
+    kr_begin_kernel<<<kr_grid(K->n), KR_THREADS, 0, st>>>(K->n, rhs, minv, K->minv, K->x, K->r, u, K->p, K->s);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return note_cuda_error(e, "kr_begin_kernel launch");
+    K->it = 0;
+    K->epoch += 1;
+    return kr_push(K, st);
+}
+
+/* Enqueue `iters` iterations (K1..K4 each) on `stream`; never synchronises. */
+int fcx_krylov_iterate(void *handle, int iters, void *stream)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K)
+        return FCX_ERR_NULL;
+    if (K->op_mode == 0)
+        return FCX_ERR_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double *u = reinterpret_cast<double *>(K->comm);
+    const unsigned ggrid = kr_grid(K->nnodes);
+    for (int k = 0; k < iters; ++k) {
+        int rc = K->op_mode == 3
+                     ? fcx_tangent_apply_rec(K->gdim, K->sdim, K->ncells, K->nq, K->nd, K->dofmap, u, K->dphi, K->weights,
+                                             K->Jinv, K->detJ, K->tang, K->fe, K->fe_pos, stream)
+                     : fcx_tangent_apply(K->gdim, K->sdim, K->ncells, K->nq, K->nd, K->dofmap, u, K->dphi, K->weights,
+                                         K->Jinv, K->detJ, K->tang, K->fe, K->fe_pos, stream);
+        if (rc != FCX_OK)
+            return rc;
+        K->epoch += 1;
+#define FCX_GSUM(G) \
+    gsum_dots_kernel<G><<<ggrid, KR_THREADS, 0, st>>>(K->adj_ptr, K->adj_idx, K->fe, K->r, u, K->minv, K->w, K->nnodes, \
+                                                      K->partials, K->ticket, K->peers, K->lay, K->rank, K->world, K->epoch)
+        if (K->gdim == 1)
+            FCX_GSUM(1);
+        else if (K->gdim == 2)
+            FCX_GSUM(2);
+        else
+            FCX_GSUM(3);
+#undef FCX_GSUM
+        cg_update_kernel<<<K->grid, KR_THREADS, 0, st>>>(K->n, K->x, K->r, u, K->w, K->p, K->s, K->minv, K->comm, K->lay,
+                                                         K->world, K->epoch, K->it == 0 ? 1 : 0, K->state, K->hist, K->it);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return note_cuda_error(e, "krylov iteration launch");
+        K->it += 1;
+        rc = kr_push(K, st);
+        if (rc != FCX_OK)
+            return rc;
+    }
+    return FCX_OK;
+}
+
+/* After a synchronisation of the stream: out[0] = iterations done, out[1] = r.r at the start of the last
+ * iteration (= after iterations-1 updates), out[2] = r.r of iteration 0 (the right-hand side), out[3] = 1 if a
+ * breakdown (p.Ap <= 0) was seen.  Blocking copies. */
+int fcx_krylov_status(void *handle, double *out4)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K || !out4)
+        return FCX_ERR_NULL;
+    out4[0] = (double)K->it;
+    out4[1] = out4[2] = out4[3] = 0.0;
+    if (K->it == 0)
+        return FCX_OK;
+    cudaError_t e = cudaMemcpy(out4 + 1, K->hist + (K->it - 1) % KR_HIST, sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(out4 + 2, K->hist, sizeof(double), cudaMemcpyDeviceToHost);
+    double st[4];
+    const int par = (int)(K->epoch & 1ULL);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(st, K->state + (size_t)par * 4, sizeof st, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+        out4[3] = st[3];
+    return note_cuda_error(e, "fcx_krylov_status");
+}
+
+/* x (DEVICE, n doubles) <- the current iterate, on `stream`. */
+int fcx_krylov_solution(void *handle, double *x_out, void *stream)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K || !x_out)
+        return FCX_ERR_NULL;
+    return note_cuda_error(cudaMemcpyAsync(x_out, K->x, sizeof(double) * K->n, cudaMemcpyDeviceToDevice,
+                                           static_cast<cudaStream_t>(stream)),
+                           "fcx_krylov_solution");
+}
+
+void fcx_krylov_destroy(void *handle)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K)
+        return;
+    cudaDeviceSynchronize();
+    for (int t = 0; t < K->world; ++t)
+        if (K->peer_open[t])
+            cudaIpcCloseMemHandle(K->peers.base[t]);
+    void *ptrs[] = {K->comm, K->x, K->r, K->w, K->p, K->s, K->minv, K->partials, K->ticket, K->state, K->hist,
+                    K->send_src, K->send_dst, K->send_nbr};
+    for (void *q : ptrs)
+        if (q)
+            cudaFree(q);
+    delete K;
+}
+
+}  // extern "C"

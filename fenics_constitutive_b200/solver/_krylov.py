@@ -1,0 +1,111 @@
+"""Python handle of the device-resident Krylov loop (csrc/fcx_krylov.cu): Chronopoulos-Gear
+single-reduction Jacobi-PCG whose dot-product reduction and ghost exchange are peer-memory
+stores over NVLink from inside the kernels (one process per GPU, CUDA IPC), driven from C in
+blocks of iterations -- the stand-in for what PETSc does behind dolfinx.nls.petsc.NewtonSolver
+on an MPI-partitioned mesh (reference solver/_solver.py:64-68).
+
+The only collective left on the host side is the one-off exchange of the 64-byte IPC handles
+(``torch.distributed.all_gather_object``) when the solver is set up.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from .. import _buffers as B
+from .._lib import check, lib
+
+
+class DeviceKrylov:
+    def __init__(self, problem, partition=None):
+        import torch
+        import torch.distributed as dist
+
+        self.problem = problem
+        self.partition = partition
+        self.device = problem.device
+        L = self.L = lib()
+        check(L.fcx_set_device(self.device.index), "fcx_set_device")
+        world = partition.world if partition is not None else 1
+        rank = partition.rank if partition is not None else 0
+        self.world, self.rank = world, rank
+        V = problem.V
+        h, comm = ctypes.c_void_p(), ctypes.c_void_p()
+        ipc = (ctypes.c_ubyte * 64)()
+        check(L.fcx_krylov_create(rank, world, problem.gdim, V.num_nodes, ctypes.byref(h), ctypes.byref(comm), ipc),
+              "fcx_krylov_create")
+        self.handle = h
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(ipc))
+            flat = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+            check(L.fcx_krylov_connect(h, flat), "fcx_krylov_connect")
+            nbr = [s for s, _, _ in partition.neighbours]
+            send_src = [np.asarray(snd, dtype=np.int32) for _, snd, _ in partition.neighbours]
+            send_dst = [np.asarray(pl, dtype=np.int32) for pl in partition.peer_local]
+            ptr = np.zeros(len(nbr) + 1, dtype=np.int32)
+            ptr[1:] = np.cumsum([a.size for a in send_src])
+            src = np.concatenate(send_src) if nbr else np.zeros(0, dtype=np.int32)
+            dst = np.concatenate(send_dst) if nbr else np.zeros(0, dtype=np.int32)
+            nbr_a = np.asarray(nbr, dtype=np.int32)
+            check(L.fcx_krylov_set_halo(h, len(nbr), nbr_a.ctypes.data, ptr.ctypes.data,
+                                        np.ascontiguousarray(src).ctypes.data, np.ascontiguousarray(dst).ctypes.data),
+                  "fcx_krylov_set_halo")
+            dist.barrier()  # every rank has opened every block before anyone stores into one
+        self._x = torch.empty(V.num_dofs, dtype=torch.float64, device=self.device)
+        self._status = (ctypes.c_double * 4)()
+
+    def _set_operator(self) -> None:
+        pb, L = self.problem, self.L
+        T = pb.tables
+        rec = pb.fused and pb._trec_valid and pb.use_tangent_records and L.fcx_tune(b"fem_variant", -1) != 0
+        tang = pb._trec if rec else pb.tangent.x.array
+        pos = pb._pos_ptr()
+        check(L.fcx_krylov_set_operator(
+            self.handle, 3 if rec else 1, pb.sdim, pb.num_cells, T.nq, T.nd, pb._dofmap.data_ptr(),
+            pb._dphi.data_ptr(), pb._weights.data_ptr(), pb._Jinv.data_ptr(), pb._detJ.data_ptr(), tang.data_ptr(),
+            pb._fe.data_ptr(), pos, pb._adj_ptr.data_ptr(), None if pos is not None else pb._adj_idx.data_ptr()),
+            "fcx_krylov_set_operator")
+
+    def solve(self, rhs, minv, rtol: float, max_it: int, check_every: int):
+        """Solve J x = rhs on the dofs where minv != 0.  Returns (x, iterations, converged, relres, breakdown);
+        x is this object's workspace, valid until the next solve."""
+        L, h = self.L, self.handle
+        check(L.fcx_set_device(self.device.index), "fcx_set_device")
+        stream = B.current_stream_ptr(self.device.index)
+        self._set_operator()
+        check(L.fcx_krylov_begin(h, rhs.data_ptr(), minv.data_ptr(), stream), "fcx_krylov_begin")
+        import torch
+
+        K = max(1, int(check_every))
+        it, ok, relres, brk = 0, False, 1.0, False
+        while it < max_it:
+            check(L.fcx_krylov_iterate(h, K, stream), "fcx_krylov_iterate")
+            it += K
+            torch.cuda.current_stream(self.device).synchronize()
+            check(L.fcx_krylov_status(h, self._status), "fcx_krylov_status")
+            _, rr, rr0, flag = (float(v) for v in self._status)
+            if rr0 == 0.0:
+                ok, relres = True, 0.0
+                break
+            relres = float(np.sqrt(max(rr, 0.0) / rr0))
+            if relres <= rtol:
+                ok = True
+                break
+            if flag != 0.0:
+                brk = True
+                break
+        check(L.fcx_krylov_solution(h, self._x.data_ptr(), stream), "fcx_krylov_solution")
+        return self._x, it, ok, relres, brk
+
+    def close(self) -> None:
+        if self.handle is not None:
+            self.L.fcx_krylov_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -68,6 +68,11 @@ class NewtonSolver:
         self.cg_eta_gamma = 0.9
         self.cg_max_it = 20000
         self.cg_check_every = 10  # host convergence checks (one sync each)
+        # "device": the whole Krylov loop runs from C (csrc/fcx_krylov.cu: single-reduction PCG, reduction and
+        # ghost exchange over peer memory inside the kernels; no NCCL, no Python per iteration).
+        # "python": two-reduction PCG issued kernel by kernel from here, NCCL all-reduces and send/recv.
+        self.cg_driver = "device"
+        self._device_krylov = None
         self.reduce_over_ranks = False  # sum norms/dots over torch.distributed ranks
         # solver/partitioned.py MeshPartition (set by MeshPartition.attach): norms and dot products run
         # over OWNED dofs, ghost values of p (before every Jacobian action) and of x (after every Newton
@@ -235,6 +240,28 @@ class NewtonSolver:
             raise KrylovError(msg)
         warnings.warn(msg, RuntimeWarning, stacklevel=3)
 
+    def _solve_cg_device(self, rhs, free_mask, diag, rtol=None):
+        """Jacobi-PCG through the device-resident Krylov loop (solver/_krylov.py)."""
+        import torch
+
+        from ._krylov import DeviceKrylov
+
+        own = self._owned(rhs)
+        fm = (free_mask if own is None else free_mask & own).to(torch.float64)
+        minv = fm / torch.where(diag.abs() > 0, diag, torch.ones_like(diag))
+        if self._device_krylov is None or self._device_krylov.problem is not self.problem:
+            self._device_krylov = DeviceKrylov(self.problem, self.partition)
+        tol = self.cg_rtol if rtol is None else rtol
+        x, it, ok, relres, brk = self._device_krylov.solve(rhs, minv, tol, self.cg_max_it, self.cg_check_every)
+        why = None
+        if brk:
+            why = ("breakdown: p.Ap <= 0 (operator not symmetric positive definite on the free dofs; "
+                   "use linear_solver='bicgstab' or 'dense')")
+        elif not ok:
+            why = f"no convergence in cg_max_it = {self.cg_max_it} iterations"
+        self._krylov_report(ok, relres, it, "cg (device)", why)
+        return x, it
+
     def _solve_bicgstab(self, apply, rhs, free_mask, diag, rtol=None):
         """Jacobi-preconditioned BiCGStab on the free (owned) dofs for NON-symmetric tangents
         (Drucker-Prager with non-associated flow).  Plain torch vector operations with one host
@@ -370,7 +397,12 @@ class NewtonSolver:
                     self.forcing_terms.append(eta)
                 elif self.cg_forcing is not None:
                     raise ValueError(f"unknown cg_forcing {self.cg_forcing!r}")
-                dx, kit = self._solve_cg(pb.J_apply, rhs, free, pb.J_diag(), eta)
+                if self.cg_driver == "device" and rhs.is_cuda:
+                    dx, kit = self._solve_cg_device(rhs, free, pb.J_diag(), eta)
+                elif self.cg_driver in ("device", "python"):
+                    dx, kit = self._solve_cg(pb.J_apply, rhs, free, pb.J_diag(), eta)
+                else:
+                    raise ValueError(f"unknown cg_driver {self.cg_driver!r}")
                 if self.profile:
                     torch.cuda.synchronize()
                     self.linear_solve_s += time.perf_counter() - t0

@@ -80,7 +80,9 @@ class MeshPartition:
         self.V = FunctionSpace.from_arrays(self.mesh, degree, Vg.node_coords[self.l2g],
                                            g2l[dm[cells]].astype(np.int32))
         # halo plan: (peer, local indices to send, local indices to receive), ascending global ids
-        self.neighbours = []
+        # peer_local[k] = the neighbour's LOCAL index of each node this rank sends to it (same order):
+        # what a peer-memory push needs to store a value straight into the neighbour's vector
+        self.neighbours, self.peer_local = [], []
         for s in range(world):
             if s == rank:
                 continue
@@ -89,6 +91,8 @@ class MeshPartition:
             recv = np.intersect1d(ghost, owned_s, assume_unique=True)
             if send.size or recv.size:
                 self.neighbours.append((s, g2l[send], g2l[recv]))
+                # local numbering of rank s = its owned nodes, then its ghosts, each ascending (as above)
+                self.peer_local.append(owned_s.size + np.searchsorted(ghost_s, send))
         self._dev_plan = {}
         self.block = g
 

@@ -283,6 +283,40 @@ int fcx_pcg_update_xr(size_t n, double *x, double *r, const double *p, const dou
 int fcx_pcg_update_p(size_t n, double *p, const double *r, const double *minv, const double *rz_new,
                      const double *rz, void *stream);
 
+/* Device-resident Krylov loop (csrc/fcx_krylov.cu): single-reduction (Chronopoulos-Gear) Jacobi-PCG for the
+ * linear solve of a Newton step -- in the reference PETSc's job behind dolfinx.nls.petsc.NewtonSolver, with
+ * the ghost exchange and the dot-product reductions of the MPI-partitioned mesh
+ * (reference solver/_solver.py:64-68, tests/solver/test_solver_mpi.py:93-121).  One process per GPU; the
+ * reduction (an all-gather of three partial sums, added in rank order on every rank) and the ghost update
+ * of the matvec input are peer-memory stores from inside the kernels over NVLink -- no NCCL, no host
+ * round trip per iteration.  Call order:
+ *   fcx_krylov_create    allocates the rank's vectors and its communication block; returns the block's
+ *                        CUDA IPC handle (64 bytes) for the other ranks
+ *   fcx_krylov_connect   handles of all ranks (world x 64 bytes, rank order)
+ *   fcx_krylov_set_halo  per neighbour: my local nodes to send and the neighbour's local index of each
+ *   fcx_krylov_set_operator  the Jacobian action: arguments of fcx_tangent_apply_rec (mode 3) or
+ *                        fcx_tangent_apply (mode 1) and the adjacency of fcx_gather_sum
+ *   fcx_krylov_begin     x = 0, r = rhs where minv != 0 (minv = inverse Jacobi diagonal, 0 on constrained
+ *                        AND ghost dofs), first ghost push
+ *   fcx_krylov_iterate   enqueue `iters` iterations (4 launches each, 3 on one rank); never synchronises
+ *   fcx_krylov_status    (after a stream synchronisation) out[0] iterations done, out[1] r.r at the start
+ *                        of the last one, out[2] r.r of the right-hand side, out[3] breakdown flag
+ *   fcx_krylov_solution  x_out <- x */
+int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, void **handle_out, void **comm_out,
+                      unsigned char *ipc_handle_out);
+int fcx_krylov_connect(void *handle, const unsigned char *ipc_handles);
+int fcx_krylov_set_halo(void *handle, int n_nbr, const int *nbr_rank, const int *send_ptr, const int *send_src,
+                        const int *send_dst);
+int fcx_krylov_set_operator(void *handle, int mode, int sdim, size_t ncells, int nq, int nd, const int *dofmap,
+                            const double *dphi_ref, const double *weights, const double *Jinv, const double *detJ,
+                            const double *tangent, double *fe, const int *fe_pos, const long long *adj_ptr,
+                            const int *adj_idx);
+int fcx_krylov_begin(void *handle, const double *rhs, const double *minv, void *stream);
+int fcx_krylov_iterate(void *handle, int iters, void *stream);
+int fcx_krylov_status(void *handle, double *out4);
+int fcx_krylov_solution(void *handle, double *x_out, void *stream);
+void fcx_krylov_destroy(void *handle);
+
 /* -------------------------------------------------------------------- host */
 
 int fcx_elastic_evaluate_host(int constraint, const double *D, size_t n,

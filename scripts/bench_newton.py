@@ -47,6 +47,10 @@ ap.add_argument("--forcing", choices=["none", "ew"], default="none",
 ap.add_argument("--newton-steps-only", type=int, default=0,
                 help="if > 0: stop each load step's CG after this many iterations (kernel timing runs)")
 ap.add_argument("--ab", action="store_true", help="also time the element kernels with fem_variant 0")
+ap.add_argument("--driver", choices=["device", "python"], default="device",
+                help="Krylov loop: device = csrc/fcx_krylov.cu (peer-memory reduction / ghost push, driven from C), "
+                     "python = kernel by kernel from Python with NCCL")
+ap.add_argument("--check-every", type=int, default=10)
 args = ap.parse_args()
 
 rank, local_rank, world = env_rank_world()
@@ -83,6 +87,8 @@ solver = S.NewtonSolver(None, problem)
 solver.linear_solver = "cg"
 solver.cg_rtol = args.cg_rtol
 solver.cg_forcing = "eisenstat-walker" if args.forcing == "ew" else None
+solver.cg_driver = args.driver
+solver.cg_check_every = args.check_every
 solver.reduce_over_ranks = world > 1
 if part is not None:
     part.attach(solver)
@@ -174,7 +180,7 @@ if rank == 0:
         "halo_neighbours": [(int(s), int(a.size), int(b.size)) for s, a, b in part.neighbours] if part is not None else [],
         "cells_per_gpu": problem.num_cells, "qps_per_gpu": nqp, "dofs_per_gpu": V.num_dofs,
         "degree": args.degree, "q_degree": qd, "load_steps": args.steps, "newton_iterations": newton_its,
-        "krylov_iterations": krylov, "cg_rtol": args.cg_rtol, "cg_forcing": args.forcing,
+        "krylov_iterations": krylov, "cg_rtol": args.cg_rtol, "cg_forcing": args.forcing, "cg_driver": args.driver,
  "fused_form": problem.fused,
         "setup_s": round(setup_s, 2), "solve_s": round(solve_s, 3),
         "linear_solve_s": round(solver.linear_solve_s, 3),

@@ -32,7 +32,7 @@ left = lambda x: np.isclose(x[0], 0.0)   # noqa: E731
 right = lambda x: np.isclose(x[0], 1.0)  # noqa: E731
 
 
-def run(V, part, steps, forcing):
+def run(V, part, steps, forcing, driver="device"):
     u = S.Function(V, dev)
     law = VonMises3D(synthetic.MISES_PARAMS)
     zero, ux = S.Constant(0.0), S.Constant(0.0)
@@ -43,6 +43,7 @@ def run(V, part, steps, forcing):
     solver.linear_solver = "cg"
     solver.cg_rtol = 1e-11
     solver.cg_forcing = forcing
+    solver.cg_driver = driver  # "device": peer-memory Krylov loop (csrc/fcx_krylov.cu); "python": NCCL from Python
     if part is not None:
         part.attach(solver)
     its = []
@@ -57,20 +58,20 @@ def run(V, part, steps, forcing):
 
 for degree, n in ((2, (12, 5, 4)), (1, (16, 6, 5))):
     mesh = S.create_unit_cube(*n)
-    for forcing in (None, "eisenstat-walker"):
+    for forcing, driver in ((None, "device"), ("eisenstat-walker", "device"), (None, "python")):
         part = S.MeshPartition(mesh, degree, rank, world)
-        u, problem, its = run(part.V, part, 2, forcing)
+        u, problem, its = run(part.V, part, 2, forcing, driver)
         glob = part.gather_global(u.x.array.cpu().numpy())
         sig_local = problem.stress_0.x.array.cpu().numpy().reshape(part.local_cells.size, -1)
         if rank == 0:
             Vg = S.functionspace(mesh, ("CG", degree, (3,)))
-            ug, pg, its_g = run(Vg, None, 2, forcing)
+            ug, pg, its_g = run(Vg, None, 2, forcing, driver)
             ref = ug.x.array.cpu().numpy()
             err = np.abs(glob - ref).max() / np.abs(ref).max()
             sig_g = pg.stress_0.x.array.cpu().numpy().reshape(mesh.num_cells, -1)[part.local_cells]
             serr = np.abs(sig_local - sig_g).max() / np.abs(sig_g).max()
             plastic = float((pg._history_0[0]["alpha"].x.array > 0).double().mean().item())
-            print(f"degree {degree} mesh {n} world {world} forcing {forcing}: |u - u_1gpu|/|u| = {err:.2e}, "
+            print(f"degree {degree} mesh {n} world {world} forcing {forcing} driver {driver}: |u - u_1gpu|/|u| = {err:.2e}, "
                   f"stress (rank 0 cells incl. ghosts) {serr:.2e}, newton/krylov its {its} vs 1 GPU {its_g}, "
                   f"plastic {plastic:.2f}, owned cells {part.num_owned_cells}/{mesh.num_cells}, "
                   f"neighbours {[(s, a.size, b.size) for s, a, b in part.neighbours]}", flush=True)

@@ -130,8 +130,8 @@ def test_gpu_gather_feeds_evaluate():
 @pytest.mark.parametrize("with_prev", [True, False])
 def test_gpu_gather_staged_kernel_bitwise(gdim, degree, qdeg, ncells, with_prev):
     """gather_staged_kernel (nodal values staged by cp.async one tile ahead, fcx_tune
-    "gather_variant" 1) and gather_cell_kernel (thread per cell, table in the constant bank, variant 2,
-    the default for 3-D 4-point rules) run the same fma chains as gather_kernel: bit-identical
+    "gather_variant" 1, the default) and gather_cell_kernel (thread per cell, table in the constant bank,
+    variant 2, 3-D 4-point rules; measured slower, kept as an option) run the same fma chains as gather_kernel: bit-identical
     output, ragged tails and many tiles per CTA included; and both match the oracle."""
     import torch
 

@@ -601,3 +601,55 @@ def test_partition_hooks_single_rank():
     assert np.abs(sols[0][0] - sols[1][0]).max() <= 1e-9 * np.abs(sols[0][0]).max()
     assert rel_err(sols[1][2], sols[0][2], 6) <= 1e-8
     assert float(np.abs(sols[0][2]).max()) > 1200.0  # the second step went plastic
+
+
+@pytest.mark.parametrize("forcing", [None, "eisenstat-walker"])
+def test_device_krylov_driver_equals_python_driver(forcing):
+    """The device-resident Krylov loop (csrc/fcx_krylov.cu: single-reduction PCG driven from C) against the
+    kernel-by-kernel two-reduction PCG issued from Python: same Newton iteration counts, same displacement
+    and stresses to the Krylov tolerance, Mises plasticity across the yield point on a P2 mesh (CG path:
+    more than 3000 dofs).  Also: every linear solve reports convergence."""
+    sols = []
+    for driver in ("device", "python"):
+        mesh = S.create_unit_cube(7, 6, 5)
+        V = S.functionspace(mesh, ("CG", 2, (3,)))
+        u = S.Function(V)
+        ux = S.Constant(mesh, 0.0)
+        bcs = [S.dirichletbc(S.Constant(mesh, 0.0), S.locate_dofs_geometrical(V, left), V),
+               S.dirichletbc(ux, S.locate_dofs_geometrical(V, right), V.sub(0))]
+        pb = S.IncrSmallStrainProblem(VonMises3D(MISES), u, bcs, 2)
+        solver = S.NewtonSolver(None, pb)
+        solver.linear_solver = "cg"
+        solver.cg_driver = driver
+        solver.cg_rtol = 1e-11
+        solver.cg_forcing = forcing
+        its = []
+        for step in (1, 2):
+            ux.value = 0.006 * step
+            k, ok = solver.solve(u)
+            assert ok and all(solver.krylov_converged)
+            its.append(k)
+            pb.update()
+        sols.append((its, np_(u.x.array).copy(), np_(pb.stress_0.x.array).copy(),
+                     float((pb._history_0[0]["alpha"].x.array > 0).double().mean().item())))
+    (ia, ua, sa, pa), (ib, ub, sb, _) = sols
+    assert ia == ib
+    assert 0.05 < pa < 1.0
+    assert np.abs(ua - ub).max() <= 1e-8 * np.abs(ub).max()
+    assert np.abs(sa - sb).max() <= 1e-6 * np.abs(sb).max()
+
+
+def test_device_krylov_reports_breakdown_on_indefinite_operator():
+    """p.Ap <= 0 is reported (KrylovError), not iterated on silently: a sign-flipped tangent."""
+    mesh = S.create_unit_cube(6, 6, 5)
+    V = S.functionspace(mesh, ("CG", 2, (3,)))
+    u = S.Function(V)
+    bcs = [S.dirichletbc(S.Constant(mesh, 0.0), S.locate_dofs_geometrical(V, left), V),
+           S.dirichletbc(S.Constant(mesh, 0.01), S.locate_dofs_geometrical(V, right), V.sub(0))]
+    law = LinearElasticityModel({"E": E, "nu": NU}, C.FULL)
+    law.D = -law.D
+    pb = S.IncrSmallStrainProblem(law, u, bcs, 2)
+    solver = S.NewtonSolver(None, pb)
+    solver.linear_solver = "cg"
+    with pytest.raises(S.KrylovError):
+        solver.solve(u)
