@@ -46,17 +46,19 @@ constexpr int KR_MAX_WORLD = 16;
 constexpr int KR_HIST = 1 << 16;  // residual history entries (ring)
 
 // One rank's communication block (a single cudaMalloc, exported through an IPC handle):
-//   [ u vector: n doubles, padded to 256 B | red[2][W][4] doubles | redflag[2][W] u64 | haloflag[W] u64 ]
+//   [ red[2][W][4] doubles | redflag[2][W] u64 | haloflag[W] u64 | pad to 256 B | u vector: n doubles ]
+// The control part comes FIRST: its offsets depend on the world size only, so they are the same in
+// every rank's block although the ranks hold different numbers of dofs.
 struct CommLayout {
-    size_t n_pad, off_red, off_redflag, off_haloflag, bytes;
-    __host__ __device__ CommLayout() : n_pad(0), off_red(0), off_redflag(0), off_haloflag(0), bytes(0) {}
+    size_t off_red, off_redflag, off_haloflag, off_u, bytes;
+    __host__ __device__ CommLayout() : off_red(0), off_redflag(0), off_haloflag(0), off_u(0), bytes(0) {}
     __host__ CommLayout(size_t n, int world)
     {
-        n_pad = (n * sizeof(double) + 255) & ~(size_t)255;
-        off_red = n_pad;
+        off_red = 0;
         off_redflag = off_red + sizeof(double) * 2 * world * 4;
         off_haloflag = off_redflag + sizeof(unsigned long long) * 2 * world;
-        bytes = (off_haloflag + sizeof(unsigned long long) * world + 255) & ~(size_t)255;
+        off_u = (off_haloflag + sizeof(unsigned long long) * world + 255) & ~(size_t)255;
+        bytes = (off_u + n * sizeof(double) + 255) & ~(size_t)255;
     }
 };
 
@@ -71,12 +73,13 @@ struct Krylov {
     char *comm = nullptr;  // own comm block
     PeerPtrs peers{};
     bool peer_open[KR_MAX_WORLD] = {};
-    // vectors (own allocations); u lives at the head of the comm block
+    // vectors (own allocations); u lives in the comm block (peers store its ghost values)
     double *x = nullptr, *r = nullptr, *w = nullptr, *p = nullptr, *s = nullptr, *minv = nullptr;
     double *partials = nullptr;          // [3][grid]
     unsigned *ticket = nullptr;          // [2]: K2 reduction, K4 completion
     double *state = nullptr;             // [2][4]: gamma, alpha, rr, breakdown flag per parity
     double *hist = nullptr;              // [KR_HIST]: r.r at the start of iteration it
+    int *err = nullptr;                  // sticky: 1 = a peer's flag never arrived (bounded spin timed out)
     // halo plan (device): flattened send entries over all neighbours
     int n_nbr = 0, n_send = 0;
     int nbr_rank[KR_MAX_WORLD] = {};
@@ -104,6 +107,18 @@ __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *
 __device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Bounded spin on a flag (until it is >= want, or == want if `exact`): a peer that never arrives must not
+// hang the GPU.  ~2^24 polls of a system-scope load are several seconds; on time-out the sticky error word
+// is set and the kernel carries on with whatever it has (the host raises after the block).
+__device__ __forceinline__ void wait_flag(const unsigned long long *p, unsigned long long want, bool exact, int *err)
+{
+    for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+        const unsigned long long v = ld_flag(p);
+        if (exact ? v == want : v >= want)
+            return;
+    }
+    atomicExch(err, 1);
 }
 __device__ __forceinline__ double ld_volatile(const double *p)
 {
@@ -236,7 +251,8 @@ __global__ void __launch_bounds__(KR_THREADS)
     cg_update_kernel(size_t n, double *__restrict__ x, double *__restrict__ r, double *__restrict__ u,
                      const double *__restrict__ w, double *__restrict__ p, double *__restrict__ s,
                      const double *__restrict__ minv, char *comm, CommLayout lay, int world,
-                     unsigned long long epoch, int first, double *state, double *hist, unsigned long long it)
+                     unsigned long long epoch, int first, double *state, double *hist, unsigned long long it,
+                     int *err)
 {
     __shared__ double sc[2];
     if (threadIdx.x == 0) {
@@ -246,8 +262,7 @@ __global__ void __launch_bounds__(KR_THREADS)
         const double *red = reinterpret_cast<const double *>(comm + lay.off_red) + (size_t)par * world * 4;
         double g = 0.0, d = 0.0, q = 0.0;
         for (int t = 0; t < world; ++t) {
-            while (ld_flag(flags + t) != epoch) {
-            }
+            wait_flag(flags + t, epoch, true, err);
             g += ld_volatile(red + t * 4 + 0);
             d += ld_volatile(red + t * 4 + 1);
             q += ld_volatile(red + t * 4 + 2);
@@ -314,12 +329,12 @@ __global__ void __launch_bounds__(KR_THREADS)
     halo_push_kernel(const double *__restrict__ u, const int *__restrict__ send_src, const int *__restrict__ send_dst,
                      const int *__restrict__ send_nbr, int n_send, PeerPtrs nbr_base, CommLayout lay, int n_nbr,
                      int rank, char *comm, const int *__restrict__ nbr_rank_dev, unsigned *ticket,
-                     unsigned long long epoch)
+                     unsigned long long epoch, int *err)
 {
     __shared__ bool last;
     const int stride = gridDim.x * blockDim.x;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_send; e += stride) {
-        double *dst = reinterpret_cast<double *>(nbr_base.base[send_nbr[e]]) + (size_t)send_dst[e] * G;
+        double *dst = reinterpret_cast<double *>(nbr_base.base[send_nbr[e]] + lay.off_u) + (size_t)send_dst[e] * G;
         const double *src = u + (size_t)send_src[e] * G;
 #pragma unroll
         for (int j = 0; j < G; ++j)
@@ -336,8 +351,7 @@ __global__ void __launch_bounds__(KR_THREADS)
             st_flag(reinterpret_cast<unsigned long long *>(nbr_base.base[k] + lay.off_haloflag) + rank, epoch);
         const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(comm + lay.off_haloflag);
         for (int k = 0; k < n_nbr; ++k)
-            while (ld_flag(mine + nbr_rank_dev[k]) < epoch) {
-            }
+            wait_flag(mine + nbr_rank_dev[k], epoch, false, err);
         *ticket = 0;
     }
 }
@@ -357,12 +371,13 @@ static int kr_push(Krylov *K, cudaStream_t st)
     for (int k = 0; k < K->n_nbr; ++k)
         nb.base[k] = K->peers.base[K->nbr_rank[k]];
     const unsigned grid = kr_grid(K->n_send > 0 ? (size_t)K->n_send : 1);
-    double *u = reinterpret_cast<double *>(K->comm);
+    double *u = reinterpret_cast<double *>(K->comm + K->lay.off_u);
     // nbr ranks on the device: kept right behind the send plan
     const int *nbr_rank_dev = K->send_nbr + K->n_send;
 #define FCX_PUSH(G) \
     halo_push_kernel<G><<<grid, KR_THREADS, 0, st>>>(u, K->send_src, K->send_dst, K->send_nbr, K->n_send, nb, K->lay, \
-                                                     K->n_nbr, K->rank, K->comm, nbr_rank_dev, K->ticket + 1, K->epoch)
+                                                     K->n_nbr, K->rank, K->comm, nbr_rank_dev, K->ticket + 1, K->epoch, \
+                                                     K->err)
     if (K->gdim == 1)
         FCX_PUSH(1);
     else if (K->gdim == 2)
@@ -414,6 +429,10 @@ int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, void **handl
         e = cudaMemset(K->state, 0, sizeof(double) * 8);
     if (e == cudaSuccess)
         e = cudaMalloc((void **)&K->hist, sizeof(double) * KR_HIST);
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&K->err, sizeof(int));
+    if (e == cudaSuccess)
+        e = cudaMemset(K->err, 0, sizeof(int));
     if (e == cudaSuccess) {
         cudaIpcMemHandle_t h;
         memset(&h, 0, sizeof h);
@@ -529,7 +548,7 @@ int fcx_krylov_begin(void *handle, const double *rhs, const double *minv, void *
     if (!K || !rhs || !minv)
         return FCX_ERR_NULL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    double *u = reinterpret_cast<double *>(K->comm);
+    double *u = reinterpret_cast<double *>(K->comm + K->lay.off_u);
     kr_begin_kernel<<<kr_grid(K->n), KR_THREADS, 0, st>>>(K->n, rhs, minv, K->minv, K->x, K->r, u, K->p, K->s);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
@@ -549,7 +568,7 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
     if (K->op_mode == 0)
         return FCX_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    double *u = reinterpret_cast<double *>(K->comm);
+    double *u = reinterpret_cast<double *>(K->comm + K->lay.off_u);
     const unsigned ggrid = kr_grid(K->nnodes);
     for (int k = 0; k < iters; ++k) {
         int rc = K->op_mode == 3
@@ -571,7 +590,8 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
             FCX_GSUM(3);
 #undef FCX_GSUM
         cg_update_kernel<<<K->grid, KR_THREADS, 0, st>>>(K->n, K->x, K->r, u, K->w, K->p, K->s, K->minv, K->comm, K->lay,
-                                                         K->world, K->epoch, K->it == 0 ? 1 : 0, K->state, K->hist, K->it);
+                                                         K->world, K->epoch, K->it == 0 ? 1 : 0, K->state, K->hist, K->it,
+                                                         K->err);
         g_launches.fetch_add(2, std::memory_order_relaxed);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess)
@@ -605,6 +625,11 @@ int fcx_krylov_status(void *handle, double *out4)
         e = cudaMemcpy(st, K->state + (size_t)par * 4, sizeof st, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess)
         out4[3] = st[3];
+    int err = 0;
+    if (e == cudaSuccess)
+        e = cudaMemcpy(&err, K->err, sizeof err, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && err != 0)
+        out4[3] = 2.0;  // a peer never arrived
     return note_cuda_error(e, "fcx_krylov_status");
 }
 
@@ -628,7 +653,7 @@ void fcx_krylov_destroy(void *handle)
     for (int t = 0; t < K->world; ++t)
         if (K->peer_open[t])
             cudaIpcCloseMemHandle(K->peers.base[t]);
-    void *ptrs[] = {K->comm, K->x, K->r, K->w, K->p, K->s, K->minv, K->partials, K->ticket, K->state, K->hist,
+    void *ptrs[] = {K->comm, K->x, K->r, K->w, K->p, K->s, K->minv, K->partials, K->ticket, K->state, K->hist, K->err,
                     K->send_src, K->send_dst, K->send_nbr};
     for (void *q : ptrs)
         if (q)

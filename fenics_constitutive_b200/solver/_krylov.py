@@ -86,6 +86,8 @@ class DeviceKrylov:
             torch.cuda.current_stream(self.device).synchronize()
             check(L.fcx_krylov_status(h, self._status), "fcx_krylov_status")
             _, rr, rr0, flag = (float(v) for v in self._status)
+            if flag == 2.0:
+                raise RuntimeError("device Krylov loop: a peer rank never arrived (peer-memory flag timed out)")
             if rr0 == 0.0:
                 ok, relres = True, 0.0
                 break

@@ -300,7 +300,8 @@ int fcx_pcg_update_p(size_t n, double *p, const double *r, const double *minv, c
  *                        AND ghost dofs), first ghost push
  *   fcx_krylov_iterate   enqueue `iters` iterations (4 launches each, 3 on one rank); never synchronises
  *   fcx_krylov_status    (after a stream synchronisation) out[0] iterations done, out[1] r.r at the start
- *                        of the last one, out[2] r.r of the right-hand side, out[3] breakdown flag
+ *                        of the last one, out[2] r.r of the right-hand side, out[3] 1 = breakdown (p.Ap <= 0),
+ *                        2 = a peer rank never arrived (bounded spin timed out)
  *   fcx_krylov_solution  x_out <- x */
 int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, void **handle_out, void **comm_out,
                       unsigned char *ipc_handle_out);
