@@ -51,7 +51,7 @@ SIGNATURES = {
     "fcx_pcg_pap": (_ci, [_sz, _dp, _dp, _dp, _dp, _vp, _dp, _vp]),
     "fcx_pcg_update_xr": (_ci, [_sz, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _dp, _vp]),
     "fcx_pcg_update_p": (_ci, [_sz, _dp, _dp, _dp, _dp, _dp, _vp]),
-    "fcx_krylov_create": (_ci, [_ci, _ci, _ci, _sz, _vp, _vp, _vp]),
+    "fcx_krylov_create": (_ci, [_ci, _ci, _ci, _sz, _sz, _vp, _vp, _vp]),
     "fcx_krylov_connect": (_ci, [_vp, _vp]),
     "fcx_krylov_set_halo": (_ci, [_vp, _ci, _vp, _vp, _vp, _vp]),
     "fcx_krylov_set_operator": (_ci, [_vp, _ci, _ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp, _vp]),

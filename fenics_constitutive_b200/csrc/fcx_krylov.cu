@@ -68,7 +68,7 @@ struct PeerPtrs {
 
 struct Krylov {
     int rank = 0, world = 1, gdim = 3;
-    size_t n = 0, nnodes = 0;
+    size_t n = 0, nnodes = 0, n_owned = 0;  // dofs, nodes, owned dofs (the first n_owned)
     CommLayout lay;
     char *comm = nullptr;  // own comm block
     PeerPtrs peers{};
@@ -146,9 +146,11 @@ __device__ __forceinline__ double kr_block_sum(double v, double *sh)
     return t;  // valid in thread 0
 }
 
-// x = 0, r = rhs on free owned dofs (minv != 0) else 0, u = minv r, p = s = 0
+// x = 0, r = rhs on free owned dofs (minv != 0) else 0, u = minv r, p = s = 0.
+// u is written on OWNED dofs only (the first n_owned): the ghost entries belong to the neighbours, whose
+// peer stores may land before this kernel runs.
 __global__ void __launch_bounds__(KR_THREADS)
-    kr_begin_kernel(size_t n, const double *__restrict__ rhs, const double *__restrict__ minv_in,
+    kr_begin_kernel(size_t n, size_t n_owned, const double *__restrict__ rhs, const double *__restrict__ minv_in,
                     double *__restrict__ minv, double *__restrict__ x, double *__restrict__ r,
                     double *__restrict__ u, double *__restrict__ p, double *__restrict__ s)
 {
@@ -159,7 +161,8 @@ __global__ void __launch_bounds__(KR_THREADS)
         minv[i] = m;
         x[i] = 0.0;
         r[i] = rv;
-        u[i] = m * rv;
+        if (i < n_owned)
+            u[i] = m * rv;
         p[i] = 0.0;
         s[i] = 0.0;
     }
@@ -246,9 +249,10 @@ __global__ void __launch_bounds__(KR_THREADS)
     }
 }
 
-// K3: finish the reduction (rank order), alpha / beta, fused vector update.
+// K3: finish the reduction (rank order), alpha / beta, fused vector update.  u is written on OWNED dofs
+// only: a faster neighbour may already have stored this iteration's ghost values.
 __global__ void __launch_bounds__(KR_THREADS)
-    cg_update_kernel(size_t n, double *__restrict__ x, double *__restrict__ r, double *__restrict__ u,
+    cg_update_kernel(size_t n, size_t n_owned, double *__restrict__ x, double *__restrict__ r, double *__restrict__ u,
                      const double *__restrict__ w, double *__restrict__ p, double *__restrict__ s,
                      const double *__restrict__ minv, char *comm, CommLayout lay, int world,
                      unsigned long long epoch, int first, double *state, double *hist, unsigned long long it,
@@ -312,13 +316,18 @@ __global__ void __launch_bounds__(KR_THREADS)
         s2[i] = sv;
         x2[i] = xv;
         r2[i] = rv;
-        u2[i] = un;
+        if (2 * i + 1 < n_owned) {
+            u2[i] = un;
+        } else if (2 * i < n_owned) {
+            u[2 * i] = un.x;
+        }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const size_t i = n - 1;
         double un;
         one(minv[i], u[i], w[i], p[i], s[i], x[i], r[i], un);
-        u[i] = un;
+        if (i < n_owned)
+            u[i] = un;
     }
 }
 
@@ -395,12 +404,13 @@ using namespace fcx;
 
 extern "C" {
 
-int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, void **handle_out, void **comm_out,
-                      unsigned char *ipc_handle_out /* 64 bytes */)
+int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, size_t nnodes_owned, void **handle_out,
+                      void **comm_out, unsigned char *ipc_handle_out /* 64 bytes */)
 {
     if (!handle_out || !comm_out || !ipc_handle_out)
         return FCX_ERR_NULL;
-    if (world < 1 || world > KR_MAX_WORLD || rank < 0 || rank >= world || gdim < 1 || gdim > 3 || nnodes == 0)
+    if (world < 1 || world > KR_MAX_WORLD || rank < 0 || rank >= world || gdim < 1 || gdim > 3 || nnodes == 0 ||
+        nnodes_owned > nnodes)
         return FCX_ERR_ARG;
     Krylov *K = new Krylov();
     K->rank = rank;
@@ -408,6 +418,7 @@ int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, void **handl
     K->gdim = gdim;
     K->nnodes = nnodes;
     K->n = nnodes * (size_t)gdim;
+    K->n_owned = nnodes_owned * (size_t)gdim;
     K->lay = CommLayout(K->n, world);
     K->grid = kr_grid(K->n / 2 + 1);
     cudaError_t e = cudaMalloc((void **)&K->comm, K->lay.bytes);
@@ -549,7 +560,7 @@ int fcx_krylov_begin(void *handle, const double *rhs, const double *minv, void *
         return FCX_ERR_NULL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *u = reinterpret_cast<double *>(K->comm + K->lay.off_u);
-    kr_begin_kernel<<<kr_grid(K->n), KR_THREADS, 0, st>>>(K->n, rhs, minv, K->minv, K->x, K->r, u, K->p, K->s);
+    kr_begin_kernel<<<kr_grid(K->n), KR_THREADS, 0, st>>>(K->n, K->n_owned, rhs, minv, K->minv, K->x, K->r, u, K->p, K->s);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
@@ -589,7 +600,7 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
         else
             FCX_GSUM(3);
 #undef FCX_GSUM
-        cg_update_kernel<<<K->grid, KR_THREADS, 0, st>>>(K->n, K->x, K->r, u, K->w, K->p, K->s, K->minv, K->comm, K->lay,
+        cg_update_kernel<<<K->grid, KR_THREADS, 0, st>>>(K->n, K->n_owned, K->x, K->r, u, K->w, K->p, K->s, K->minv, K->comm, K->lay,
                                                          K->world, K->epoch, K->it == 0 ? 1 : 0, K->state, K->hist, K->it,
                                                          K->err);
         g_launches.fetch_add(2, std::memory_order_relaxed);

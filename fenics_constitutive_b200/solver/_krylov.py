@@ -33,8 +33,9 @@ class DeviceKrylov:
         V = problem.V
         h, comm = ctypes.c_void_p(), ctypes.c_void_p()
         ipc = (ctypes.c_ubyte * 64)()
-        check(L.fcx_krylov_create(rank, world, problem.gdim, V.num_nodes, ctypes.byref(h), ctypes.byref(comm), ipc),
-              "fcx_krylov_create")
+        owned = partition.num_owned_nodes if partition is not None else V.num_nodes
+        check(L.fcx_krylov_create(rank, world, problem.gdim, V.num_nodes, owned, ctypes.byref(h), ctypes.byref(comm),
+                                  ipc), "fcx_krylov_create")
         self.handle = h
         if world > 1:
             handles = [None] * world

@@ -291,7 +291,9 @@ int fcx_pcg_update_p(size_t n, double *p, const double *r, const double *minv, c
  * of the matvec input are peer-memory stores from inside the kernels over NVLink -- no NCCL, no host
  * round trip per iteration.  Call order:
  *   fcx_krylov_create    allocates the rank's vectors and its communication block; returns the block's
- *                        CUDA IPC handle (64 bytes) for the other ranks
+ *                        CUDA IPC handle (64 bytes) for the other ranks.  Local numbering: the nnodes_owned
+ *                        owned nodes first, then the ghosts (ghost entries of the matvec input are written by
+ *                        their owners only)
  *   fcx_krylov_connect   handles of all ranks (world x 64 bytes, rank order)
  *   fcx_krylov_set_halo  per neighbour: my local nodes to send and the neighbour's local index of each
  *   fcx_krylov_set_operator  the Jacobian action: arguments of fcx_tangent_apply_rec (mode 3) or
@@ -303,8 +305,8 @@ int fcx_pcg_update_p(size_t n, double *p, const double *r, const double *minv, c
  *                        of the last one, out[2] r.r of the right-hand side, out[3] 1 = breakdown (p.Ap <= 0),
  *                        2 = a peer rank never arrived (bounded spin timed out)
  *   fcx_krylov_solution  x_out <- x */
-int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, void **handle_out, void **comm_out,
-                      unsigned char *ipc_handle_out);
+int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, size_t nnodes_owned, void **handle_out,
+                      void **comm_out, unsigned char *ipc_handle_out);
 int fcx_krylov_connect(void *handle, const unsigned char *ipc_handles);
 int fcx_krylov_set_halo(void *handle, int n_nbr, const int *nbr_rank, const int *send_ptr, const int *send_src,
                         const int *send_dst);
