@@ -11,17 +11,20 @@
 // two GPUs against 0.18 ms of kernels.  Here one iteration is
 //     K1  element kernel        fe = B^T C B u_e             (fcx_tangent_apply[_rec], unchanged)
 //     K2  gsum_dots_kernel      w = sum fe (node-wise, fixed order);  partial (r.u, w.u, r.r) over
-//                               owned free dofs; the last CTA adds the CTA partials in index order
-//                               and STORES the three sums into every rank's reduction slot
-//     K3  cg_update_kernel      waits for all ranks' slots, adds them in RANK order (every rank gets
-//                               the same bits), alpha / beta, then  p = u + beta p;  s = w + beta s;
-//                               x += alpha p;  r -= alpha s;  u = minv r
-//     K4  halo_push_kernel      u of the nodes that are ghosts elsewhere is stored straight into the
-//                               neighbours' vectors; a system-scope flag tells them; then waits for
-//                               the neighbours' flags (so K1 of the next iteration reads fresh ghosts)
+//                               owned free dofs; the last CTA adds the CTA partials in index order,
+//                               STORES the three sums into every rank's reduction slot, waits for
+//                               the other ranks' sums and adds them in RANK order (every rank gets
+//                               the same bits): alpha / beta
+//     K3  cg_update_kernel      p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;
+//                               u = minv r;  then the last CTA stores u of the nodes that are ghosts
+//                               elsewhere straight into the neighbours' vectors, raises a system-scope
+//                               flag and waits for the neighbours' flags (so K1 of the next iteration
+//                               reads fresh ghosts)
+// (the standalone halo_push_kernel does the same push at the start of a solve and for
+// fcx_krylov_halo_update)
 // with  gamma = r.u, delta = w.u:  beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)
 // -- ONE reduction per iteration instead of two, one fused vector pass instead of three kernels.
-// fcx_krylov_iterate enqueues a block of iterations from C; the host looks at the residual history
+// Three launches per iteration; fcx_krylov_iterate enqueues a block of iterations from C; the host looks at the residual history
 // once per block.  One process per GPU: peers' buffers come from CUDA IPC handles.
 //
 // Ordering between ranks: a reduction slot / flag pair is double-buffered by iteration parity; a rank
@@ -78,6 +81,7 @@ struct Krylov {
     double *partials = nullptr;          // [3][grid]
     unsigned *ticket = nullptr;          // [2]: K2 reduction, K4 completion
     double *state = nullptr;             // [2][4]: gamma, alpha, rr, breakdown flag per parity
+    double *scal = nullptr;              // [2]: alpha, beta of the iteration in flight (K2 -> K3)
     double *hist = nullptr;              // [KR_HIST]: r.r at the start of iteration it
     int *err = nullptr;                  // sticky: 1 = a peer's flag never arrived (bounded spin timed out)
     // halo plan (device): flattened send entries over all neighbours
@@ -176,7 +180,8 @@ __global__ void __launch_bounds__(KR_THREADS)
                      const double *__restrict__ fe, const double *__restrict__ r, const double *__restrict__ u,
                      const double *__restrict__ minv, double *__restrict__ w, unsigned long long nnodes,
                      double *partials, unsigned *ticket, PeerPtrs peers, CommLayout lay, int rank, int world,
-                     unsigned long long epoch)
+                     unsigned long long epoch, int first, double *state, double *scal, double *hist,
+                     unsigned long long it, int *err)
 {
     __shared__ double sh[KR_THREADS / 32];
     __shared__ bool last;
@@ -245,54 +250,55 @@ __global__ void __launch_bounds__(KR_THREADS)
                 reinterpret_cast<unsigned long long *>(peers.base[t] + lay.off_redflag) + (size_t)par * world + rank;
             st_flag(flag, epoch);
         }
+        // ... and finish the reduction right here, in this ONE thread: wait for every rank's sums, add them
+        // in rank order (every rank gets the same bits), alpha / beta for the update kernel that follows in
+        // stream order (1184 CTAs polling a system-scope flag there cost more than the exchange itself)
+        const unsigned long long *flags =
+            reinterpret_cast<const unsigned long long *>(peers.base[rank] + lay.off_redflag) + (size_t)par * world;
+        const double *red = reinterpret_cast<const double *>(peers.base[rank] + lay.off_red) + (size_t)par * world * 4;
+        double gs = 0.0, ds = 0.0, qs = 0.0;
+        for (int t = 0; t < world; ++t) {
+            wait_flag(flags + t, epoch, true, err);
+            gs += ld_volatile(red + t * 4 + 0);
+            ds += ld_volatile(red + t * 4 + 1);
+            qs += ld_volatile(red + t * 4 + 2);
+        }
+        const double *prev = state + (size_t)(par ^ 1) * 4;  // written by the previous iteration's launch
+        double beta = 0.0, den = ds;
+        if (!first) {
+            beta = prev[0] > 0.0 ? gs / prev[0] : 0.0;
+            den = prev[1] != 0.0 ? ds - beta * gs / prev[1] : ds;
+        }
+        // den <= 0: the operator is not positive definite on the free dofs (or the solve has converged to
+        // round-off): stop moving and flag it; the host decides
+        const double alpha = den > 0.0 ? gs / den : 0.0;
+        scal[0] = alpha;
+        scal[1] = beta;
+        double *cur = state + (size_t)par * 4;
+        cur[0] = gs;
+        cur[1] = alpha;
+        cur[2] = qs;
+        cur[3] = den > 0.0 ? (first ? 0.0 : prev[3]) : 1.0;  // sticky breakdown flag of this solve
+        hist[it % KR_HIST] = qs;
         *ticket = 0;
     }
 }
 
-// K3: finish the reduction (rank order), alpha / beta, fused vector update.  u is written on OWNED dofs
-// only: a faster neighbour may already have stored this iteration's ghost values.
+// K3: fused vector update with the alpha / beta K2 left in `scal`, then -- by the last CTA to finish -- the
+// ghost push of the new matvec input: owned values that are ghosts elsewhere are stored straight into the
+// neighbours' vectors, a system-scope flag tells them, and the CTA waits for the neighbours' flags of the same
+// epoch (so K1 of the next iteration reads fresh ghosts).  u is written on OWNED dofs only: a faster neighbour
+// may already have stored this iteration's ghost values.
 __global__ void __launch_bounds__(KR_THREADS)
     cg_update_kernel(size_t n, size_t n_owned, double *__restrict__ x, double *__restrict__ r, double *__restrict__ u,
                      const double *__restrict__ w, double *__restrict__ p, double *__restrict__ s,
-                     const double *__restrict__ minv, char *comm, CommLayout lay, int world,
-                     unsigned long long epoch, int first, double *state, double *hist, unsigned long long it,
-                     int *err)
+                     const double *__restrict__ minv, const double *__restrict__ scal, int gdim,
+                     const int *__restrict__ send_src, const int *__restrict__ send_dst,
+                     const int *__restrict__ send_nbr, int n_send, PeerPtrs nbr_base, CommLayout lay, int n_nbr,
+                     int rank, char *comm, const int *__restrict__ nbr_rank_dev, unsigned *ticket,
+                     unsigned long long epoch, int *err)
 {
-    __shared__ double sc[2];
-    if (threadIdx.x == 0) {
-        const int par = (int)(epoch & 1ULL);
-        const unsigned long long *flags =
-            reinterpret_cast<const unsigned long long *>(comm + lay.off_redflag) + (size_t)par * world;
-        const double *red = reinterpret_cast<const double *>(comm + lay.off_red) + (size_t)par * world * 4;
-        double g = 0.0, d = 0.0, q = 0.0;
-        for (int t = 0; t < world; ++t) {
-            wait_flag(flags + t, epoch, true, err);
-            g += ld_volatile(red + t * 4 + 0);
-            d += ld_volatile(red + t * 4 + 1);
-            q += ld_volatile(red + t * 4 + 2);
-        }
-        const double *prev = state + (size_t)(par ^ 1) * 4;  // written by the previous iteration's launch
-        double beta = 0.0, den = d;
-        if (!first) {
-            beta = prev[0] > 0.0 ? g / prev[0] : 0.0;
-            den = prev[1] != 0.0 ? d - beta * g / prev[1] : d;
-        }
-        // den <= 0: the operator is not positive definite on the free dofs (or the solve has converged to
-        // round-off): stop moving and flag it; the host decides
-        const double alpha = den > 0.0 ? g / den : 0.0;
-        sc[0] = alpha;
-        sc[1] = beta;
-        if (blockIdx.x == 0) {
-            double *cur = state + (size_t)par * 4;
-            cur[0] = g;
-            cur[1] = alpha;
-            cur[2] = q;
-            cur[3] = den > 0.0 ? (first ? 0.0 : prev[3]) : 1.0;  // sticky breakdown flag of this solve
-            hist[it % KR_HIST] = q;
-        }
-    }
-    __syncthreads();
-    const double alpha = sc[0], beta = sc[1];
+    const double alpha = scal[0], beta = scal[1];
     const size_t n2 = n / 2;
     double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
     double2 *u2 = reinterpret_cast<double2 *>(u), *p2 = reinterpret_cast<double2 *>(p);
@@ -329,6 +335,35 @@ __global__ void __launch_bounds__(KR_THREADS)
         if (i < n_owned)
             u[i] = un;
     }
+    if (n_nbr == 0)
+        return;
+    // ---- ghost push by the last CTA to finish ----
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last)
+        return;
+    __threadfence();
+    for (int e = threadIdx.x; e < n_send; e += KR_THREADS) {
+        double *dst = reinterpret_cast<double *>(nbr_base.base[send_nbr[e]] + lay.off_u) + (size_t)send_dst[e] * gdim;
+        const double *src = u + (size_t)send_src[e] * gdim;
+        for (int j = 0; j < gdim; ++j)
+            dst[j] = __ldcg(src + j);  // written by other SMs in this launch: read it from L2
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int k = 0; k < n_nbr; ++k)
+            st_flag(reinterpret_cast<unsigned long long *>(nbr_base.base[k] + lay.off_haloflag) + rank, epoch);
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(comm + lay.off_haloflag);
+        for (int k = 0; k < n_nbr; ++k)
+            wait_flag(mine + nbr_rank_dev[k], epoch, false, err);
+        *ticket = 0;
+    }
 }
 
 // K4: owned values that are ghosts elsewhere -> the neighbours' u vectors (peer stores), then the
@@ -363,6 +398,15 @@ __global__ void __launch_bounds__(KR_THREADS)
             wait_flag(mine + nbr_rank_dev[k], epoch, false, err);
         *ticket = 0;
     }
+}
+
+// Ghost refresh of an arbitrary nodal vector through the comm block: owned part -> exchange vector
+__global__ void __launch_bounds__(KR_THREADS)
+    kr_copy_kernel(size_t lo, size_t hi, const double *__restrict__ src, double *__restrict__ dst)
+{
+    const size_t stride = (size_t)gridDim.x * KR_THREADS;
+    for (size_t i = lo + (size_t)blockIdx.x * KR_THREADS + threadIdx.x; i < hi; i += stride)
+        dst[i] = src[i];
 }
 
 static unsigned kr_grid(size_t work)
@@ -438,6 +482,8 @@ int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, size_t nnode
         e = cudaMalloc((void **)&K->state, sizeof(double) * 8);
     if (e == cudaSuccess)
         e = cudaMemset(K->state, 0, sizeof(double) * 8);
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&K->scal, sizeof(double) * 2);
     if (e == cudaSuccess)
         e = cudaMalloc((void **)&K->hist, sizeof(double) * KR_HIST);
     if (e == cudaSuccess)
@@ -590,9 +636,11 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
         if (rc != FCX_OK)
             return rc;
         K->epoch += 1;
+        const int first = K->it == 0 ? 1 : 0;
 #define FCX_GSUM(G) \
     gsum_dots_kernel<G><<<ggrid, KR_THREADS, 0, st>>>(K->adj_ptr, K->adj_idx, K->fe, K->r, u, K->minv, K->w, K->nnodes, \
-                                                      K->partials, K->ticket, K->peers, K->lay, K->rank, K->world, K->epoch)
+                                                      K->partials, K->ticket, K->peers, K->lay, K->rank, K->world, K->epoch, \
+                                                      first, K->state, K->scal, K->hist, K->it, K->err)
         if (K->gdim == 1)
             FCX_GSUM(1);
         else if (K->gdim == 2)
@@ -600,19 +648,45 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
         else
             FCX_GSUM(3);
 #undef FCX_GSUM
-        cg_update_kernel<<<K->grid, KR_THREADS, 0, st>>>(K->n, K->n_owned, K->x, K->r, u, K->w, K->p, K->s, K->minv, K->comm, K->lay,
-                                                         K->world, K->epoch, K->it == 0 ? 1 : 0, K->state, K->hist, K->it,
-                                                         K->err);
+        PeerPtrs nb{};
+        for (int q = 0; q < K->n_nbr; ++q)
+            nb.base[q] = K->peers.base[K->nbr_rank[q]];
+        const int n_nbr = K->world > 1 ? K->n_nbr : 0;
+        cg_update_kernel<<<K->grid, KR_THREADS, 0, st>>>(K->n, K->n_owned, K->x, K->r, u, K->w, K->p, K->s, K->minv, K->scal,
+                                                         K->gdim, K->send_src, K->send_dst, K->send_nbr, K->n_send, nb,
+                                                         K->lay, n_nbr, K->rank, K->comm,
+                                                         n_nbr > 0 ? K->send_nbr + K->n_send : nullptr, K->ticket + 1,
+                                                         K->epoch, K->err);
         g_launches.fetch_add(2, std::memory_order_relaxed);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess)
             return note_cuda_error(e, "krylov iteration launch");
         K->it += 1;
-        rc = kr_push(K, st);
-        if (rc != FCX_OK)
-            return rc;
     }
     return FCX_OK;
+}
+
+/* Overwrite the ghost entries of the nodal vector x (DEVICE, n doubles, owned nodes first) with their owners'
+ * values -- the same peer-memory push as inside the iteration, with the exchange vector of the (finished) solve
+ * as the staging area: what the reference gets from PETSc's ghostUpdate / dolfinx's scatter_forward
+ * (solver/_incrementalunknowns.py:36-38) after the Newton update.  Collective over the ranks; enqueue-only. */
+int fcx_krylov_halo_update(void *handle, double *x, void *stream)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K || !x)
+        return FCX_ERR_NULL;
+    if (K->world == 1 || K->n_nbr == 0)
+        return FCX_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double *u = reinterpret_cast<double *>(K->comm + K->lay.off_u);
+    kr_copy_kernel<<<kr_grid(K->n_owned), KR_THREADS, 0, st>>>(0, K->n_owned, x, u);
+    K->epoch += 1;
+    int rc = kr_push(K, st);
+    if (rc != FCX_OK)
+        return rc;
+    kr_copy_kernel<<<kr_grid(K->n - K->n_owned + 1), KR_THREADS, 0, st>>>(K->n_owned, K->n, u, x);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "fcx_krylov_halo_update");
 }
 
 /* After a synchronisation of the stream: out[0] = iterations done, out[1] = r.r at the start of the last
@@ -664,7 +738,7 @@ void fcx_krylov_destroy(void *handle)
     for (int t = 0; t < K->world; ++t)
         if (K->peer_open[t])
             cudaIpcCloseMemHandle(K->peers.base[t]);
-    void *ptrs[] = {K->comm, K->x, K->r, K->w, K->p, K->s, K->minv, K->partials, K->ticket, K->state, K->hist, K->err,
+    void *ptrs[] = {K->comm, K->x, K->r, K->w, K->p, K->s, K->minv, K->partials, K->ticket, K->state, K->scal, K->hist, K->err,
                     K->send_src, K->send_dst, K->send_nbr};
     for (void *q : ptrs)
         if (q)

@@ -102,6 +102,14 @@ class DeviceKrylov:
         check(L.fcx_krylov_solution(h, self._x.data_ptr(), stream), "fcx_krylov_solution")
         return self._x, it, ok, relres, brk
 
+    def halo_update(self, x) -> None:
+        """Ghost entries of the nodal vector x <- their owners' values (peer-memory push; collective)."""
+        if self.world == 1:
+            return
+        check(self.L.fcx_set_device(self.device.index), "fcx_set_device")
+        check(self.L.fcx_krylov_halo_update(self.handle, x.data_ptr(), B.current_stream_ptr(self.device.index)),
+              "fcx_krylov_halo_update")
+
     def close(self) -> None:
         if self.handle is not None:
             self.L.fcx_krylov_destroy(self.handle)

@@ -84,6 +84,9 @@ class NewtonSolver:
         self._cg_ws = None
         self.profile = False  # accumulate wall time of the linear solves (adds two syncs per solve)
         self.linear_solve_s = 0.0
+        self.residual_s = 0.0   # profile: form + F + lifting + norm
+        self.update_s = 0.0     # profile: x update + ghost refresh of x
+        self.krylov_setup_s = 0.0  # one-off set-up of the device Krylov loop (IPC handles, buffers)
 
     # ------------------------------------------------------------ helpers
     def _owned(self, like):
@@ -250,7 +253,12 @@ class NewtonSolver:
         fm = (free_mask if own is None else free_mask & own).to(torch.float64)
         minv = fm / torch.where(diag.abs() > 0, diag, torch.ones_like(diag))
         if self._device_krylov is None or self._device_krylov.problem is not self.problem:
+            import time
+
+            t0 = time.perf_counter()
             self._device_krylov = DeviceKrylov(self.problem, self.partition)
+            torch.cuda.synchronize()
+            self.krylov_setup_s += time.perf_counter() - t0
         tol = self.cg_rtol if rtol is None else rtol
         x, it, ok, relres, brk = self._device_krylov.solve(rhs, minv, tol, self.cg_max_it, self.cg_check_every)
         why = None
@@ -349,6 +357,18 @@ class NewtonSolver:
             b[bc_dofs] = x[bc_dofs] - bc_vals
             return self._norm(b)
 
+        import time as _time
+
+        def _timed(fn, attr):
+            if not self.profile:
+                return fn()
+            torch.cuda.synchronize()
+            t0 = _time.perf_counter()
+            out = fn()
+            torch.cuda.synchronize()
+            setattr(self, attr, getattr(self, attr) + _time.perf_counter() - t0)
+            return out
+
         self.residual_history, self.krylov_iterations = [], []
         self.krylov_converged, self.krylov_relres = [], []
         multi_rank = self.partition is not None or self.reduce_over_ranks
@@ -358,7 +378,7 @@ class NewtonSolver:
         if self.linear_solver not in ("auto", "cg", "bicgstab", "dense"):
             raise ValueError(f"unknown linear_solver {self.linear_solver!r}")
         symmetric = bool(getattr(pb, "symmetric_tangent", True))
-        r = residual()
+        r = _timed(residual, "residual_s")
         r0 = r
         self.residual_history.append(r)
         dx0 = None
@@ -408,11 +428,18 @@ class NewtonSolver:
                     self.linear_solve_s += time.perf_counter() - t0
             dx[bc_dofs] = b[bc_dofs]  # identity rows: dx_bc = x_bc - g
             self.krylov_iterations.append(kit)
-            x.add_(dx, alpha=-self.relaxation_parameter)
-            if self.partition is not None:
-                self.partition.halo_update(x)
+
+            def _update():
+                x.add_(dx, alpha=-self.relaxation_parameter)
+                if self.partition is not None:
+                    if self._device_krylov is not None and self._device_krylov.problem is self.problem and x.is_cuda:
+                        self._device_krylov.halo_update(x)  # peer-memory push, no NCCL
+                    else:
+                        self.partition.halo_update(x)
+
+            _timed(_update, "update_s")
             it += 1
-            r = residual()
+            r = _timed(residual, "residual_s")
             self.residual_history.append(r)
             if self.convergence_criterion == "incremental":
                 dxn = self._norm(dx)

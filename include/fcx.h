@@ -300,7 +300,7 @@ int fcx_pcg_update_p(size_t n, double *p, const double *r, const double *minv, c
  *                        fcx_tangent_apply (mode 1) and the adjacency of fcx_gather_sum
  *   fcx_krylov_begin     x = 0, r = rhs where minv != 0 (minv = inverse Jacobi diagonal, 0 on constrained
  *                        AND ghost dofs), first ghost push
- *   fcx_krylov_iterate   enqueue `iters` iterations (4 launches each, 3 on one rank); never synchronises
+ *   fcx_krylov_iterate   enqueue `iters` iterations (3 launches each); never synchronises
  *   fcx_krylov_status    (after a stream synchronisation) out[0] iterations done, out[1] r.r at the start
  *                        of the last one, out[2] r.r of the right-hand side, out[3] 1 = breakdown (p.Ap <= 0),
  *                        2 = a peer rank never arrived (bounded spin timed out)
@@ -318,6 +318,10 @@ int fcx_krylov_begin(void *handle, const double *rhs, const double *minv, void *
 int fcx_krylov_iterate(void *handle, int iters, void *stream);
 int fcx_krylov_status(void *handle, double *out4);
 int fcx_krylov_solution(void *handle, double *x_out, void *stream);
+/* Ghost entries of the nodal vector x (owned nodes first) <- their owners' values, through the same peer-memory
+ * push (reference: PETSc ghostUpdate / scatter_forward of the displacement, solver/_incrementalunknowns.py:36-38).
+ * Collective over the ranks of the solver; enqueue-only; not during a solve. */
+int fcx_krylov_halo_update(void *handle, double *x, void *stream);
 void fcx_krylov_destroy(void *handle);
 
 /* -------------------------------------------------------------------- host */

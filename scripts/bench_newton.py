@@ -183,7 +183,8 @@ if rank == 0:
         "krylov_iterations": krylov, "cg_rtol": args.cg_rtol, "cg_forcing": args.forcing, "cg_driver": args.driver,
  "fused_form": problem.fused,
         "setup_s": round(setup_s, 2), "solve_s": round(solve_s, 3),
-        "linear_solve_s": round(solver.linear_solve_s, 3),
+        "linear_solve_s": round(solver.linear_solve_s, 3), "residual_s": round(solver.residual_s, 3),
+        "update_s": round(solver.update_s, 3), "krylov_setup_s": round(solver.krylov_setup_s, 3),
         "ms_per_krylov_iteration": 1e3 * solver.linear_solve_s / max(1, sum(sum(k) for k in krylov)), "form_calls": form_calls,
         "qp_updates_per_s_whole_solve": (mesh.num_cells * (nqp // problem.num_cells) if part is not None else world * nqp) * form_calls / solve_s,
         "plastic_fraction_final": round(plastic_frac, 4), "mean_sigma_xx": sxx,
