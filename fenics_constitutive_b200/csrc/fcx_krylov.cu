@@ -16,15 +16,14 @@
 //                               the other ranks' sums and adds them in RANK order (every rank gets
 //                               the same bits): alpha / beta
 //     K3  cg_update_kernel      p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;
-//                               u = minv r;  then the last CTA stores u of the nodes that are ghosts
-//                               elsewhere straight into the neighbours' vectors, raises a system-scope
-//                               flag and waits for the neighbours' flags (so K1 of the next iteration
-//                               reads fresh ghosts)
-// (the standalone halo_push_kernel does the same push at the start of a solve and for
-// fcx_krylov_halo_update)
+//                               u = minv r
+//     K4  halo_push_kernel      u of the nodes that are ghosts elsewhere is stored straight into the
+//                               neighbours' vectors; a system-scope flag tells them; then waits for
+//                               the neighbours' flags (so K1 of the next iteration reads fresh ghosts);
+//                               also used at the start of a solve and by fcx_krylov_halo_update
 // with  gamma = r.u, delta = w.u:  beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)
 // -- ONE reduction per iteration instead of two, one fused vector pass instead of three kernels.
-// Three launches per iteration; fcx_krylov_iterate enqueues a block of iterations from C; the host looks at the residual history
+// Four launches per iteration (three on one rank); fcx_krylov_iterate enqueues a block of iterations from C; the host looks at the residual history
 // once per block.  One process per GPU: peers' buffers come from CUDA IPC handles.
 //
 // Ordering between ranks: a reduction slot / flag pair is double-buffered by iteration parity; a rank
@@ -651,7 +650,10 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
         PeerPtrs nb{};
         for (int q = 0; q < K->n_nbr; ++q)
             nb.base[q] = K->peers.base[K->nbr_rank[q]];
-        const int n_nbr = K->world > 1 ? K->n_nbr : 0;
+        // ghost push: its own kernel (K4) over a full grid.  Folding it into the tail of K3 (the last CTA to
+        // finish stores all send entries) was measured: 24 k nodes x 3 peer stores from ONE CTA cost 0.23 ms
+        // per iteration on two GPUs (0.55 vs 0.32 ms, profiles/r2e_*), so K3's tail is switched off (n_nbr = 0)
+        const int n_nbr = 0;
         cg_update_kernel<<<K->grid, KR_THREADS, 0, st>>>(K->n, K->n_owned, K->x, K->r, u, K->w, K->p, K->s, K->minv, K->scal,
                                                          K->gdim, K->send_src, K->send_dst, K->send_nbr, K->n_send, nb,
                                                          K->lay, n_nbr, K->rank, K->comm,
@@ -662,6 +664,9 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
         if (e != cudaSuccess)
             return note_cuda_error(e, "krylov iteration launch");
         K->it += 1;
+        rc = kr_push(K, st);
+        if (rc != FCX_OK)
+            return rc;
     }
     return FCX_OK;
 }

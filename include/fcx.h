@@ -300,7 +300,7 @@ int fcx_pcg_update_p(size_t n, double *p, const double *r, const double *minv, c
  *                        fcx_tangent_apply (mode 1) and the adjacency of fcx_gather_sum
  *   fcx_krylov_begin     x = 0, r = rhs where minv != 0 (minv = inverse Jacobi diagonal, 0 on constrained
  *                        AND ghost dofs), first ghost push
- *   fcx_krylov_iterate   enqueue `iters` iterations (3 launches each); never synchronises
+ *   fcx_krylov_iterate   enqueue `iters` iterations (4 launches each, 3 on one rank); never synchronises
  *   fcx_krylov_status    (after a stream synchronisation) out[0] iterations done, out[1] r.r at the start
  *                        of the last one, out[2] r.r of the right-hand side, out[3] 1 = breakdown (p.Ap <= 0),
  *                        2 = a peer rank never arrived (bounded spin timed out)
