@@ -29,6 +29,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--qps", type=int, default=16_000_000)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--quick", action="store_true", help="defaults + wires only")
+ap.add_argument("--mini", action="store_true", help="defaults, wires and a few chunk / thread points (multi-GPU sessions)")
 ap.add_argument("--kinds", default="pageable,pinned")
 ap.add_argument("--stress-only", action="store_true")
 args = ap.parse_args()
@@ -90,7 +91,12 @@ for kind in args.kinds.split(","):
     run(kind, A, "defaults (wire auto)")
     for wire in (0, 1, 2):
         run(kind, A, "wire", wire=wire)
-    if not args.quick:
+    if args.mini:
+        for chunk in (8192, 16384, 65536):
+            run(kind, A, "chunk", chunk_qps=chunk)
+        for threads in (2, 4, 8):
+            run(kind, A, "threads", threads=threads)
+    elif not args.quick:
         for chunk in (1 << 14, 1 << 15, 1 << 16, 1 << 17, 1 << 18):
             run(kind, A, "chunk", chunk_qps=chunk)
         for slots in (3, 4, 6, 8):
