@@ -949,9 +949,14 @@ static void plastic_wire_expand(const PlasticWire &W, size_t q0, size_t cnt, con
 // Tried and reverted (profiles/r1zg_*): packing the records in device memory and letting a second
 // drain stage DMA exactly `count` of them -- same link rate, one more host round trip per chunk.
 // 3 = AUTO (the default): the record wire (1) unless several ranks share the host's memory system AND
-// every result array of the call is page-locked -- then plain DMA (0), which costs no host-thread byte:
-// with 4-8 ranks per host the pool shrinks to a few threads per rank and the expansion, not the link,
-// bounds the record wire (SCALE_r01: 217 M QP/s for 8 GPUs).  Threshold: FCX_WIRE_AUTO_RANKS (default 4).
+// every result array of the call is page-locked -- then the direct wire (2): the GPU stores the plastic
+// tangents in place, the few pool threads a rank has left only fill the elastic runs.  Measured on the
+// 32-core hosts of this pool, 16 M QPs per rank, page-locked arrays (profiles/r2f_e2e_sweep_pinned_n*.jsonl):
+//   4 ranks: wire 0 / 1 / 2 = 221 / 224 / 241 M QP/s,   8 ranks: 202 / 216 / 233
+// (one rank on a 16-core host: 124 / 156 / 135, profiles/r2b_e2e_sweep_pinned.jsonl).  Plain DMA of every array
+// (0) -- no host-thread byte at all -- is the SLOWEST with many ranks: all of them are bound by the host's
+// DRAM (166-172 GB/s memcpy on these hosts), and 392 B/QP of DMA writes cost more of it than 161 B/QP of
+// records plus streaming fills.  Threshold: FCX_WIRE_AUTO_RANKS (default 4).
 static int g_wire = 3;
 
 static int local_world_size()
@@ -990,7 +995,7 @@ static int effective_wire(const void *stress, const void *tangent, const void *h
     }();
     if (local_world_size() >= ranks && page_locked(stress) && page_locked(tangent) && page_locked(h0) &&
         page_locked(h1))
-        return 0;
+        return 2;
     return 1;
 }
 static int g_last_wire = -1;  // what the last plastic host call resolved to (fcx_host_wire_used)

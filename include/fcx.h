@@ -376,11 +376,11 @@ int fcx_host_threads(int n);
  * slower on the hosts measured so far, profiles/r1zf_host_wire_stats.jsonl);
  * 0 = plain D2H of every array, 3 = auto (below), -1 = query; returns the old value. */
 int fcx_host_wire(int on);
-/* 3 = AUTO, the default since 0.2: wire 1, except that with several ranks per host
- * (LOCAL_WORLD_SIZE >= FCX_WIRE_AUTO_RANKS, default 4) and every result array page-locked the call
- * takes wire 0 -- plain DMA costs no host-thread byte, and with 4-8 ranks sharing one memory system the
- * host-thread expansion is what bounds the record wire.  fcx_host_wire_used(): what the last plastic
- * host call resolved to (0/1/2; -1 before the first call). */
+/* 3 = AUTO, the default since 0.2: wire 1, except that stress-only calls take wire 0 and, with several
+ * ranks per host (LOCAL_WORLD_SIZE >= FCX_WIRE_AUTO_RANKS, default 4) and every result array page-locked,
+ * the call takes wire 2 (measured best at 4 and 8 ranks per host, profiles/r2f_e2e_sweep_pinned_n*.jsonl;
+ * plain DMA, wire 0, is the slowest there: every variant is bound by the host's DRAM).
+ * fcx_host_wire_used(): what the last plastic host call resolved to (0/1/2; -1 before the first call). */
 int fcx_host_wire_used(void);
 /* NUMA placement of the host pipeline (pool threads, drain thread, pinned ring slots) on the node
  * the bound GPU hangs off; 1 = on (default), 0 = off, -1 = query; returns the old value.  A no-op on
