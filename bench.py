@@ -361,7 +361,10 @@ def run_native(args):
                     "bytes_per_qp": tr, "achieved_host_bytes_per_s": leg["value"] * tr["host_dram"],
                     "peak": roof["host_memory"]["memcpy_rw_GBps"] * 1e9,
                     "peak_unit": "B/s, host memcpy read+write, measured at start-up",
-                    "frac": leg["value"] / caps[bound]}
+                    "frac": leg["value"] / caps[bound],
+                    "note": "host_dram counts every pass through a pinned ring slot as DRAM traffic; the part the "
+                            "last-level cache serves makes frac exceed 1 (bytes_per_qp.host_dram_if_slots_stay_in_llc "
+                            "is the other extreme)"}
 
         e2e = {"value": head["value"], "unit": UNIT, "h2d_bytes_per_step": H2D_PER_QP * ne,
                "d2h_bytes_per_step": D2H_PER_QP * ne,

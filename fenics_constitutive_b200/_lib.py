@@ -32,6 +32,7 @@ SIGNATURES = {
     "fcx_strain_from_grad_u": (_ci, [_ci, _sz, _dp, _dp, _vp]),
     "fcx_embed_3d": (_ci, [_ci, _sz, _dp, _dp, _dp, _dp, _vp]),
     "fcx_extract_from_3d": (_ci, [_ci, _sz, _dp, _dp, _dp, _dp, _vp]),
+    "fcx_nodal_increment": (_ci, [_sz, _dp, _dp, _dp, _vp]),
     "fcx_gather_grad": (_ci, [_ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _vp]),
     "fcx_mises_linear_hardening_evaluate": (_ci, [_dp, _sz, _dp, _dp, _dp, _dp, _vp, _vp]),
     "fcx_mises_linear_hardening_evaluate_host": (_ci, [_dp, _sz, _dp, _dp, _dp, _dp, _vp]),

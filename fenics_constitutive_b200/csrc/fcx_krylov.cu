@@ -107,9 +107,11 @@ __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// Flag stores are RELAXED system-scope stores behind ONE system-scope fence of the signalling thread (a
+// release per flag would repeat that fence for every peer: 8 of them per reduction at 8 ranks).
 __device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // Bounded spin on a flag (until it is >= want, or == want if `exact`): a peer that never arrives must not
 // hang the GPU.  ~2^24 polls of a system-scope load are several seconds; on time-out the sticky error word

@@ -115,6 +115,10 @@ class IncrementalGradient:
         assert self.dphi_ref.shape == (self.nq, self.nd, self.gdim)
         assert self.Jinv.shape == (self.ncells, self.gdim, self.gdim)
         self.device = dev
+        # True: with u_prev given, form du = u - u_prev once as a nodal vector (fcx_nodal_increment) and gather
+        # that -- every nodal value is fetched once instead of twice, same bits.  False: the kernel fetches both.
+        self.form_increment_first = True
+        self._du = None
 
     @property
     def num_qps(self) -> int:
@@ -131,10 +135,20 @@ class IncrementalGradient:
         assert bg.size == self.num_qps * self.gdim**2, "grad_del_u has the wrong size"
         L = lib()
         check(L.fcx_set_device(bu.device_index))
+        stream = B.current_stream_ptr(bu.device_index)
+        u_ptr, prev_ptr = bu.ptr, (bp.ptr if bp is not None else None)
+        if bp is not None and self.form_increment_first:
+            assert bp.size == bu.size, "u and u_prev differ in size"
+            import torch
+
+            if self._du is None or self._du.numel() != bu.size or self._du.device.index != bu.device_index:
+                self._du = torch.empty(bu.size, dtype=torch.float64, device=f"cuda:{bu.device_index}")
+            check(L.fcx_nodal_increment(bu.size, bu.ptr, bp.ptr, self._du.data_ptr(), stream), "fcx_nodal_increment")
+            u_ptr, prev_ptr = self._du.data_ptr(), None
         rc = L.fcx_gather_grad(
-            self.gdim, self.ncells, self.nq, self.nd, self.dofmap.data_ptr(), bu.ptr,
-            bp.ptr if bp is not None else None, self.dphi_ref.data_ptr(), self.Jinv.data_ptr(),
-            bg.ptr, B.current_stream_ptr(bu.device_index),
+            self.gdim, self.ncells, self.nq, self.nd, self.dofmap.data_ptr(), u_ptr,
+            prev_ptr, self.dphi_ref.data_ptr(), self.Jinv.data_ptr(),
+            bg.ptr, stream,
         )
         check(rc, "IncrementalGradient.evaluate")
 

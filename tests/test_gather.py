@@ -153,11 +153,14 @@ def test_gpu_gather_staged_kernel_bitwise(gdim, degree, qdeg, ncells, with_prev)
     try:
         for variant in (0, 1, 2, 2):  # 2 = gather_cell_kernel (thread per cell, 3-D 4-point rules; else as 1)
             L.fcx_tune(b"gather_variant", variant)
-            out = torch.full((op.num_qps * gdim * gdim,), float("nan"), dtype=torch.float64, device="cuda")
-            op.evaluate(torch.from_numpy(u).cuda(), torch.from_numpy(u_prev).cuda() if with_prev else None, out)
-            outs.append(out.cpu().numpy())
+            # u_prev fetched by the kernel (False) or subtracted first as a nodal vector (True, the default)
+            for first in ((False, True) if with_prev else (True,)):
+                op.form_increment_first = first
+                out = torch.full((op.num_qps * gdim * gdim,), float("nan"), dtype=torch.float64, device="cuda")
+                op.evaluate(torch.from_numpy(u).cuda(), torch.from_numpy(u_prev).cuda() if with_prev else None, out)
+                outs.append(out.cpu().numpy())
     finally:
         L.fcx_tune(b"gather_variant", old)
     assert all(np.array_equal(outs[0], o) for o in outs[1:])
     ref = om.gather_grad(gdim, dofmap, u, u_prev, dphi, Jinv)
-    assert np.max(np.abs(outs[1] - ref)) <= 1e-12 * np.abs(ref).max()
+    assert np.max(np.abs(outs[-1] - ref)) <= 1e-12 * np.abs(ref).max()
