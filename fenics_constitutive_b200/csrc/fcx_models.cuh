@@ -750,6 +750,57 @@ struct DruckerPragerModel {
         return acc;
     }
 
+    // Two-phase update (fcx_tile.cuh TwoPhase): `trial` classifies the point and finishes it if it is elastic
+    // (or fails the apex assert); returns true if the return mapping has to run -- then `qp` below is called
+    // for the point by whichever thread picks it from the CTA's list (it repeats the trial arithmetic, so
+    // the classification and every bit of the result are those of the single-phase update).
+    static constexpr __host__ __device__ bool two_phase() { return true; }
+
+    template <class V>
+    __device__ static __forceinline__ bool trial(const Params &P, const V &v, double *aux, int t,
+                                                 bool &plastic, bool &failed)
+    {
+        double g[9], sig0[6];
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            g[i] = v.template ld<0>(i);
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            sig0[i] = v.template ld<1>(i);
+        const double fr = 0.70710678118654752440;
+        const double e[6] = {g[0], g[4], g[8], fr * (g[1] + g[3]), fr * (g[2] + g[6]), fr * (g[5] + g[7])};
+        const double two_mu = 2.0 * P.mu, k3 = 3.0 * P.kappa;
+        const double bfe = (P.b == P.b_flow) ? P.b : P.b_flow;
+        const double etr = (e[0] + e[1]) + e[2];
+        double sigtr[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double ev = (k < 3) ? etr / 3.0 : 0.0;
+            sigtr[k] = (two_mu * (e[k] - ev) + k3 * ev) + sig0[k];
+        }
+        State S;
+        state(P, sigtr, bfe, S);
+        failed = S.apex;
+        plastic = !(S.f <= 0.0);
+        if (plastic && !failed)
+            return true;
+        if (aux != nullptr) {  // elastic tangent 3 kappa P_vol + 2 mu P_dev (also what a failed point reports)
+            double *rec = aux + t * REC;
+            rec[0] = P.kappa + two_mu * (2.0 / 3.0);
+            rec[1] = P.kappa - two_mu / 3.0;
+            rec[2] = two_mu;
+#pragma unroll
+            for (int k = 3; k < 12; ++k)
+                rec[k] = 0.0;
+        }
+        if (!failed) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+                v.template st<1>(i, sigtr[i]);
+        }
+        return false;
+    }
+
     template <class V>
     __device__ static __forceinline__ void qp(const Params &P, const V &v, double *aux, int t,
                                               bool &plastic, bool &failed)

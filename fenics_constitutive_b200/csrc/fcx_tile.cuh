@@ -22,6 +22,8 @@
 // Tail tiles (n % TILE != 0) and pointers that are not 16-byte aligned take a
 // generic-proxy path with plain coalesced loads/stores through the same stage.
 #pragma once
+#include <type_traits>
+
 #include "fcx_ptx.cuh"
 
 namespace fcx {
@@ -30,6 +32,16 @@ template <int N>
 struct SegPtrs {
     double *p[N];
 };
+
+// Models whose plastic branch is an expensive loop (the Drucker-Prager return mapping) may opt into a
+// TWO-PHASE update: Model::trial(...) classifies every point of the tile and finishes the elastic ones;
+// the points that need the return mapping are appended to a CTA-wide list in shared memory and
+// Model::qp(...) then runs on the list with consecutive threads -- whole warps iterate or sit out,
+// instead of every warp iterating with half of its lanes idle at ~50 % plastic points.
+template <class M, class = void>
+struct TwoPhase : std::false_type {};
+template <class M>
+struct TwoPhase<M, std::void_t<decltype(M::two_phase())>> : std::bool_constant<M::two_phase()> {};
 
 // Accessor for one QP's slot of segment K inside a shared stage.
 template <class M, int TILE>
@@ -196,17 +208,56 @@ __global__ void __launch_bounds__(TILE, tile_min_ctas<M, TILE, WT>())
         }
 
         // ---- per-QP update, registers only; results go back in place ----
-        if (tid < cnt) {
+        auto report_failure = [&](int j) {
+            if (status != nullptr) {
+                atomicAdd(&status[0], 1);
+                const unsigned long long q = qbase + q0 + j;
+                atomicMin(&status[1], q > 0x7fffffffULL ? 0x7fffffff : (int)q);
+            }
+        };
+        if constexpr (TwoPhase<M>::value) {
+            __shared__ int s_np;
+            __shared__ unsigned short s_list[TILE];
+            if (tid == 0)
+                s_np = 0;
+            __syncthreads();
+            bool plastic = false, failed = false, need = false;
+            if (tid < cnt) {
+                QpView<M, TILE> v{stage, tid};
+                need = M::trial(prm, v, aux, tid, plastic, failed);
+                if (flag != nullptr)
+                    flag[q0 + tid] = plastic ? 1 : 0;
+                if (failed)
+                    report_failure(tid);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (m != 0) {
+                const int lane = tid & 31, leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader)
+                    base = atomicAdd(&s_np, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (need)
+                    s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)tid;
+            }
+            __syncthreads();
+            const int np = s_np;
+            for (int k = tid; k < np; k += TILE) {
+                const int j = s_list[k];
+                bool pl2 = false, f2 = false;
+                QpView<M, TILE> v{stage, j};
+                M::qp(prm, v, aux, j, pl2, f2);
+                if (f2)
+                    report_failure(j);
+            }
+        } else if (tid < cnt) {
             bool plastic = false, failed = false;
             QpView<M, TILE> v{stage, tid};
             M::qp(prm, v, aux, tid, plastic, failed);
             if (M::has_flag() && flag != nullptr)
                 flag[q0 + tid] = plastic ? 1 : 0;
-            if (M::has_flag() && failed && status != nullptr) {
-                atomicAdd(&status[0], 1);
-                const unsigned long long q = qbase + q0 + tid;
-                atomicMin(&status[1], q > 0x7fffffffULL ? 0x7fffffff : (int)q);
-            }
+            if (M::has_flag() && failed)
+                report_failure(tid);
         }
         if (bulk)
             fence_proxy_async_smem();
