@@ -754,7 +754,11 @@ struct DruckerPragerModel {
     // (or fails the apex assert); returns true if the return mapping has to run -- then `qp` below is called
     // for the point by whichever thread picks it from the CTA's list (it repeats the trial arithmetic, so
     // the classification and every bit of the result are those of the single-phase update).
-    static constexpr __host__ __device__ bool two_phase() { return true; }
+    // MEASURED and switched OFF (profiles/r2g_models.json, 16 M points, 52 % plastic, 425 GPU tests green with it
+    // on): classic 2.85 ms against 2.6 ms single-phase, hyperbolic 3.29 against 3.3.  With 128 points per tile
+    // the list fills two warps and a few lanes of a third, so only one warp of four sits the return mapping
+    // out, and that is paid for with two more CTA barriers per tile and the repeated trial arithmetic.
+    static constexpr __host__ __device__ bool two_phase() { return false; }
 
     template <class V>
     __device__ static __forceinline__ bool trial(const Params &P, const V &v, double *aux, int t,
