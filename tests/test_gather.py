@@ -164,3 +164,57 @@ def test_gpu_gather_staged_kernel_bitwise(gdim, degree, qdeg, ncells, with_prev)
     assert all(np.array_equal(outs[0], o) for o in outs[1:])
     ref = om.gather_grad(gdim, dofmap, u, u_prev, dphi, Jinv)
     assert np.max(np.abs(outs[-1] - ref)) <= 1e-12 * np.abs(ref).max()
+
+
+def _permutation_case(seed=5, ncells=4 * 64 + 37):
+    rng = np.random.default_rng(seed)
+    pts, _ = G.simplex_quadrature(3, 2)
+    dphi = G.lagrange_gradients(3, 2, pts)          # [nq][nd][3]
+    nq, nd = dphi.shape[0], dphi.shape[1]
+    nnodes = ncells * 2
+    dofmap = rng.integers(0, nnodes, size=(ncells, nd)).astype(np.int32)
+    Jinv = rng.standard_normal((ncells, 3, 3)) + 3 * np.eye(3)
+    u, u_prev = rng.standard_normal(nnodes * 3), rng.standard_normal(nnodes * 3)
+    pd, pq = rng.permutation(nd), rng.permutation(nq)
+    return dphi, dofmap, Jinv, u, u_prev, pd, pq, nq
+
+
+def test_gather_permutation_covariance_oracle():
+    """The element's dof and point ORDERING (basix's, in the reference: _incrementalunknowns.py:21-27) enters the
+    gather only through the caller-supplied tables: permuting the local dofs in `dphi_ref` and `dofmap`
+    together changes nothing (to round-off of the reordered sum); permuting the quadrature points permutes
+    the output rows identically.  CPU: the oracle restatement."""
+    dphi, dofmap, Jinv, u, u_prev, pd, pq, nq = _permutation_case()
+    base = om.gather_grad(3, dofmap, u, u_prev, dphi, Jinv).reshape(-1, nq, 9)
+    by_dof = om.gather_grad(3, dofmap[:, pd], u, u_prev, dphi[:, pd, :], Jinv).reshape(-1, nq, 9)
+    assert np.abs(by_dof - base).max() <= 1e-13 * np.abs(base).max()
+    by_q = om.gather_grad(3, dofmap, u, u_prev, dphi[pq], Jinv).reshape(-1, nq, 9)
+    assert np.array_equal(by_q, base[:, pq, :])
+
+
+@pytest.mark.gpu
+def test_gather_permutation_covariance():
+    """Same property on the CUDA path (fcx_nodal_increment + fcx_gather_grad), every kernel variant."""
+    import torch
+
+    from fenics_constitutive_b200._lib import lib
+
+    dphi, dofmap, Jinv, u, u_prev, pd, pq, nq = _permutation_case()
+    ud, upd = torch.from_numpy(u).cuda(), torch.from_numpy(u_prev).cuda()
+
+    def run(dm, tab):
+        op = G.IncrementalGradient(3, np.ascontiguousarray(dm), np.ascontiguousarray(tab), Jinv)
+        out = torch.empty(op.num_qps * 9, dtype=torch.float64, device="cuda")
+        op.evaluate(ud, upd, out)
+        return out.cpu().numpy().reshape(-1, nq, 9)
+
+    L = lib()
+    old = L.fcx_tune(b"gather_variant", -1)
+    try:
+        for variant in (0, 1, 2):
+            L.fcx_tune(b"gather_variant", variant)
+            base = run(dofmap, dphi)
+            assert np.abs(run(dofmap[:, pd], dphi[:, pd, :]) - base).max() <= 1e-13 * np.abs(base).max()
+            assert np.array_equal(run(dofmap, dphi[pq]), base[:, pq, :])
+    finally:
+        L.fcx_tune(b"gather_variant", old)
