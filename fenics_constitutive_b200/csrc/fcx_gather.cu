@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "../../include/fcx.h"
 #include "fcx_fem.cuh"
@@ -500,6 +501,188 @@ __global__ void __launch_bounds__(64)
     bulk_wait_read_all();
 }
 
+// ---------------------------------------------------------------------------
+// gather_wq_kernel: gather_staged_kernel's staging and occupancy (two threads per cell, 6 CTAs per SM) with
+// a WARP-UNIFORM quadrature-point pair: warp w of the CTA takes points {2w, 2w+1} of the tile's 32 cells
+// (lane = cell), so the basis-gradient table entries are compile-time indices into __constant__ memory --
+// operands of the DFMAs instead of 120 of the 255 LDS wavefronts per tile -- each thread reads its cell's
+// nodal values with conflict-free 16-byte loads, and writes its 18 results into a padded row (38 doubles per
+// cell: conflict-free 16-byte stores); warp 0 ships the 32 rows with one 288-byte bulk store each.
+// Same fma chains in the same order (grad_at_qps), hence the same bits.  3-D, 4-point rules, whole 32-cell
+// tiles; fcx_tune "gather_variant" 3.
+// ---------------------------------------------------------------------------
+template <int ND, bool PREV>
+struct WqGatherCfg {
+    static constexpr int NQ = 4, G = 3, GG = 9;
+    static constexpr int CPT = 32, NT = 64;
+    static constexpr int ROW = 38;
+    static constexpr int NDU = CPT * ND * G;
+    static constexpr int NVEC = PREV ? 2 : 1;
+    static constexpr int DOF_DBL = (CPT * ND + 1) / 2;
+    static constexpr size_t smem_bytes =
+        sizeof(double) * ((size_t)CPT * ROW + 2 * NVEC * NDU + 3 * CPT * GG + 3 * DOF_DBL + 4);
+};
+
+template <int ND, bool PREV, int Q0>
+__device__ __forceinline__ void wq_compute(const double *__restrict__ kin, const double2 *__restrict__ du2,
+                                           int ndu_half, double *__restrict__ orow)
+{
+    constexpr int G = 3, GG = 9;
+    double K[GG];
+#pragma unroll
+    for (int k = 0; k < GG; ++k)
+        K[k] = kin[k];
+    double T[2][G][G];
+#pragma unroll
+    for (int qq = 0; qq < 2; ++qq)
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                T[qq][k][j] = 0.0;
+#pragma unroll
+    for (int a2 = 0; a2 < ND / 2; ++a2) {
+        double v[6];
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            double2 x = du2[a2 * 3 + h];
+            if (PREV) {
+                const double2 y = du2[ndu_half + a2 * 3 + h];
+                x.x -= y.x;
+                x.y -= y.y;
+            }
+            v[2 * h] = x.x;
+            v[2 * h + 1] = x.y;
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int a = 2 * a2 + half;
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq)
+#pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    const double d = c_gather_tab[((Q0 + qq) * ND + a) * G + k];
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+                        T[qq][k][j] = fma(d, v[3 * half + j], T[qq][k][j]);
+                }
+        }
+    }
+    double g[2 * GG];
+#pragma unroll
+    for (int qq = 0; qq < 2; ++qq)
+#pragma unroll
+        for (int ii = 0; ii < G; ++ii)
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < G; ++k)
+                    acc = fma(K[k * G + ii], T[qq][k][j], acc);
+                g[qq * GG + ii * G + j] = acc;
+            }
+#pragma unroll
+    for (int p = 0; p < GG; ++p)
+        *reinterpret_cast<double2 *>(orow + Q0 * GG + 2 * p) = make_double2(g[2 * p], g[2 * p + 1]);
+}
+
+template <int ND, bool PREV>
+__global__ void __launch_bounds__(64)
+    gather_wq_kernel(const __grid_constant__ GatherArgs A)
+{
+    using SC = WqGatherCfg<ND, PREV>;
+    constexpr int NQ = 4, G = 3, GG = 9, CPT = SC::CPT, NT = SC::NT, NDU = SC::NDU, NVEC = SC::NVEC, ROW = SC::ROW;
+    static_assert((ND * G) % 2 == 0, "a cell's nodal block must be a whole number of 16-byte pairs");
+    extern __shared__ __align__(128) double smem[];
+    double *s_out = smem;                          // [CPT][ROW]
+    double *s_du = s_out + CPT * ROW;              // [2][NVEC][NDU]
+    double *s_jinv = s_du + 2 * NVEC * NDU;        // [3][CPT][GG]
+    double *s_dofd = s_jinv + 3 * CPT * GG;        // [3][CPT][ND] ints
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_dofd + 3 * SC::DOF_DBL);  // [3]
+    __shared__ unsigned long long s_tile[4];
+    auto dof_slot = [&](int s) { return reinterpret_cast<int *>(s_dofd + s * SC::DOF_DBL); };
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned long long ntiles = A.ncells / CPT;  // whole tiles only
+    auto issue_A = [&](unsigned long long t, int s) {
+        const unsigned long long c0 = t * CPT;
+        mbar_arrive_expect_tx(bar + s, (uint32_t)(sizeof(double) * CPT * GG + sizeof(int) * CPT * ND));
+        bulk_g2s(s_jinv + s * CPT * GG, A.Jinv + c0 * GG, (uint32_t)(sizeof(double) * CPT * GG), bar + s);
+        bulk_g2s(dof_slot(s), A.dofmap + c0 * ND, (uint32_t)(sizeof(int) * CPT * ND), bar + s);
+    };
+    auto next_ticket = [&]() -> unsigned long long { return gridDim.x + atomicAdd(A.ticket, 1ULL); };
+    auto issue_B = [&](int s, int b) {
+        const int *dm = dof_slot(s);
+        double *dst = s_du + b * NVEC * NDU;
+        for (int e = tid; e < NDU; e += NT) {
+            const int cn = e / G, j = e - cn * G;
+            const size_t src = (size_t)dm[cn] * G + j;
+            cp_async_8(dst + e, A.u + src);
+            if (PREV)
+                cp_async_8(dst + NDU + e, A.u_prev + src);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < 3; ++s)
+            mbar_init(bar + s, 1);
+        fence_mbar_init();
+        const unsigned long long t0 = blockIdx.x, t1 = next_ticket();
+        s_tile[0] = t0;
+        s_tile[1] = t1;
+        issue_A(t0, 0);
+        if (t1 < ntiles)
+            issue_A(t1, 1);
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    mbar_wait(bar + 0, 0);
+    phase ^= 1u;
+    issue_B(0, 0);
+    cp_async_commit();
+
+    for (int i = 0;; ++i) {
+        const unsigned long long tile = s_tile[i & 3];
+        if (tile >= ntiles)
+            break;
+        const int s0 = i % 3, s1 = (i + 1) % 3, s2 = (i + 2) % 3;
+        if (tid == 0) {
+            const unsigned long long t2 = next_ticket();
+            s_tile[(i + 2) & 3] = t2;
+            if (t2 < ntiles)
+                issue_A(t2, s2);
+        }
+        const unsigned long long tile1 = s_tile[(i + 1) & 3];
+        if (tile1 < ntiles) {
+            mbar_wait(bar + s1, (phase >> s1) & 1u);
+            phase ^= 1u << s1;
+            issue_B(s1, (i + 1) & 1);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();    // this thread's share of B(i) has landed
+        if (wid == 0)
+            bulk_wait_read_all();  // the row this lane shipped one tile ago has left shared memory
+        __syncthreads();           // B(i) complete for every thread; s_out free
+        {
+            const double *kin = s_jinv + s0 * CPT * GG + lane * GG;
+            const double2 *du2 = reinterpret_cast<const double2 *>(s_du + (i & 1) * NVEC * NDU + lane * ND * G);
+            double *orow = s_out + lane * ROW;
+            if (wid == 0)
+                wq_compute<ND, PREV, 0>(kin, du2, NDU / 2, orow);
+            else
+                wq_compute<ND, PREV, 2>(kin, du2, NDU / 2, orow);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();  // both halves of every row staged; s_du[i & 1], Jinv slot s0 consumed
+        if (wid == 0) {
+            bulk_s2g(A.grad + (tile * CPT + lane) * (NQ * GG), s_out + lane * ROW, (uint32_t)(sizeof(double) * NQ * GG));
+            bulk_commit();
+        }
+    }
+    cp_async_wait<0>();
+    if (wid == 0)
+        bulk_wait_read_all();
+}
+
 // Generic fallback for element/quadrature combinations without a compiled
 // specialisation: one thread per (cell, qp), runtime loops.
 __global__ void gather_generic_kernel(int G, int nq, int nd, const int *__restrict__ dofmap,
@@ -588,15 +771,16 @@ static int launch_gather_staged(size_t nfull_cells, const int *dofmap, const dou
 // One launch of gather_cell_kernel over `nfull_cells` (a multiple of 64).  The table is copied
 // device-to-device into c_gather_tab on the launch stream; launches on other streams are ordered
 // behind the previous user of the symbol with an event (no host synchronisation).
-template <int ND, bool PREV>
+template <int ND, bool PREV, bool WQ>
 static int launch_gather_cell(size_t nfull_cells, const int *dofmap, const double *u, const double *u_prev,
                               const double *dphi, const double *Jinv, double *grad, cudaStream_t st)
 {
-    using SC = CellGatherCfg<ND, PREV>;
-    auto kern = gather_cell_kernel<ND, PREV>;
+    using SC = std::conditional_t<WQ, WqGatherCfg<ND, PREV>, CellGatherCfg<ND, PREV>>;
+    auto kern = WQ ? gather_wq_kernel<ND, PREV> : gather_cell_kernel<ND, PREV>;
+    constexpr int THREADS = 64;
     static OccCache cache;  // per device
     int occ = 1;
-    if (int rc = kernel_occupancy(cache, kern, SC::CPT, SC::smem_bytes, "occupancy(gather cell)", &occ))
+    if (int rc = kernel_occupancy(cache, kern, THREADS, SC::smem_bytes, "occupancy(gather cell)", &occ))
         return rc;
     unsigned long long *ticket = tile_ticket(st);
     if (ticket == nullptr)
@@ -623,7 +807,7 @@ static int launch_gather_cell(size_t nfull_cells, const int *dofmap, const doubl
     if (grid > ntiles)
         grid = ntiles;
     GatherArgs A{dofmap, u, u_prev, dphi, Jinv, grad, (unsigned long long)nfull_cells, ticket, 1};
-    kern<<<(unsigned)grid, SC::CPT, SC::smem_bytes, st>>>(A);
+    kern<<<(unsigned)grid, THREADS, SC::smem_bytes, st>>>(A);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     e = cudaGetLastError();
     if (e == cudaSuccess)
@@ -639,10 +823,15 @@ static int launch_gather(size_t ncells, const int *dofmap, const double *u, cons
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     // thread-per-cell kernel (fcx_tune "gather_variant" 2): 3-D cells with 4-point rules, whole 64-cell tiles
     if constexpr (G == 3 && NQ == 4) {
-        const size_t nfull64 = ncells / 64 * 64;
-        if (gather_variant() >= 2 && nfull64 >= 64 * 4 && al16(dofmap) && al16(Jinv) && al16(grad) && al16(dphi)) {
-            int rc = u_prev ? launch_gather_cell<ND, true>(nfull64, dofmap, u, u_prev, dphi, Jinv, grad, st)
-                            : launch_gather_cell<ND, false>(nfull64, dofmap, u, u_prev, dphi, Jinv, grad, st);
+        // 2: thread per cell (64-cell tiles), 3: warp-uniform quadrature-point pair (32-cell tiles)
+        const bool wq = gather_variant() >= 3;
+        const size_t cpt = wq ? 32 : 64;
+        const size_t nfull64 = ncells / cpt * cpt;
+        if (gather_variant() >= 2 && nfull64 >= cpt * 4 && al16(dofmap) && al16(Jinv) && al16(grad) && al16(dphi)) {
+            int rc = wq ? (u_prev ? launch_gather_cell<ND, true, true>(nfull64, dofmap, u, u_prev, dphi, Jinv, grad, st)
+                                  : launch_gather_cell<ND, false, true>(nfull64, dofmap, u, u_prev, dphi, Jinv, grad, st))
+                        : (u_prev ? launch_gather_cell<ND, true, false>(nfull64, dofmap, u, u_prev, dphi, Jinv, grad, st)
+                                  : launch_gather_cell<ND, false, false>(nfull64, dofmap, u, u_prev, dphi, Jinv, grad, st));
             if (rc != -1) {
                 if (rc != FCX_OK || nfull64 == ncells)
                     return rc;

@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--grid", type=int, default=55)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--ctas", default="0,1,2,3,4,6")
+ap.add_argument("--variants", default="0,1,2,3")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 L = lib()
@@ -50,7 +51,7 @@ def timed(prev):
 
 
 ref = {}
-for variant in (0, 1, 2):
+for variant in [int(v) for v in args.variants.split(',')]:
     L.fcx_tune(b"gather_variant", variant)
     for ctas in [int(c) for c in args.ctas.split(",")]:
         L.fcx_tune(b"ctas_per_sm", ctas)

@@ -151,7 +151,9 @@ def test_gpu_gather_staged_kernel_bitwise(gdim, degree, qdeg, ncells, with_prev)
     outs = []
     old = L.fcx_tune(b"gather_variant", -1)
     try:
-        for variant in (0, 1, 2, 2):  # 2 = gather_cell_kernel (thread per cell, 3-D 4-point rules; else as 1)
+        # 2 = gather_cell_kernel (thread per cell), 3 = gather_wq_kernel (warp-uniform point pair): 3-D 4-point
+        # rules only, otherwise as 1
+        for variant in (0, 1, 2, 3, 3):
             L.fcx_tune(b"gather_variant", variant)
             # u_prev fetched by the kernel (False) or subtracted first as a nodal vector (True, the default)
             for first in ((False, True) if with_prev else (True,)):
@@ -211,7 +213,7 @@ def test_gather_permutation_covariance():
     L = lib()
     old = L.fcx_tune(b"gather_variant", -1)
     try:
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             L.fcx_tune(b"gather_variant", variant)
             base = run(dofmap, dphi)
             assert np.abs(run(dofmap[:, pd], dphi[:, pd, :]) - base).max() <= 1e-13 * np.abs(base).max()

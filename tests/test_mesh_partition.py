@@ -119,3 +119,35 @@ def test_two_rank_halo_exchange_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok and glob_ok and tot == ref_tot
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("degree", [1, 2])
+def test_peer_memory_push_plan_reaches_the_right_slots(degree, world):
+    """The plan of the peer-memory ghost push (csrc/fcx_krylov.cu halo_push_kernel; MeshPartition.peer_local):
+    for every neighbour, peer_local[k][e] is the NEIGHBOUR's local index of the node this rank sends as entry
+    e.  Simulated on the host: every rank pushes the owned values of a global field into its neighbours'
+    vectors at those indices; afterwards every ghost slot of every rank holds its owner's value, every slot is
+    written exactly once, and no owned slot is touched."""
+    mesh = create_unit_cube(7, 3, 2)
+    parts = [MeshPartition(mesh, degree, r, world) for r in range(world)]
+    rng = np.random.default_rng(0)
+    field = rng.standard_normal(parts[0].global_space.num_nodes)
+    vecs, hits = [], []
+    for P in parts:
+        v = np.full(P.l2g.size, np.nan)
+        v[: P.num_owned_nodes] = field[P.l2g[: P.num_owned_nodes]]  # owned part known locally
+        vecs.append(v)
+        hits.append(np.zeros(P.l2g.size, dtype=int))
+    for P in parts:
+        assert len(P.peer_local) == len(P.neighbours)
+        for (s, snd, _), dst in zip(P.neighbours, P.peer_local):
+            assert dst.size == snd.size
+            assert np.all(snd < P.num_owned_nodes)                       # only owned values are sent
+            assert np.all(dst >= parts[s].num_owned_nodes)               # ... into ghost slots of the neighbour
+            assert np.array_equal(parts[s].l2g[dst], P.l2g[snd])         # the same mesh node on both sides
+            vecs[s][dst] = vecs[P.rank][snd]
+            hits[s][dst] += 1
+    for P, v, h in zip(parts, vecs, hits):
+        assert np.array_equal(v, field[P.l2g])                           # every ghost refreshed from its owner
+        assert np.all(h[: P.num_owned_nodes] == 0) and np.all(h[P.num_owned_nodes:] == 1)
