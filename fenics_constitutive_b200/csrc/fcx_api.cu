@@ -69,7 +69,9 @@ static int g_fem_variant = 1;
 // (gather_kernel), 2 = thread per cell with the basis-gradient table in the constant bank (gather_cell_kernel,
 // 3-D 4-point rules): bit-identical, but measured SLOWER on B200 (0.139 vs 0.104 ms for 998 250 P2 tets,
 // profiles/r2c_gather_ab.jsonl): its 1.1 KB of shared memory per cell caps an SM at 6 warps (ncu: 9 % occupancy,
-// issue slots 34 %, every stall a fixed-latency wait with nothing else to issue).
+// issue slots 34 %, every stall a fixed-latency wait with nothing else to issue); 3 = warp-uniform quadrature-point
+// pair with the table in the constant bank at the staged kernel's occupancy (gather_wq_kernel): 0.127 ms, slower too
+// (profiles/r2h_gather_ab.jsonl).
 static int g_gather_variant = 1;
 static int g_hints = 8;  // bit1: evict_first on bulk loads, bit2: on bulk stores,
                          // bit3: constant tangents written by bulk stores from shared memory
