@@ -17,6 +17,10 @@ from .. import _buffers as B
 from .._lib import check, lib
 
 
+class PeerMemoryUnavailable(RuntimeError):
+    """The ranks' GPUs cannot map each other's memory (raised on every rank together)."""
+
+
 class DeviceKrylov:
     def __init__(self, problem, partition=None):
         import torch
@@ -37,11 +41,22 @@ class DeviceKrylov:
         check(L.fcx_krylov_create(rank, world, problem.gdim, V.num_nodes, owned, ctypes.byref(h), ctypes.byref(comm),
                                   ipc), "fcx_krylov_create")
         self.handle = h
+        self._status = (ctypes.c_double * 4)()
         if world > 1:
             handles = [None] * world
             dist.all_gather_object(handles, bytes(ipc))
             flat = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
-            check(L.fcx_krylov_connect(h, flat), "fcx_krylov_connect")
+            rc = L.fcx_krylov_connect(h, flat)
+            # a rank that cannot open its peers' blocks (no P2P between the GPUs, IPC disabled) must not leave the
+            # others waiting in a spin: the outcome is agreed on collectively, and everybody raises or nobody
+            ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                L.fcx_krylov_destroy(h)
+                self.handle = None
+                raise PeerMemoryUnavailable(
+                    "device Krylov loop: CUDA IPC / peer access between the ranks' GPUs is not available "
+                    f"(rank {rank}: {L.fcx_last_cuda_error().decode() or 'ok here, failed on a peer'})")
             nbr = [s for s, _, _ in partition.neighbours]
             send_src = [np.asarray(snd, dtype=np.int32) for _, snd, _ in partition.neighbours]
             send_dst = [np.asarray(pl, dtype=np.int32) for pl in partition.peer_local]

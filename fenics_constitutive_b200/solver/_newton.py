@@ -255,8 +255,15 @@ class NewtonSolver:
         if self._device_krylov is None or self._device_krylov.problem is not self.problem:
             import time
 
+            from ._krylov import PeerMemoryUnavailable
+
             t0 = time.perf_counter()
-            self._device_krylov = DeviceKrylov(self.problem, self.partition)
+            try:
+                self._device_krylov = DeviceKrylov(self.problem, self.partition)
+            except PeerMemoryUnavailable as exc:  # raised on every rank together: fall back together
+                warnings.warn(f"{exc}; falling back to cg_driver='python' (NCCL)", RuntimeWarning, stacklevel=2)
+                self.cg_driver = "python"
+                return self._solve_cg(self.problem.J_apply, rhs, free_mask, diag, rtol)
             torch.cuda.synchronize()
             self.krylov_setup_s += time.perf_counter() - t0
         tol = self.cg_rtol if rtol is None else rtol

@@ -79,6 +79,51 @@ for degree, n in ((2, (12, 5, 4)), (1, (16, 6, 5))):
             assert [i[0] for i in its] == [i[0] for i in its_g]
         if world > 1:
             dist.barrier()
+# ---- twin of the reference's partition-independence test (tests/solver/test_solver_mpi.py:93-121): unit cube 4 x 6 x 7,
+# P1, q_degree 1, VonMises3D, left face clamped, right face pulled to 0.05 in load steps; the N-rank solution against the
+# one-rank solution in the relative L2 (here: nodal l2) norm.  The reference compares two PETSc LU solves (1e-14); here
+# both sides are Krylov solves driven to cg_rtol = 1e-14, so the difference is the round-off of two converged solves.
+mesh = S.create_unit_cube(4, 6, 7)
+nsteps = 20
+
+
+def run_ref_test(V, part):
+    u = S.Function(V, dev)
+    law = VonMises3D({"p_ka": 175000, "p_mu": 80769, "p_y0": 1200, "p_y00": 2500, "p_w": 200})
+    zero, ux = S.Constant(0.0), S.Constant(0.0)
+    bcs = [S.dirichletbc(zero, S.locate_dofs_geometrical(V, left), V),
+           S.dirichletbc(ux, S.locate_dofs_geometrical(V, right), V.sub(0)),
+           S.dirichletbc(zero, S.locate_dofs_geometrical(V, right), V.sub(1)),
+           S.dirichletbc(zero, S.locate_dofs_geometrical(V, right), V.sub(2))]
+    problem = S.IncrSmallStrainProblem(law, u, bcs, q_degree=1)
+    solver = S.NewtonSolver(None, problem)
+    solver.linear_solver = "cg"
+    solver.cg_rtol = 1e-14
+    solver.error_on_krylov_failure = False  # at 1e-14 the last solves may stall at round-off: that is the point
+    if part is not None:
+        part.attach(solver)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k in range(1, nsteps + 1):
+            ux.value = 0.05 * k / nsteps
+            solver.solve(u)
+            problem.update()
+    return u
+
+
+part = S.MeshPartition(mesh, 1, rank, world)
+u = run_ref_test(part.V, part)
+glob = part.gather_global(u.x.array.cpu().numpy())
+if rank == 0:
+    ref = run_ref_test(S.functionspace(mesh, ("CG", 1, (3,))), None).x.array.cpu().numpy()
+    err = np.linalg.norm(glob - ref) / np.linalg.norm(ref)
+    print(f"reference test_mpi_solver twin (4x6x7 P1, {nsteps} load steps to 0.05, cg_rtol 1e-14), world {world}: "
+          f"|u_world - u_self| / |u_self| = {err:.2e}", flush=True)
+    assert err < 1e-11, err
+if world > 1:
+    dist.barrier()
 if rank == 0:
     print("check_partitioned_newton: ok", flush=True)
 if world > 1:
