@@ -56,7 +56,8 @@ def run(V, part, steps, forcing, driver="device"):
     return u, problem, its
 
 
-for degree, n in ((2, (12, 5, 4)), (1, (16, 6, 5))):
+ONLY_TWIN = "--only-twin" in sys.argv
+for degree, n in (() if ONLY_TWIN else ((2, (12, 5, 4)), (1, (16, 6, 5)))):
     mesh = S.create_unit_cube(*n)
     for forcing, driver in ((None, "device"), ("eisenstat-walker", "device"), (None, "python")):
         part = S.MeshPartition(mesh, degree, rank, world)
@@ -100,6 +101,8 @@ def run_ref_test(V, part):
     solver.linear_solver = "cg"
     solver.cg_rtol = 1e-14
     solver.error_on_krylov_failure = False  # at 1e-14 the last solves may stall at round-off: that is the point
+    solver.rtol, solver.atol = 1e-13, 1e-11  # Newton driven to round-off too (dolfinx default 1e-9 leaves 1e-11 in u)
+    solver.error_on_nonconvergence = False
     if part is not None:
         part.attach(solver)
     import warnings
@@ -121,7 +124,7 @@ if rank == 0:
     err = np.linalg.norm(glob - ref) / np.linalg.norm(ref)
     print(f"reference test_mpi_solver twin (4x6x7 P1, {nsteps} load steps to 0.05, cg_rtol 1e-14), world {world}: "
           f"|u_world - u_self| / |u_self| = {err:.2e}", flush=True)
-    assert err < 1e-11, err
+    assert err < 1e-14, err  # the reference's bar (test_solver_mpi.py:118-121)
 if world > 1:
     dist.barrier()
 if rank == 0:
