@@ -376,6 +376,9 @@ class IncrSmallStrainProblem:
 
         if out is None:
             out = torch.empty(self.V.num_dofs, dtype=torch.float64, device=self.device)
+        if self.fused and not self.dense_tangent:
+            raise RuntimeError("J_diag reads the dense tangent array: keep IncrSmallStrainProblem.dense_tangent = True "
+                               "(the default) when a solver needs the Jacobi diagonal")
         L = lib()
         g, s, nc, nq, nd = self._tables_args()
         check(L.fcx_tangent_diag(g, s, nc, nq, nd, self._dphi.data_ptr(), self._weights.data_ptr(),
