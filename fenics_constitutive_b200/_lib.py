@@ -55,7 +55,7 @@ SIGNATURES = {
     "fcx_krylov_create": (_ci, [_ci, _ci, _ci, _sz, _sz, _vp, _vp, _vp]),
     "fcx_krylov_connect": (_ci, [_vp, _vp]),
     "fcx_krylov_set_halo": (_ci, [_vp, _ci, _vp, _vp, _vp, _vp]),
-    "fcx_krylov_set_operator": (_ci, [_vp, _ci, _ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp, _vp]),
+    "fcx_krylov_set_operator": (_ci, [_vp, _ci, _ci, _sz, _ci, _ci, _vp, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp, _vp, _sz]),
     "fcx_krylov_begin": (_ci, [_vp, _dp, _dp, _vp]),
     "fcx_krylov_iterate": (_ci, [_vp, _ci, _vp]),
     "fcx_krylov_status": (_ci, [_vp, _vp]),

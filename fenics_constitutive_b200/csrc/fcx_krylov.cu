@@ -18,9 +18,11 @@
 //     K3  cg_update_kernel      p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;
 //                               u = minv r
 //     K4  halo_push_kernel      u of the nodes that are ghosts elsewhere is stored straight into the
-//                               neighbours' vectors; a system-scope flag tells them; then waits for
-//                               the neighbours' flags (so K1 of the next iteration reads fresh ghosts);
-//                               also used at the start of a solve and by fcx_krylov_halo_update
+//                               neighbours' vectors; a system-scope flag tells them.  The WAIT for the
+//                               neighbours' flags is a one-thread kernel that the next iteration issues
+//                               BEHIND its interior cells (K1 runs on the cells that touch no ghost node
+//                               first, MeshPartition orders them first), so the exchange hides behind
+//                               ~90 % of the element work; then K1 on the boundary cells
 // with  gamma = r.u, delta = w.u:  beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)
 // -- ONE reduction per iteration instead of two, one fused vector pass instead of three kernels.
 // Four launches per iteration (three on one rank); fcx_krylov_iterate enqueues a block of iterations from C; the host looks at the residual history
@@ -97,6 +99,9 @@ struct Krylov {
     double *fe = nullptr;
     // progress
     unsigned long long epoch = 0;  // reductions / pushes done since creation (same on every rank)
+    unsigned long long push_epoch = 0;  // epoch of the last ghost push
+    bool push_waited = true;            // ... and whether the neighbours' pushes of that epoch have been waited for
+    size_t ncells_interior = 0;         // local cells [0, ncells_interior) touch no ghost node
     unsigned long long it = 0;     // iterations of the current solve
     unsigned grid = 1;
 };
@@ -285,19 +290,14 @@ __global__ void __launch_bounds__(KR_THREADS)
     }
 }
 
-// K3: fused vector update with the alpha / beta K2 left in `scal`, then -- by the last CTA to finish -- the
-// ghost push of the new matvec input: owned values that are ghosts elsewhere are stored straight into the
-// neighbours' vectors, a system-scope flag tells them, and the CTA waits for the neighbours' flags of the same
-// epoch (so K1 of the next iteration reads fresh ghosts).  u is written on OWNED dofs only: a faster neighbour
-// may already have stored this iteration's ghost values.
+// K3: fused vector update with the alpha / beta K2 left in `scal`.  u is written on OWNED dofs only: a faster
+// neighbour may already have stored this iteration's ghost values.  (Folding the ghost push into this kernel's
+// tail -- the last CTA to finish stores all send entries -- was measured: 24 k nodes x 3 peer stores from ONE
+// CTA cost 0.23 ms per iteration on two GPUs, 0.55 vs 0.32 ms; the push has its own full-grid kernel.)
 __global__ void __launch_bounds__(KR_THREADS)
     cg_update_kernel(size_t n, size_t n_owned, double *__restrict__ x, double *__restrict__ r, double *__restrict__ u,
                      const double *__restrict__ w, double *__restrict__ p, double *__restrict__ s,
-                     const double *__restrict__ minv, const double *__restrict__ scal, int gdim,
-                     const int *__restrict__ send_src, const int *__restrict__ send_dst,
-                     const int *__restrict__ send_nbr, int n_send, PeerPtrs nbr_base, CommLayout lay, int n_nbr,
-                     int rank, char *comm, const int *__restrict__ nbr_rank_dev, unsigned *ticket,
-                     unsigned long long epoch, int *err)
+                     const double *__restrict__ minv, const double *__restrict__ scal)
 {
     const double alpha = scal[0], beta = scal[1];
     const size_t n2 = n / 2;
@@ -336,35 +336,6 @@ __global__ void __launch_bounds__(KR_THREADS)
         if (i < n_owned)
             u[i] = un;
     }
-    if (n_nbr == 0)
-        return;
-    // ---- ghost push by the last CTA to finish ----
-    __shared__ bool last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0)
-        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last)
-        return;
-    __threadfence();
-    for (int e = threadIdx.x; e < n_send; e += KR_THREADS) {
-        double *dst = reinterpret_cast<double *>(nbr_base.base[send_nbr[e]] + lay.off_u) + (size_t)send_dst[e] * gdim;
-        const double *src = u + (size_t)send_src[e] * gdim;
-        for (int j = 0; j < gdim; ++j)
-            dst[j] = __ldcg(src + j);  // written by other SMs in this launch: read it from L2
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        for (int k = 0; k < n_nbr; ++k)
-            st_flag(reinterpret_cast<unsigned long long *>(nbr_base.base[k] + lay.off_haloflag) + rank, epoch);
-        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(comm + lay.off_haloflag);
-        for (int k = 0; k < n_nbr; ++k)
-            wait_flag(mine + nbr_rank_dev[k], epoch, false, err);
-        *ticket = 0;
-    }
 }
 
 // K4: owned values that are ghosts elsewhere -> the neighbours' u vectors (peer stores), then the
@@ -374,7 +345,7 @@ __global__ void __launch_bounds__(KR_THREADS)
     halo_push_kernel(const double *__restrict__ u, const int *__restrict__ send_src, const int *__restrict__ send_dst,
                      const int *__restrict__ send_nbr, int n_send, PeerPtrs nbr_base, CommLayout lay, int n_nbr,
                      int rank, char *comm, const int *__restrict__ nbr_rank_dev, unsigned *ticket,
-                     unsigned long long epoch, int *err)
+                     unsigned long long epoch, int do_wait, int *err)
 {
     __shared__ bool last;
     const int stride = gridDim.x * blockDim.x;
@@ -395,9 +366,21 @@ __global__ void __launch_bounds__(KR_THREADS)
         for (int k = 0; k < n_nbr; ++k)
             st_flag(reinterpret_cast<unsigned long long *>(nbr_base.base[k] + lay.off_haloflag) + rank, epoch);
         const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(comm + lay.off_haloflag);
+        if (do_wait)
+            for (int k = 0; k < n_nbr; ++k)
+                wait_flag(mine + nbr_rank_dev[k], epoch, false, err);
+        *ticket = 0;
+    }
+}
+
+// The wait half of a push issued with do_wait = 0: one thread, until every neighbour's flag has reached `epoch`.
+__global__ void halo_wait_kernel(const char *comm, CommLayout lay, int n_nbr, const int *__restrict__ nbr_rank_dev,
+                                 unsigned long long epoch, int *err)
+{
+    if (threadIdx.x == 0) {
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(comm + lay.off_haloflag);
         for (int k = 0; k < n_nbr; ++k)
             wait_flag(mine + nbr_rank_dev[k], epoch, false, err);
-        *ticket = 0;
     }
 }
 
@@ -417,10 +400,12 @@ static unsigned kr_grid(size_t work)
     return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
-static int kr_push(Krylov *K, cudaStream_t st)
+static int kr_push(Krylov *K, cudaStream_t st, int do_wait = 1)
 {
     if (K->world == 1 || K->n_nbr == 0)
         return FCX_OK;
+    K->push_epoch = K->epoch;
+    K->push_waited = do_wait != 0;
     PeerPtrs nb{};
     for (int k = 0; k < K->n_nbr; ++k)
         nb.base[k] = K->peers.base[K->nbr_rank[k]];
@@ -431,7 +416,7 @@ static int kr_push(Krylov *K, cudaStream_t st)
 #define FCX_PUSH(G) \
     halo_push_kernel<G><<<grid, KR_THREADS, 0, st>>>(u, K->send_src, K->send_dst, K->send_nbr, K->n_send, nb, K->lay, \
                                                      K->n_nbr, K->rank, K->comm, nbr_rank_dev, K->ticket + 1, K->epoch, \
-                                                     K->err)
+                                                     do_wait, K->err)
     if (K->gdim == 1)
         FCX_PUSH(1);
     else if (K->gdim == 2)
@@ -441,6 +426,17 @@ static int kr_push(Krylov *K, cudaStream_t st)
 #undef FCX_PUSH
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return note_cuda_error(cudaGetLastError(), "halo_push_kernel launch");
+}
+
+// Wait for the neighbours' pushes of the last epoch this rank pushed without waiting.
+static int kr_wait(Krylov *K, cudaStream_t st)
+{
+    if (K->world == 1 || K->n_nbr == 0 || K->push_waited)
+        return FCX_OK;
+    halo_wait_kernel<<<1, 32, 0, st>>>(K->comm, K->lay, K->n_nbr, K->send_nbr + K->n_send, K->push_epoch, K->err);
+    K->push_waited = true;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return note_cuda_error(cudaGetLastError(), "halo_wait_kernel launch");
 }
 
 }  // namespace fcx
@@ -573,7 +569,7 @@ int fcx_krylov_set_halo(void *handle, int n_nbr, const int *nbr_rank, const int 
 int fcx_krylov_set_operator(void *handle, int mode, int sdim, size_t ncells, int nq, int nd, const int *dofmap,
                             const double *dphi_ref, const double *weights, const double *Jinv, const double *detJ,
                             const double *tangent, double *fe, const int *fe_pos, const long long *adj_ptr,
-                            const int *adj_idx)
+                            const int *adj_idx, size_t ncells_interior)
 {
     Krylov *K = static_cast<Krylov *>(handle);
     if (!K || !dofmap || !dphi_ref || !weights || !Jinv || !detJ || !tangent || !fe || !adj_ptr)
@@ -595,6 +591,7 @@ int fcx_krylov_set_operator(void *handle, int mode, int sdim, size_t ncells, int
     K->fe_pos = fe_pos;
     K->adj_ptr = adj_ptr;
     K->adj_idx = fe_pos != nullptr ? nullptr : adj_idx;
+    K->ncells_interior = ncells_interior <= ncells ? ncells_interior : ncells;  // ncells = no split
     return FCX_OK;
 }
 
@@ -607,6 +604,8 @@ int fcx_krylov_begin(void *handle, const double *rhs, const double *minv, void *
         return FCX_ERR_NULL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *u = reinterpret_cast<double *>(K->comm + K->lay.off_u);
+    if (int rc = kr_wait(K, st))  // a previous solve's last push is still owed its wait
+        return rc;
     kr_begin_kernel<<<kr_grid(K->n), KR_THREADS, 0, st>>>(K->n, K->n_owned, rhs, minv, K->minv, K->x, K->r, u, K->p, K->s);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
@@ -614,7 +613,7 @@ int fcx_krylov_begin(void *handle, const double *rhs, const double *minv, void *
         return note_cuda_error(e, "kr_begin_kernel launch");
     K->it = 0;
     K->epoch += 1;
-    return kr_push(K, st);
+    return kr_push(K, st, 0);  // the first iteration waits, behind its interior cells
 }
 
 /* Enqueue `iters` iterations (K1..K4 each) on `stream`; never synchronises. */
@@ -628,12 +627,31 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *u = reinterpret_cast<double *>(K->comm + K->lay.off_u);
     const unsigned ggrid = kr_grid(K->nnodes);
+    // element kernel over the local cells [c0, c0 + nc)
+    auto element_kernel = [&](size_t c0, size_t nc) -> int {
+        if (nc == 0)
+            return FCX_OK;
+        const int fs = K->gdim == 3 ? 4 : K->gdim;
+        const int rl = K->op_mode == 3 ? 10 : K->sdim * K->sdim;  // tangent doubles per quadrature point
+        const int *pos = K->fe_pos ? K->fe_pos + c0 * K->nd : nullptr;
+        double *fe = K->fe_pos ? K->fe : K->fe + c0 * K->nd * fs;
+        return K->op_mode == 3
+                   ? fcx_tangent_apply_rec(K->gdim, K->sdim, nc, K->nq, K->nd, K->dofmap + c0 * K->nd, u, K->dphi,
+                                           K->weights, K->Jinv + c0 * K->gdim * K->gdim, K->detJ + c0,
+                                           K->tang + c0 * K->nq * rl, fe, pos, stream)
+                   : fcx_tangent_apply(K->gdim, K->sdim, nc, K->nq, K->nd, K->dofmap + c0 * K->nd, u, K->dphi,
+                                       K->weights, K->Jinv + c0 * K->gdim * K->gdim, K->detJ + c0,
+                                       K->tang + c0 * K->nq * rl, fe, pos, stream);
+    };
     for (int k = 0; k < iters; ++k) {
-        int rc = K->op_mode == 3
-                     ? fcx_tangent_apply_rec(K->gdim, K->sdim, K->ncells, K->nq, K->nd, K->dofmap, u, K->dphi, K->weights,
-                                             K->Jinv, K->detJ, K->tang, K->fe, K->fe_pos, stream)
-                     : fcx_tangent_apply(K->gdim, K->sdim, K->ncells, K->nq, K->nd, K->dofmap, u, K->dphi, K->weights,
-                                         K->Jinv, K->detJ, K->tang, K->fe, K->fe_pos, stream);
+        // K1: cells that touch no ghost node first -- the neighbours' ghost stores of the previous update arrive
+        // behind them; then the wait (one thread), then the boundary cells
+        const size_t n_int = (K->world > 1 && K->n_nbr > 0) ? K->ncells_interior : K->ncells;
+        int rc = element_kernel(0, n_int);
+        if (rc == FCX_OK)
+            rc = kr_wait(K, st);
+        if (rc == FCX_OK)
+            rc = element_kernel(n_int, K->ncells - n_int);
         if (rc != FCX_OK)
             return rc;
         K->epoch += 1;
@@ -649,24 +667,13 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
         else
             FCX_GSUM(3);
 #undef FCX_GSUM
-        PeerPtrs nb{};
-        for (int q = 0; q < K->n_nbr; ++q)
-            nb.base[q] = K->peers.base[K->nbr_rank[q]];
-        // ghost push: its own kernel (K4) over a full grid.  Folding it into the tail of K3 (the last CTA to
-        // finish stores all send entries) was measured: 24 k nodes x 3 peer stores from ONE CTA cost 0.23 ms
-        // per iteration on two GPUs (0.55 vs 0.32 ms, profiles/r2e_*), so K3's tail is switched off (n_nbr = 0)
-        const int n_nbr = 0;
-        cg_update_kernel<<<K->grid, KR_THREADS, 0, st>>>(K->n, K->n_owned, K->x, K->r, u, K->w, K->p, K->s, K->minv, K->scal,
-                                                         K->gdim, K->send_src, K->send_dst, K->send_nbr, K->n_send, nb,
-                                                         K->lay, n_nbr, K->rank, K->comm,
-                                                         n_nbr > 0 ? K->send_nbr + K->n_send : nullptr, K->ticket + 1,
-                                                         K->epoch, K->err);
+        cg_update_kernel<<<K->grid, KR_THREADS, 0, st>>>(K->n, K->n_owned, K->x, K->r, u, K->w, K->p, K->s, K->minv, K->scal);
         g_launches.fetch_add(2, std::memory_order_relaxed);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess)
             return note_cuda_error(e, "krylov iteration launch");
         K->it += 1;
-        rc = kr_push(K, st);
+        rc = kr_push(K, st, 0);  // push and go on: the wait sits behind the next iteration's interior cells
         if (rc != FCX_OK)
             return rc;
     }
@@ -686,9 +693,12 @@ int fcx_krylov_halo_update(void *handle, double *x, void *stream)
         return FCX_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *u = reinterpret_cast<double *>(K->comm + K->lay.off_u);
+    int rc = kr_wait(K, st);  // the last iteration's push is still owed its wait
+    if (rc != FCX_OK)
+        return rc;
     kr_copy_kernel<<<kr_grid(K->n_owned), KR_THREADS, 0, st>>>(0, K->n_owned, x, u);
     K->epoch += 1;
-    int rc = kr_push(K, st);
+    rc = kr_push(K, st, 1);
     if (rc != FCX_OK)
         return rc;
     kr_copy_kernel<<<kr_grid(K->n - K->n_owned + 1), KR_THREADS, 0, st>>>(K->n_owned, K->n, u, x);

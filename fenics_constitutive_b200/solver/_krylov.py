@@ -69,6 +69,9 @@ class DeviceKrylov:
                                         np.ascontiguousarray(src).ctypes.data, np.ascontiguousarray(dst).ctypes.data),
                   "fcx_krylov_set_halo")
             dist.barrier()  # every rank has opened every block before anyone stores into one
+        # local cells [0, num_interior_cells) touch no ghost node (MeshPartition orders them first)
+        self.num_interior_cells = (partition.num_interior_cells if partition is not None and world > 1
+                                   else problem.num_cells)
         self._x = torch.empty(V.num_dofs, dtype=torch.float64, device=self.device)
         self._status = (ctypes.c_double * 4)()
 
@@ -81,8 +84,8 @@ class DeviceKrylov:
         check(L.fcx_krylov_set_operator(
             self.handle, 3 if rec else 1, pb.sdim, pb.num_cells, T.nq, T.nd, pb._dofmap.data_ptr(),
             pb._dphi.data_ptr(), pb._weights.data_ptr(), pb._Jinv.data_ptr(), pb._detJ.data_ptr(), tang.data_ptr(),
-            pb._fe.data_ptr(), pos, pb._adj_ptr.data_ptr(), None if pos is not None else pb._adj_idx.data_ptr()),
-            "fcx_krylov_set_operator")
+            pb._fe.data_ptr(), pos, pb._adj_ptr.data_ptr(), None if pos is not None else pb._adj_idx.data_ptr(),
+            self.num_interior_cells), "fcx_krylov_set_operator")
 
     def solve(self, rhs, minv, rtol: float, max_it: int, check_every: int):
         """Solve J x = rhs on the dofs where minv != 0.  Returns (x, iterations, converged, relres, breakdown);

@@ -66,7 +66,13 @@ class MeshPartition:
             return cells, owned, ghost
 
         cells, owned, ghost = local_sets(rank)
-        self.local_cells = cells                      # global cell ids, ascending
+        # INTERIOR cells (all nodes owned by this rank) first, then the cells that touch a ghost node, each in
+        # ascending global order: the Krylov loop runs its element kernel on the interior cells while the
+        # neighbours' ghost values are still on their way (csrc/fcx_krylov.cu)
+        interior = (owner_of_cell_nodes[cells] == rank).all(axis=1)
+        cells = np.concatenate([cells[interior], cells[~interior]])
+        self.num_interior_cells = int(interior.sum())
+        self.local_cells = cells                      # global cell ids: interior (ascending), boundary (ascending)
         self.num_owned_cells = int((cell_owner[cells] == rank).sum())
         self.l2g = np.concatenate([owned, ghost])     # local node -> global node
         self.num_owned_nodes = int(owned.size)

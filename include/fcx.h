@@ -304,10 +304,13 @@ int fcx_pcg_update_p(size_t n, double *p, const double *r, const double *minv, c
  *   fcx_krylov_connect   handles of all ranks (world x 64 bytes, rank order)
  *   fcx_krylov_set_halo  per neighbour: my local nodes to send and the neighbour's local index of each
  *   fcx_krylov_set_operator  the Jacobian action: arguments of fcx_tangent_apply_rec (mode 3) or
- *                        fcx_tangent_apply (mode 1) and the adjacency of fcx_gather_sum
+ *                        fcx_tangent_apply (mode 1) and the adjacency of fcx_gather_sum; the local cells
+ *                        [0, ncells_interior) touch no ghost node -- the element kernel runs on them while the
+ *                        neighbours' ghost stores arrive, then waits, then runs on the rest (pass ncells for
+ *                        no split)
  *   fcx_krylov_begin     x = 0, r = rhs where minv != 0 (minv = inverse Jacobi diagonal, 0 on constrained
  *                        AND ghost dofs), first ghost push
- *   fcx_krylov_iterate   enqueue `iters` iterations (4 launches each, 3 on one rank); never synchronises
+ *   fcx_krylov_iterate   enqueue `iters` iterations (6 launches each, 3 on one rank); never synchronises
  *   fcx_krylov_status    (after a stream synchronisation) out[0] iterations done, out[1] r.r at the start
  *                        of the last one, out[2] r.r of the right-hand side, out[3] 1 = breakdown (p.Ap <= 0),
  *                        2 = a peer rank never arrived (bounded spin timed out)
@@ -320,7 +323,7 @@ int fcx_krylov_set_halo(void *handle, int n_nbr, const int *nbr_rank, const int 
 int fcx_krylov_set_operator(void *handle, int mode, int sdim, size_t ncells, int nq, int nd, const int *dofmap,
                             const double *dphi_ref, const double *weights, const double *Jinv, const double *detJ,
                             const double *tangent, double *fe, const int *fe_pos, const long long *adj_ptr,
-                            const int *adj_idx);
+                            const int *adj_idx, size_t ncells_interior);
 int fcx_krylov_begin(void *handle, const double *rhs, const double *minv, void *stream);
 int fcx_krylov_iterate(void *handle, int iters, void *stream);
 int fcx_krylov_status(void *handle, double *out4);
