@@ -233,24 +233,30 @@ __global__ void __launch_bounds__(KR_THREADS)
         last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x < 3) {
-        __threadfence();
-        double acc = 0.0;
-        const volatile double *src = partials + (size_t)threadIdx.x * gridDim.x;
-        for (unsigned b = 0; b < gridDim.x; ++b)
-            acc += src[b];
+    if (!last)
+        return;
+    // The last CTA adds the CTA partials: thread t takes partials t, t + 256, ... (in that order), then the
+    // fixed shuffle / shared-memory tree of kr_block_sum -- the same order every run and on every rank, so the
+    // sums are reproducible bit for bit.  (Three threads walking all 8 x SMs partials one dependent L2 load
+    // after the other cost 0.04 ms of the 0.466 ms iteration on one GPU, profiles/r2k_newton55_device_n1.json.)
+    __threadfence();
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += KR_THREADS) {
+        a0 += ld_volatile(partials + b);
+        a1 += ld_volatile(partials + gridDim.x + b);
+        a2 += ld_volatile(partials + 2 * (size_t)gridDim.x + b);
+    }
+    const double s0 = kr_block_sum(a0, sh), s1 = kr_block_sum(a1, sh), s2 = kr_block_sum(a2, sh);
+    if (threadIdx.x == 0) {
         // all-gather of the local sums: one slot per (parity, source rank) in EVERY rank's block
         const int par = (int)(epoch & 1ULL);
         for (int t = 0; t < world; ++t) {
             double *slot = reinterpret_cast<double *>(peers.base[t] + lay.off_red) + ((size_t)par * world + rank) * 4;
-            slot[threadIdx.x] = acc;
+            slot[0] = s0;
+            slot[1] = s1;
+            slot[2] = s2;
         }
         __threadfence_system();
-    }
-    __syncthreads();
-    if (last && threadIdx.x == 0) {
-        __threadfence_system();
-        const int par = (int)(epoch & 1ULL);
         for (int t = 0; t < world; ++t) {
             unsigned long long *flag =
                 reinterpret_cast<unsigned long long *>(peers.base[t] + lay.off_redflag) + (size_t)par * world + rank;

@@ -13,7 +13,7 @@ namespace fcx {
 // one ulp below the correctly rounded 1/sqrt(2).
 __device__ __forceinline__ double shear_factor() { return 0x1.6a09e667f3bccp-1; }
 // np.sqrt(2 / 3)
-__device__ __forceinline__ double sqrt23() { return 0x1.a20bd700c2c3ep-1; }
+__host__ __device__ __forceinline__ double sqrt23() { return 0x1.a20bd700c2c3ep-1; }
 
 // fc/models/utils.py:132-208 (strain_from_grad_u), one QP.
 template <int S, int G>
@@ -712,7 +712,7 @@ struct DruckerPragerModel {
     };
 
     // set_model_state (classic :75-108, hyperbolic :64-102)
-    __device__ static __forceinline__ void state(const Params &P, const double *sg, double bfe, State &S)
+    __host__ __device__ static __forceinline__ void state(const Params &P, const double *sg, double bfe, State &S)
     {
         const double i_1 = (sg[0] + sg[1]) + sg[2];
         const double m = i_1 / 3.0;
@@ -741,7 +741,7 @@ struct DruckerPragerModel {
         S.gn = sqrt(gsq);
     }
 
-    __device__ static __forceinline__ double normsq6(const double *x)
+    __host__ __device__ static __forceinline__ double normsq6(const double *x)
     {
         double acc = 0.0;
 #pragma unroll
@@ -761,7 +761,7 @@ struct DruckerPragerModel {
     static constexpr __host__ __device__ bool two_phase() { return false; }
 
     template <class V>
-    __device__ static __forceinline__ bool trial(const Params &P, const V &v, double *aux, int t,
+    __host__ __device__ static __forceinline__ bool trial(const Params &P, const V &v, double *aux, int t,
                                                  bool &plastic, bool &failed)
     {
         double g[9], sig0[6];
@@ -806,7 +806,7 @@ struct DruckerPragerModel {
     }
 
     template <class V>
-    __device__ static __forceinline__ void qp(const Params &P, const V &v, double *aux, int t,
+    __host__ __device__ static __forceinline__ void qp(const Params &P, const V &v, double *aux, int t,
                                               bool &plastic, bool &failed)
     {
         double g[9], sig0[6], hist[7];
@@ -983,7 +983,7 @@ struct DruckerPragerModel {
     }
 
     // M_ij = [vol block] + m1 delta_ij + A3 s_i s_j + A4 1_i s_j + A5 s_i 1_j
-    __device__ static __forceinline__ double entry(const double *rec, int i, int j)
+    __host__ __device__ static __forceinline__ double entry(const double *rec, int i, int j)
     {
         const bool vi = i < 3, vj = j < 3, diag = (i == j);
         const double base = (vi && vj) ? (diag ? rec[0] : rec[1]) : (diag ? rec[2] : 0.0);

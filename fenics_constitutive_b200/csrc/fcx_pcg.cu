@@ -7,7 +7,7 @@
 //
 // All scalars stay on the device.  Reductions are DETERMINISTIC: every CTA writes
 // its partial sum to `partials`, the last CTA to finish (atomic ticket) adds them
-// in index order -- no floating-point atomics, same result run to run (cf. the
+// in a fixed order -- no floating-point atomics, same result run to run (cf. the
 // reference's partition-independence test, tests/solver/test_solver_mpi.py:93-121).
 //
 // `minv` is the inverse Jacobi diagonal with ZERO on constrained (Dirichlet) dofs;
@@ -42,10 +42,13 @@ __device__ __forceinline__ double block_sum(double v, double *sh)
     return t;  // valid in thread 0
 }
 
-// Last CTA adds partials[k * gridDim.x + b] over b in order, for k < NOUT.
+// The last CTA to finish adds partials[k * gridDim.x + b] over b, for k < NOUT: thread t takes b = t,
+// t + 256, ... in that order, then the fixed tree of block_sum -- the same order every run.  (One thread
+// per output walking all partials, one dependent L2 load after the other, cost tens of microseconds per
+// launch with 8 x SMs CTAs.)
 template <int NOUT>
 __device__ __forceinline__ void finish_reduction(const double *mine, double *partials, double *out,
-                                                 unsigned *ticket)
+                                                 unsigned *ticket, double *sh)
 {
     __shared__ bool last;
     if (threadIdx.x == 0) {
@@ -57,16 +60,21 @@ __device__ __forceinline__ void finish_reduction(const double *mine, double *par
         last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (last && threadIdx.x < NOUT) {
-        __threadfence();
+    if (!last)
+        return;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+        const volatile double *src = partials + (size_t)k * gridDim.x;
         double acc = 0.0;
-        const volatile double *src = partials + (size_t)threadIdx.x * gridDim.x;
-        for (unsigned b = 0; b < gridDim.x; ++b)
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += PCG_THREADS)
             acc += src[b];
-        out[threadIdx.x] = acc;
+        const double tot = block_sum(acc, sh);
         if (threadIdx.x == 0)
-            *ticket = 0;  // ready for the next launch on this stream
+            out[k] = tot;
     }
+    if (threadIdx.x == 0)
+        *ticket = 0;  // ready for the next launch on this stream
 }
 
 // The reduction kernels read 16 bytes per access, two pairs per trip with independent
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(PCG_THREADS)
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
         acc0 = fma(minv[n - 1] != 0.0 ? p[n - 1] : 0.0, Ap[n - 1], acc0);
     double mine[1] = {block_sum((acc0 + acc1) + (acc2 + acc3), sh)};
-    finish_reduction<1>(mine, partials, out, ticket);
+    finish_reduction<1>(mine, partials, out, ticket, sh);
 }
 
 // alpha = rz / pAp (0 if pAp <= 0);  x += alpha p;  r -= alpha Ap  (free dofs; r is and stays 0
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(PCG_THREADS)
     double mine[2];
     mine[0] = block_sum(s0 + s1, sh);
     mine[1] = block_sum(q0 + q1, sh);
-    finish_reduction<2>(mine, partials, out, ticket);
+    finish_reduction<2>(mine, partials, out, ticket, sh);
 }
 
 // p = minv r + (rz_new / rz) p   (beta = 0 if rz <= 0)

@@ -635,7 +635,10 @@ def test_device_krylov_driver_equals_python_driver(forcing):
     (ia, ua, sa, pa), (ib, ub, sb, _) = sols
     assert ia == ib
     assert 0.05 < pa < 1.0
-    assert np.abs(ua - ub).max() <= 1e-8 * np.abs(ub).max()
+    # fixed Krylov tolerance (1e-11): the two solves agree to it.  Inexact Newton (Eisenstat-Walker): the two PCG
+    # variants stop their loose linear solves at different iterates, so the Newton paths differ and agree only to
+    # the Newton stop rule (residual rtol 1e-9) -- the bar scripts/check_partitioned_newton.py uses as well
+    assert np.abs(ua - ub).max() <= (1e-8 if forcing is None else 1e-7) * np.abs(ub).max()
     assert np.abs(sa - sb).max() <= 1e-6 * np.abs(sb).max()
 
 
