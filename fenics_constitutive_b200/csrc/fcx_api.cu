@@ -62,6 +62,9 @@ static int g_mises_tile = 64;  // QPs per tile of the output-staged kernel (64 o
 // (fcx_tile_kernel<MisesModel, 128, false>), 1 = single-stage output-staged kernel without the tangent
 // region.  Measured on B200, 16 M QPs (profiles/r2a_tune_stress_only.jsonl): 0.75 vs 0.80 ms.
 static int g_mises_so_variant = 0;
+// Drucker-Prager kernels: 1 = slow fp64 operations spelled for latency (DruckerPragerModel VAR 1, the
+// default), 0 = the reference's spelling (VAR 0)
+static int g_dp_variant = 1;
 // Hand tiles out through an atomic ticket counter (all tile kernels).
 static int g_dynamic_tiles = 1;
 static int g_fem_variant = 1;
@@ -540,6 +543,12 @@ int fcx_tune(const char *key, int value)
         g_mises_variant = value;
         return old;
     }
+    if (key && strcmp(key, "dp_variant") == 0) {
+        const int old = g_dp_variant;
+        if (value == 0 || value == 1)
+            g_dp_variant = value;
+        return old;
+    }
     if (key && strcmp(key, "mises_so_variant") == 0) {
         if (value != 0 && value != 1)
             return FCX_ERR_ARG;
@@ -684,9 +693,14 @@ int fcx_drucker_prager_evaluate(int hyperbolic, const double *params, size_t n, 
     SegPtrs<3> io{{const_cast<double *>(grad), stress, history}};
     const bool al = aligned16(grad) && aligned16(stress) && aligned16(tangent) && aligned16(history);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g_dp_variant == 0) {  // the reference's spelling of every division / square root (A/B only)
+        if (hyperbolic)
+            return launch_tile<DruckerPragerModel<true, 0>>(P, io, tangent, n, al, plastic_flag, status, st);
+        return launch_tile<DruckerPragerModel<false, 0>>(P, io, tangent, n, al, plastic_flag, status, st);
+    }
     if (hyperbolic)
-        return launch_tile<DruckerPragerModel<true>>(P, io, tangent, n, al, plastic_flag, status, st);
-    return launch_tile<DruckerPragerModel<false>>(P, io, tangent, n, al, plastic_flag, status, st);
+        return launch_tile<DruckerPragerModel<true, 1>>(P, io, tangent, n, al, plastic_flag, status, st);
+    return launch_tile<DruckerPragerModel<false, 1>>(P, io, tangent, n, al, plastic_flag, status, st);
 }
 
 int fcx_mises_form(const double *params, size_t ncells, const int *cells, int nq, int nd, const int *dofmap,

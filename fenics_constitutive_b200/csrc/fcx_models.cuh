@@ -688,9 +688,40 @@ struct DruckerPragerParams {
     double apex;  // a / b
 };
 
-template <bool HYP>
+//
+// VAR selects how the slow fp64 operations (division, square root: 20-30 instructions and ~60-80 cycles of
+// dependent latency each on sm_100a) are spelled.  The kernel is latency-bound on exactly those chains (ncu,
+// profiles/r1t_rs_ncu_full.json: 3 warps per scheduler, 2.8 cycles of fixed-latency stall per issue), so
+//   VAR 0  the reference's spelling, operation for operation: x / 3.0, sqrt then 1 / r, one division per
+//          quotient -- 51 slow operations for a plastic point with four Newton steps;
+//   VAR 1  the same algorithm -- same iterates, same stop rule -- with x * (1/3), r = x * rsqrt(x), one
+//          reciprocal of opa * den for both quotients of the step, reciprocals instead of repeated divisions
+//          in the tangent and the commit: 24 slow operations, results within a few ulp of VAR 0 (the model's
+//          tolerance against the restated Rust algorithm is 1e-10; tests/test_dp_host_harness.py checks both
+//          variants on the host, tests/test_drucker_prager.py on the GPU).
+template <bool HYP, int VAR = 1>
 struct DruckerPragerModel {
     using Params = DruckerPragerParams;
+    static constexpr bool FAST = VAR != 0;
+    __host__ __device__ static __forceinline__ double third(double x) { return FAST ? x * (1.0 / 3.0) : x / 3.0; }
+    // a * b + c: fused in VAR 1 (the library is compiled with -fmad=false so that the Python models' kernels
+    // round like numpy; this model's tolerance is 1e-10 against a restated algorithm, and ncu counted 4 unfused
+    // fp64 instructions for every fused one)
+    __host__ __device__ static __forceinline__ double mad(double a, double b, double c)
+    {
+        return FAST ? fma(a, b, c) : a * b + c;
+    }
+    // r = sqrt(x), inv_r = 1 / r  (x >= 0; x == 0 gives r = 0, inv_r = inf like the reference's 1 / sqrt(0))
+    __host__ __device__ static __forceinline__ void sqrt_and_inverse(double x, double &r, double &inv_r)
+    {
+        if (FAST) {
+            inv_r = rsqrt(x);
+            r = x > 0.0 ? x * inv_r : 0.0;
+        } else {
+            r = sqrt(x);
+            inv_r = 1.0 / r;
+        }
+    }
     static constexpr int REC = 13;  // 12 used; odd stride -> conflict-free 64-bit smem access
     static constexpr __host__ __device__ int nseg() { return 3; }
     static constexpr __host__ __device__ int w(int k) { return k == 0 ? 9 : (k == 1 ? 6 : 7); }
@@ -704,10 +735,15 @@ struct DruckerPragerModel {
     static constexpr __host__ __device__ int min_ctas(int tile) { return 384 / tile; }
     static constexpr __host__ __device__ bool has_flag() { return true; }
 
-    __device__ static void init_aux(const Params &, double *, int, int) {}
+    // slot 12 of every record stays 0.0: the "no base term" operand of entry_fixed
+    __device__ static void init_aux(const Params &, double *aux, int tid, int tile)
+    {
+        for (int t = tid; t < tile; t += blockDim.x)
+            aux[t * REC + 12] = 0.0;
+    }
 
     struct State {
-        double s[6], nsq, f, c1, c2, gn;
+        double s[6], nsq, f, c1, c2, gn, inv_gn;
         bool apex;
     };
 
@@ -715,30 +751,33 @@ struct DruckerPragerModel {
     __host__ __device__ static __forceinline__ void state(const Params &P, const double *sg, double bfe, State &S)
     {
         const double i_1 = (sg[0] + sg[1]) + sg[2];
-        const double m = i_1 / 3.0;
+        const double m = third(i_1);
 #pragma unroll
         for (int k = 0; k < 6; ++k)
             S.s[k] = (k < 3) ? sg[k] + (-m) : sg[k];
         double nsq = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; ++k)
-            nsq += S.s[k] * S.s[k];
+            nsq = mad(S.s[k], S.s[k], nsq);
         S.nsq = nsq;
         const double j_2 = 0.5 * nsq;
         // one division per state: c1 = 1/(2r), c2 = -1/(4 r^3) with r = sqrt(J2 [+ d^2])
-        const double r = sqrt(HYP ? j_2 + P.d2 : j_2);
-        const double inv_r = 1.0 / r;
+        double r, inv_r;
+        sqrt_and_inverse(HYP ? j_2 + P.d2 : j_2, r, inv_r);
         S.apex = HYP ? false : !(i_1 < P.apex);  // assert!(i_1 < a/b), classic :86
-        S.f = r + P.b * i_1 - P.a;
+        S.f = mad(P.b, i_1, r) - P.a;
         S.c1 = 0.5 * inv_r;
         S.c2 = -0.25 * (inv_r * inv_r) * inv_r;
         double gsq = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            const double gk = ((k < 3) ? bfe : 0.0) + S.c1 * S.s[k];
-            gsq += gk * gk;
+            const double gk = mad(S.c1, S.s[k], (k < 3) ? bfe : 0.0);
+            gsq = mad(gk, gk, gsq);
         }
-        S.gn = sqrt(gsq);
+        if (FAST)
+            sqrt_and_inverse(gsq, S.gn, S.inv_gn);
+        else
+            S.gn = sqrt(gsq);
     }
 
     __host__ __device__ static __forceinline__ double normsq6(const double *x)
@@ -779,8 +818,8 @@ struct DruckerPragerModel {
         double sigtr[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            const double ev = (k < 3) ? etr / 3.0 : 0.0;
-            sigtr[k] = (two_mu * (e[k] - ev) + k3 * ev) + sig0[k];
+            const double ev = (k < 3) ? third(etr) : 0.0;
+            sigtr[k] = mad(two_mu, e[k] - ev, k3 * ev) + sig0[k];
         }
         State S;
         state(P, sigtr, bfe, S);
@@ -791,7 +830,7 @@ struct DruckerPragerModel {
         if (aux != nullptr) {  // elastic tangent 3 kappa P_vol + 2 mu P_dev (also what a failed point reports)
             double *rec = aux + t * REC;
             rec[0] = P.kappa + two_mu * (2.0 / 3.0);
-            rec[1] = P.kappa - two_mu / 3.0;
+            rec[1] = P.kappa - third(two_mu);
             rec[2] = two_mu;
 #pragma unroll
             for (int k = 3; k < 12; ++k)
@@ -829,8 +868,8 @@ struct DruckerPragerModel {
         double sol[6], sigtr[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            const double ev = (k < 3) ? etr / 3.0 : 0.0;
-            sigtr[k] = (two_mu * (e[k] - ev) + k3 * ev) + sig0[k];
+            const double ev = (k < 3) ? third(etr) : 0.0;
+            sigtr[k] = mad(two_mu, e[k] - ev, k3 * ev) + sig0[k];
             sol[k] = sigtr[k];
         }
         State S;
@@ -848,7 +887,7 @@ struct DruckerPragerModel {
             }
         };
         rec[0] = P.kappa + two_mu * (2.0 / 3.0);  // elastic tangent 3 kappa P_vol + 2 mu P_dev
-        rec[1] = P.kappa - two_mu / 3.0;          // (also what a failed point reports)
+        rec[1] = P.kappa - third(two_mu);          // (also what a failed point reports)
         rec[2] = two_mu;
 #pragma unroll
         for (int k = 3; k < 12; ++k)
@@ -872,13 +911,21 @@ struct DruckerPragerModel {
             const double alpha = two_mu * dl * S.c1;
             beta = -(two_mu * dl * S.c2);
             opa = 1.0 + alpha;
-            den = opa - beta * S.nsq;
+            den = mad(-beta, S.nsq, opa);
             const double tr = ((rs[0] + rs[1]) + rs[2]) * (1.0 / 3.0);
             double sdot = 0.0;
 #pragma unroll
             for (int k = 0; k < 6; ++k)
                 sdot = fma(S.s[k], rs[k], sdot);
-            const double inv_opa = 1.0 / opa, inv_den = 1.0 / den;
+            double inv_opa, inv_den;
+            if (FAST) {  // one reciprocal for both
+                const double t = 1.0 / (opa * den);
+                inv_opa = den * t;
+                inv_den = opa * t;
+            } else {
+                inv_opa = 1.0 / opa;
+                inv_den = 1.0 / den;
+            }
             const double cf = beta * sdot * (inv_opa * inv_den);
             const double h = two_mu * S.c1 * inv_den, q1 = k3 * bfe;
             double y1[6], y2[6];
@@ -894,8 +941,8 @@ struct DruckerPragerModel {
                 sy1 = fma(S.s[k], y1[k], sy1);
                 sy2 = fma(S.s[k], y2[k], sy2);
             }
-            const double cy1 = P.b * ((y1[0] + y1[1]) + y1[2]) + S.c1 * sy1;
-            const double cy2 = P.b * ((y2[0] + y2[1]) + y2[2]) + S.c1 * sy2;
+            const double cy1 = mad(S.c1, sy1, P.b * ((y1[0] + y1[1]) + y1[2]));
+            const double cy2 = mad(S.c1, sy2, P.b * ((y2[0] + y2[1]) + y2[2]));
             const double dlam = (cy1 - rf) / cy2;
             double dsig[6], sds = 0.0;
 #pragma unroll
@@ -904,8 +951,8 @@ struct DruckerPragerModel {
                 sds = fma(S.s[k], dsig[k], sds);
             }
             const double kk = c23 * S.gn;
-            const double dkc = (c23 / S.gn) * S.c1 * (S.c1 + S.c2 * S.nsq);  // dk/dsigma = dkc s
-            const double dkap = rk + dl * (dkc * sds) + kk * dlam;
+            const double dkc = (FAST ? c23 * S.inv_gn : c23 / S.gn) * S.c1 * mad(S.c2, S.nsq, S.c1);  // dk/dsigma = dkc s
+            const double dkap = mad(kk, dlam, mad(dl, dkc * sds, rk));
 #pragma unroll
             for (int k = 0; k < 6; ++k)
                 sol[k] -= dsig[k];
@@ -919,17 +966,18 @@ struct DruckerPragerModel {
             }
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                const double cg = ((k < 3) ? k3 * bfe : 0.0) + two_mu * S.c1 * S.s[k];
-                rs[k] = sol[k] - sigtr[k] + dl * cg;
+                const double cg = mad(two_mu * S.c1, S.s[k], (k < 3) ? k3 * bfe : 0.0);
+                rs[k] = mad(dl, cg, sol[k] - sigtr[k]);
             }
-            rk = al - alpha_0 - c23 * S.gn;
+            rk = mad(-c23, S.gn, al - alpha_0);
             rf = S.f;
             // |x| < t  <=>  x.x < t^2 for t > 0: two of the three square roots go
             const bool conv_res = normsq6(rs) < atol * atol && fabs(rk) < atol && fabs(rf) < atol;
-            const double tinc = atol + rtol * sqrt(normsq6(sol));
-            const bool conv_inc = normsq6(dsig) < tinc * tinc &&
-                                  fabs(dkap) < atol + rtol * fabs(al) &&
-                                  fabs(dlam) < atol + rtol * fabs(dl);
+            bool conv_inc = fabs(dkap) < atol + rtol * fabs(al) && fabs(dlam) < atol + rtol * fabs(dl);
+            if (!FAST || (conv_inc && !conv_res)) {  // FAST: the square root only when it decides (same outcome)
+                const double tinc = atol + rtol * sqrt(normsq6(sol));
+                conv_inc = conv_inc && normsq6(dsig) < tinc * tinc;
+            }
             if (conv_res || conv_inc)
                 break;
             if (it > 25) {  // maxit, :167,:228
@@ -946,12 +994,13 @@ struct DruckerPragerModel {
 #pragma unroll
         for (int k = 0; k < 6; ++k)
             x[k] = sol[k] - sig0[k];
-        const double xv = ((x[0] + x[1]) + x[2]) / 3.0;
+        const double xv = third((x[0] + x[1]) + x[2]);
         hist[0] = al;
+        const double i2mu = FAST ? 1.0 / two_mu : 0.0, ik3 = FAST ? 1.0 / k3 : 0.0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             const double vol = (k < 3) ? xv : 0.0;
-            hist[1 + k] += e[k] - ((x[k] - vol) / two_mu + vol / k3);
+            hist[1 + k] += e[k] - (FAST ? (x[k] - vol) * i2mu + vol * ik3 : (x[k] - vol) / two_mu + vol / k3);
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i)
@@ -964,17 +1013,34 @@ struct DruckerPragerModel {
             const double alpha = two_mu * dl * S.c1;
             beta = -(two_mu * dl * S.c2);
             opa = 1.0 + alpha;
-            den = opa - beta * S.nsq;
-            const double m1 = two_mu / opa, m2 = two_mu * (beta / (opa * den));
-            const double h = two_mu * S.c1 / den, q1 = k3 * bfe, q2 = k3 * P.b;
-            const double D = P.b * (3.0 * q1) + S.c1 * (h * S.nsq);
-            const double A0 = P.kappa - q1 * q2 / D;
-            rec[0] = A0 + m1 * (2.0 / 3.0);
-            rec[1] = A0 - m1 / 3.0;
-            rec[2] = m1;
-            rec[3] = m2 - h * h / D;
-            rec[4] = -(q1 * h) / D;
-            rec[5] = -(h * q2) / D;
+            den = mad(-beta, S.nsq, opa);
+            const double q1 = k3 * bfe, q2 = k3 * P.b;
+            if (FAST) {  // two reciprocals instead of eight divisions
+                const double t = 1.0 / (opa * den);
+                const double inv_opa = den * t, inv_den = opa * t;
+                const double m1 = two_mu * inv_opa, m2 = two_mu * (beta * t);
+                const double h = two_mu * S.c1 * inv_den;
+                const double D = fma(S.c1, h * S.nsq, P.b * (3.0 * q1));
+                const double iD = 1.0 / D;
+                const double A0 = P.kappa - q1 * q2 * iD;
+                rec[0] = A0 + m1 * (2.0 / 3.0);
+                rec[1] = A0 - m1 * (1.0 / 3.0);
+                rec[2] = m1;
+                rec[3] = m2 - h * h * iD;
+                rec[4] = -(q1 * h) * iD;
+                rec[5] = -(h * q2) * iD;
+            } else {
+                const double m1 = two_mu / opa, m2 = two_mu * (beta / (opa * den));
+                const double h = two_mu * S.c1 / den;
+                const double D = P.b * (3.0 * q1) + S.c1 * (h * S.nsq);
+                const double A0 = P.kappa - q1 * q2 / D;
+                rec[0] = A0 + m1 * (2.0 / 3.0);
+                rec[1] = A0 - m1 / 3.0;
+                rec[2] = m1;
+                rec[3] = m2 - h * h / D;
+                rec[4] = -(q1 * h) / D;
+                rec[5] = -(h * q2) / D;
+            }
 #pragma unroll
             for (int k = 0; k < 6; ++k)
                 rec[6 + k] = S.s[k];
@@ -983,8 +1049,24 @@ struct DruckerPragerModel {
     }
 
     // M_ij = [vol block] + m1 delta_ij + A3 s_i s_j + A4 1_i s_j + A5 s_i 1_j
+    // record: rec[0..2] = vol-block diagonal / off-diagonal / shear diagonal, rec[3..5] = A3, A4, A5,
+    // rec[6..11] = s, rec[12] = 0.0
+    __host__ __device__ static __forceinline__ int base_slot(int i, int j)
+    {
+        return (i < 3 && j < 3) ? (i == j ? 0 : 1) : (i == j ? 2 : 12);
+    }
+    // VAR 1: everything that depends on (i, j) only -- the record slot of the base term and the two 0/1 factors --
+    // comes in as an argument, so a thread that owns a fixed (i, j) pays six loads and five fused operations
+    __host__ __device__ static __forceinline__ double entry_fixed(const double *rec, int i, int j, int slot,
+                                                                  double ci, double cj)
+    {
+        const double si = rec[6 + i];
+        return fma(cj * rec[5], si, fma(rec[6 + j], fma(rec[3], si, ci * rec[4]), rec[slot]));
+    }
     __host__ __device__ static __forceinline__ double entry(const double *rec, int i, int j)
     {
+        if (FAST)
+            return entry_fixed(rec, i, j, base_slot(i, j), i < 3 ? 1.0 : 0.0, j < 3 ? 1.0 : 0.0);
         const bool vi = i < 3, vj = j < 3, diag = (i == j);
         const double base = (vi && vj) ? (diag ? rec[0] : rec[1]) : (diag ? rec[2] : 0.0);
         const double si = rec[6 + i], sj = rec[6 + j];
@@ -995,7 +1077,24 @@ struct DruckerPragerModel {
                                                          double *tang, int cnt, int tid,
                                                          int nthreads, bool vec_ok)
     {
-        if (vec_ok) {
+        if (vec_ok && FAST) {
+            // 18 consecutive threads write the 18 16-byte pairs of one point's 6x6 block, nthreads / 18 points
+            // per round: a thread keeps ONE (row, column pair) for the whole kernel, so the index arithmetic and
+            // the selects of entry() leave the loop (ncu on the p-strided loop below: 57 % of the kernel's
+            // instructions, profiles/r2m_dp_ncu_full.json); stores stay consecutive 16-byte chunks
+            const int qpr = nthreads / 18;
+            const int ql = tid / 18, pr = tid - 18 * ql;
+            if (ql < qpr) {
+                const int i = pr / 3, j = 2 * (pr - 3 * i);
+                const int b0 = base_slot(i, j), b1 = base_slot(i, j + 1);
+                const double ci = i < 3 ? 1.0 : 0.0, cj0 = j < 3 ? 1.0 : 0.0, cj1 = j + 1 < 3 ? 1.0 : 0.0;
+                for (int q = ql; q < cnt; q += qpr) {
+                    const double *rec = aux + q * REC;
+                    st_stream_v2(tang + (size_t)q * 36 + 2 * pr, entry_fixed(rec, i, j, b0, ci, cj0),
+                                 entry_fixed(rec, i, j + 1, b1, ci, cj1));
+                }
+            }
+        } else if (vec_ok) {
             const int npairs = cnt * 18;
             for (int p = tid; p < npairs; p += nthreads) {
                 const int q = p / 18;

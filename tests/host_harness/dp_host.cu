@@ -28,14 +28,15 @@ struct HostView {
     }
 };
 
-template <bool HYP>
+template <bool HYP, int VAR>
 int run(const fcx::DruckerPragerParams &P, size_t n, const double *grad, double *stress, double *tangent,
         double *hist, unsigned char *flag)
 {
-    using M = fcx::DruckerPragerModel<HYP>;
+    using M = fcx::DruckerPragerModel<HYP, VAR>;
     int nfail = 0;
     for (size_t q = 0; q < n; ++q) {
         double rec[M::REC];
+        rec[12] = 0.0;  // what init_aux leaves in every record of the tile kernel
         bool plastic = false, failed = false;
         HostView v{grad + 9 * q, stress + 6 * q, hist + 7 * q};
         M::qp(P, v, tangent != nullptr ? rec : nullptr, 0, plastic, failed);
@@ -53,7 +54,8 @@ int run(const fcx::DruckerPragerParams &P, size_t n, const double *grad, double 
 
 // params as in fcx_drucker_prager_evaluate (include/fcx.h): classic [mu, kappa, a, b, b_flow], hyperbolic
 // [mu, kappa, a, b, d, b_flow]; returns the number of failed points
-extern "C" int dp_host_evaluate(int hyperbolic, const double *params, size_t n, const double *grad, double *stress,
+// variant: the model's VAR (0 = the reference's spelling of every division / square root, 1 = the shipped one)
+extern "C" int dp_host_evaluate(int hyperbolic, int variant, const double *params, size_t n, const double *grad, double *stress,
                                 double *tangent, double *hist, unsigned char *flag)
 {
     fcx::DruckerPragerParams P;
@@ -64,6 +66,9 @@ extern "C" int dp_host_evaluate(int hyperbolic, const double *params, size_t n, 
     P.d2 = hyperbolic ? params[4] * params[4] : 0.0;
     P.b_flow = hyperbolic ? params[5] : params[4];
     P.apex = P.a / P.b;
-    return hyperbolic ? run<true>(P, n, grad, stress, tangent, hist, flag)
-                      : run<false>(P, n, grad, stress, tangent, hist, flag);
+    if (variant == 0)
+        return hyperbolic ? run<true, 0>(P, n, grad, stress, tangent, hist, flag)
+                          : run<false, 0>(P, n, grad, stress, tangent, hist, flag);
+    return hyperbolic ? run<true, 1>(P, n, grad, stress, tangent, hist, flag)
+                      : run<false, 1>(P, n, grad, stress, tangent, hist, flag);
 }
