@@ -72,6 +72,8 @@ SIGNATURES = {
     "fcx_host_threads": (_ci, [_ci]),
     "fcx_host_wire": (_ci, [_ci]),
     "fcx_host_wire_used": (_ci, []),
+    "fcx_host_wire_mix": (_ci, [_ci]),
+    "fcx_host_wire_mix_used": (_ci, []),
     "fcx_host_numa": (_ci, [_ci]),
     "fcx_host_numa_info": (_ci, [_vp, _ci]),
     "fcx_diag_host_bandwidth": (_ci, [_ci, _sz, _vp, _ci]),

@@ -179,7 +179,10 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
 // (0.110 ms, profiles/r1zi_*): lane = cell / warp = quadrature point with the basis-gradient
 // table as constant-bank DFMA operands, odd-stride nodal stage, rotated 16-byte result stores --
 // the table loads it removes were broadcasts that cost one wavefront each, while the padded
-// stage made the LDGSTS writes less regular.
+// stage made the LDGSTS writes less regular.  Also measured slower (0.119 ms, profiles/r2p_*): the
+// staging loop node by node (address arithmetic once per node instead of once per value: 33 % fewer
+// instructions) -- a warp's copy then touches 32 different nodes instead of 11 and the shared-memory
+// wavefronts go up by a quarter: this kernel is bound by L1 / shared-memory wavefronts, not by issue.
 // ---------------------------------------------------------------------------
 template <int G, int ND, int NQ, bool PREV>
 struct StagedCfg {

@@ -850,6 +850,16 @@ struct PlasticWire {
     unsigned char *user_flag = nullptr;
     double tmpl[36];  // elastic tangent, computed on the GPU
     size_t chunk = 0;
+    // Mixed download: `mix` percent of the chunks leave by plain DMA straight into the caller's page-locked
+    // arrays (392 B per point over the link, no host-thread byte), the others by records (161 B per point over
+    // the link, 392 B per point written by the host threads): the link and the pool threads work side by side
+    // on DIFFERENT chunks instead of the threads alone bounding the call (see g_wire_mix).
+    int mix = 0;
+    bool plain(size_t q0) const
+    {
+        const size_t ci = chunk ? q0 / chunk : 0;
+        return mix > 0 && ((ci + 1) * (size_t)mix) / 100 != (ci * (size_t)mix) / 100;
+    }
     int rec() const { return nt + hw[0] + hw[1]; }
     // wire layout inside the pinned slot
     size_t off_count() const { return 0; }
@@ -958,6 +968,16 @@ static void plastic_wire_expand(const PlasticWire &W, size_t q0, size_t cnt, con
 // DRAM (166-172 GB/s memcpy on these hosts), and 392 B/QP of DMA writes cost more of it than 161 B/QP of
 // records plus streaming fills.  Threshold: FCX_WIRE_AUTO_RANKS (default 4).
 static int g_wire = 3;
+// Share (percent) of the chunks of a record-wire call (1) that leave by plain DMA instead, when every result
+// array of the call is page-locked.  With records alone a call on page-locked arrays is bound by the pool
+// threads' stores (392 B per point, ~8 GB/s per thread) while the link idles at 161 B per point; a plain-DMA
+// chunk costs the link 392 B per point and the threads nothing.  -1 = AUTO.
+// MEASURED (16 M points, page-locked arrays, one GPU on a 16-core host, profiles/r2s_e2e_mix_pinned.jsonl):
+// 0 / 15 / 25 / 35 / 50 / 100 % = 158 / 150 / 144 / 139 / 131 / 122 M QP/s, the same with 12 pool threads --
+// the call time grows linearly with the share, i.e. the plain chunks and the record chunks do not overlap the
+// way two independent resources would: AUTO therefore resolves to 0 (FCX_WIRE_MIX_AUTO overrides); the
+// option stays for hosts with a faster link or fewer cores.
+static int g_wire_mix = -1;
 
 static int local_world_size()
 {
@@ -999,6 +1019,21 @@ static int effective_wire(const void *stress, const void *tangent, const void *h
     return 1;
 }
 static int g_last_wire = -1;  // what the last plastic host call resolved to (fcx_host_wire_used)
+static int g_last_wire_mix = 0;
+
+// AUTO: FCX_WIRE_MIX_AUTO percent (default below) when one rank has the host's cores to itself; with several
+// ranks per host the host's DRAM is the bound and plain DMA costs more of it than records do (g_wire above).
+static int effective_wire_mix()
+{
+    if (g_wire_mix >= 0)
+        return g_wire_mix;
+    static const int pct = [] {
+        const char *e = getenv("FCX_WIRE_MIX_AUTO");
+        const int v = e ? atoi(e) : 0;
+        return v < 0 ? 0 : (v > 100 ? 100 : v);
+    }();
+    return local_world_size() > 1 ? 0 : pct;
+}
 
 // Device alias of a page-locked host range (pinned allocation or cudaHostRegister), or nullptr.
 static void *device_alias(const void *p, size_t bytes)
@@ -1243,6 +1278,10 @@ static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
             }
             W.user_flag = H.flag;
             W.nt = H.tangent == nullptr ? 0 : (H.symmetric ? 21 : 36);
+            if (wire == 1 && H.tangent != nullptr && page_locked(H.stress) && page_locked(H.tangent) &&
+                page_locked(H.hist[0]) && page_locked(H.nh > 1 ? H.hist[1] : nullptr))
+                W.mix = effective_wire_mix();
+            g_last_wire_mix = W.mix;
             if (wire >= 2 && H.tangent != nullptr && (reinterpret_cast<uintptr_t>(H.tangent) & 15u) == 0) {
                 W.tangent_dev = (double *)device_alias(H.tangent, n * 36 * d);
                 if (W.tangent_dev != nullptr && (reinterpret_cast<uintptr_t>(W.tangent_dev) & 15u) == 0)
@@ -1254,6 +1293,16 @@ static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
             P.dev_bytes = W.dev_bytes();
             P.wire_bytes = W.wire_bytes();
             P.enqueue = [&W](void **dev, void *scratch, void *wire, size_t q0, size_t cnt, cudaStream_t st) {
+                if (W.plain(q0)) {  // this chunk by plain DMA into the page-locked arrays of the caller
+                    cudaError_t e = cudaMemcpyAsync(W.tangent + q0 * 36, dev[2], cnt * 36 * sizeof(double),
+                                                    cudaMemcpyDeviceToHost, st);
+                    for (int h = 0; h < W.nh && e == cudaSuccess; ++h)
+                        e = cudaMemcpyAsync(W.hist[h] + q0 * W.hw[h], dev[3 + h], cnt * W.hw[h] * sizeof(double),
+                                            cudaMemcpyDeviceToHost, st);
+                    if (e == cudaSuccess && W.user_flag != nullptr)  // flags through the slot (the array may be pageable)
+                        e = cudaMemcpyAsync((char *)wire + W.off_flag(), dev[5], cnt, cudaMemcpyDeviceToHost, st);
+                    return note_cuda_error(e, "plastic wire: plain chunk");
+                }
                 char *wb = (char *)wire;
                 unsigned *list = (unsigned *)scratch, *count = list + W.chunk;
                 const unsigned char *fl = (const unsigned char *)dev[5];
@@ -1278,7 +1327,10 @@ static int run_plastic_host(const PlasticHost &H, size_t n, Launch &&launch)
                 return note_cuda_error(e, "plastic wire pack");
             };
             P.expand = [&W](size_t q0, size_t cnt, const void *wire, Group &g) {
-                plastic_wire_expand(W, q0, cnt, wire, g);
+                if (!W.plain(q0))
+                    plastic_wire_expand(W, q0, cnt, wire, g);
+                else if (W.user_flag != nullptr)
+                    memcpy(W.user_flag + q0, (const char *)wire + W.off_flag(), cnt);
             };
             // tangent, history, flag: uploaded / kept on the device as before, downloaded by the wire
             const HostArr arr[6] = {{H.grad, nullptr, bpq[0]},  {H.stress, H.stress, bpq[1]},
@@ -1329,6 +1381,16 @@ int fcx_host_wire(int on)
 }
 
 int fcx_host_wire_used(void) { return g_last_wire; }
+
+int fcx_host_wire_mix(int percent)
+{
+    const int old = g_wire_mix;
+    if (percent >= -1)
+        g_wire_mix = percent > 100 ? 100 : percent;
+    return old;
+}
+
+int fcx_host_wire_mix_used(void) { return g_last_wire_mix; }
 
 int fcx_host_numa(int on)
 {

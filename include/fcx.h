@@ -392,6 +392,17 @@ int fcx_host_wire(int on);
  * plain DMA, wire 0, is the slowest there: every variant is bound by the host's DRAM).
  * fcx_host_wire_used(): what the last plastic host call resolved to (0/1/2; -1 before the first call). */
 int fcx_host_wire_used(void);
+/* Mixed download of a record-wire call (wire 1) whose result arrays are ALL page-locked: `percent` of the chunks
+ * leave by plain DMA straight into the caller's arrays (392 B per point over the link, no host-thread byte), the
+ * others by records (161 B per point over the link, 392 B per point written by the pool threads) -- the link and
+ * the threads work side by side on different chunks.  0 = off, 1..100, -1 = AUTO (default: FCX_WIRE_MIX_AUTO
+ * percent with one rank per host, 0 with several); values below -1 only query.  Returns the old setting.
+ * Bit-identical arrays either way (tests/test_gpu_parity.py::test_host_path_memory_kinds[mixed_wire-*]).
+ * Measured on this pool's 16-core hosts it is SLOWER at every share (158 -> 122 M QP/s from 0 to 100 %,
+ * profiles/r2s_e2e_mix_pinned.jsonl), so AUTO is 0 unless FCX_WIRE_MIX_AUTO says otherwise.
+ * fcx_host_wire_mix_used(): the share the last plastic host call ran with (0 if its arrays were not page-locked). */
+int fcx_host_wire_mix(int percent);
+int fcx_host_wire_mix_used(void);
 /* NUMA placement of the host pipeline (pool threads, drain thread, pinned ring slots) on the node
  * the bound GPU hangs off; 1 = on (default), 0 = off, -1 = query; returns the old value.  A no-op on
  * single-node hosts and where sysfs hides the topology.  fcx_host_numa_info: out[0..4) = GPU's NUMA

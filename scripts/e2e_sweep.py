@@ -32,6 +32,10 @@ ap.add_argument("--quick", action="store_true", help="defaults + wires only")
 ap.add_argument("--mini", action="store_true", help="defaults, wires and a few chunk / thread points (multi-GPU sessions)")
 ap.add_argument("--kinds", default="pageable,pinned")
 ap.add_argument("--stress-only", action="store_true")
+ap.add_argument("--mix", default=None,
+                help="only this: record wire (1) with these shares (percent, comma separated) of the chunks by plain "
+                     "DMA (fcx_host_wire_mix), optionally x --mix-threads pool threads")
+ap.add_argument("--mix-threads", default="0")
 args = ap.parse_args()
 rank, local_rank, world = env_rank_world()
 torch.cuda.set_device(local_rank)
@@ -81,12 +85,22 @@ def run(kind, A, tag, **knobs):
     if rank == 0:
         med = float(np.median(times))
         print(json.dumps({"n_gpus": world, "memory": kind, **knobs, "wire_used": int(L.fcx_host_wire_used()),
+                          "wire_mix_used": int(L.fcx_host_wire_mix_used()),
                           "stress_only": args.stress_only, "tag": tag,
                           "MQPps_aggregate": round(world * n / med / 1e6, 1), "step_s": [round(t, 4) for t in times]}),
               flush=True)
 
 
-for kind in args.kinds.split(","):
+for kind in args.kinds.split(",") if args.mix else ():
+    A = arrays(kind)
+    for threads in [int(t) for t in args.mix_threads.split(",")]:
+        for mix in [int(m) for m in args.mix.split(",")]:
+            kn = {"wire": 1, "wire_mix": mix}
+            if threads > 0:
+                kn["threads"] = threads
+            run(kind, A, "mix", **kn)
+    del A
+for kind in args.kinds.split(",") if not args.mix else ():
     A = arrays(kind)
     run(kind, A, "defaults (wire auto)")
     for wire in (0, 1, 2):

@@ -400,7 +400,7 @@ def test_elastic_16m_linearity():
 
 # ------------------------------------------------------------------ host-memory kinds
 
-@pytest.mark.parametrize("wire", [2, 1, 0], ids=["direct_wire", "slot_wire", "plain_d2h"])
+@pytest.mark.parametrize("wire", [2, 1, 0, 4], ids=["direct_wire", "slot_wire", "plain_d2h", "mixed_wire"])
 @pytest.mark.parametrize("kind", ["pageable_staged", "pageable_driver", "pinned", "registered", "mixed"])
 def test_host_path_memory_kinds(kind, wire):
     """The host entry points give bit-identical results for every kind of caller memory:
@@ -410,7 +410,8 @@ def test_host_path_memory_kinds(kind, wire):
     wire (plastic points only; elastic tangents filled on the host from the GPU-computed constant):
     `slot_wire` = compacted records [upper triangle, eps_n, alpha] expanded by the host threads,
     `direct_wire` = additionally, page-locked tangent arrays get the plastic tangents stored in
-    place by a kernel through the array's device alias (records carry the history only)."""
+    place by a kernel through the array's device alias (records carry the history only),
+    `mixed_wire` = slot wire with 40 % of the chunks by plain DMA (page-locked result arrays only)."""
     from fenics_constitutive_b200._lib import lib
 
     n = 300_007
@@ -444,13 +445,17 @@ def test_host_path_memory_kinds(kind, wire):
             assert L.fcx_host_register(a.ctypes.data, a.nbytes) == 0
     old_stage = L.fcx_host_staging(0 if kind == "pageable_driver" else 1)
     old_chunk = L.fcx_host_chunk_qps(40_000)
-    old_wire = L.fcx_host_wire(wire)
+    old_wire = L.fcx_host_wire(1 if wire == 4 else wire)
+    old_mix = L.fcx_host_wire_mix(40 if wire == 4 else 0)
     try:
         law.evaluate(0.0, 1.0, arrs[0], arrs[1], arrs[2], {"eps_n": arrs[3], "alpha": arrs[4]})
+        if wire == 4:  # the share applies only when every result array is page-locked
+            assert L.fcx_host_wire_mix_used() == (40 if kind in ("pinned", "registered") else 0)
     finally:
         L.fcx_host_staging(old_stage)
         L.fcx_host_chunk_qps(old_chunk)
         L.fcx_host_wire(old_wire)
+        L.fcx_host_wire_mix(old_mix)
         if kind == "registered":
             for a in arrs:
                 L.fcx_host_unregister(a.ctypes.data)
