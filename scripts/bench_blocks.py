@@ -139,6 +139,39 @@ def models_block(dev, n: int, peak_gbs: float, steps: int = 10) -> dict:
         row(f"{cls.__name__}_FULL_per_increment", 648, ms, increments=100, total_ms_100_increments=round(100 * ms, 3))
         del grad, stress, ev, et, tangent
 
+    # ---- comfe-rs mirrors: linear-hardening Mises, Drucker-Prager classic / hyperbolic, ~52 % plastic
+    from fenics_constitutive_b200.models import (DruckerPrager3D, DruckerPragerHyperbolic3D,
+                                                 MisesPlasticityLinearHardening3D)
+
+    A1 = lambda v: np.array([v])  # noqa: E731
+    rs_cases = [
+        ("rs_mises_linear_hardening", MisesPlasticityLinearHardening3D,
+         {"mu": A1(80769.0), "kappa": A1(175000.0), "y_0": A1(1200.0), "h": A1(200.0)}, synthetic.MISES_GRAD_STD, None),
+        ("rs_drucker_prager", DruckerPrager3D,
+         {"mu": A1(80769.0), "kappa": A1(175000.0), "a": A1(300.0), "b": A1(0.05), "b_flow": A1(0.05)}, 1.7e-3, 4e-4),
+        ("rs_drucker_prager_hyperbolic", DruckerPragerHyperbolic3D,
+         {"mu": A1(80769.0), "kappa": A1(175000.0), "a": A1(300.0), "b": A1(0.05), "d": A1(40.0), "b_flow": A1(0.02)},
+         1.7e-3, 4e-4),
+    ]
+    for name, cls, prm, shear, vol in rs_cases:
+        law = cls(prm)
+        law.record_plastic_flag = True
+        grad = rnd(n * 9, shear)
+        if vol is not None:  # deviator-dominated increments (stay away from the apex of the cone)
+            grad.view(n, 9)[:, [0, 4, 8]] = rnd(n * 3, vol).view(n, 3)
+        tangent = torch.empty(n * 36, dtype=torch.float64, device=dev)
+        states = [(z(n * 6), z(n * 7)) for _ in range(steps + 3)]  # a fresh virgin state per launch
+
+        def rs_step(i, law=law, grad=grad, tangent=tangent, states=states):
+            st, hi = states[i]
+            law.evaluate(0.0, 1.0, grad, st, tangent, {"history": hi})
+
+        ms = _time_steps(torch, rs_step, steps)
+        row(name, 8 * (9 + 6 + 6 + 36 + 7 + 7) + 1, ms,
+            plastic_fraction=round(float(law.plastic_flag.double().mean().item()), 4),
+            parity="vs the C restatement of comfe-rs (unpinned against the reference: no rustc here)")
+        del states, grad, tangent
+
     # ---- companion gather + fused form(): 998 250 P2 tets (BASELINE config 5 mesh size), q_degree 2
     coords, cv, dofmap = G.unit_cube_p2_tets(55, 55, 55)
     Jinv = G.affine_inverse_jacobians(coords, cv)

@@ -97,6 +97,7 @@ if args.newton_steps_only > 0:
     solver.cg_max_it = args.newton_steps_only
     solver.max_it = 2
     solver.error_on_nonconvergence = False
+    solver.error_on_krylov_failure = False  # truncated solves are the point of this mode
 setup_s = time.perf_counter() - t0
 
 

@@ -25,7 +25,8 @@ KERNELS = {  # file tag -> (object, regex on the demangled name)
     "elastic_full_tile_128": ("fcx_api.o", r"fcx_tile_kernel<fcx::ElasticModel<6, 3>, 128, true>"),
     "kelvin_full_tile_128": ("fcx_api.o", r"fcx_tile_kernel<fcx::KelvinModel<6, 3>, 128, true>"),
     "maxwell_full_tile_128": ("fcx_api.o", r"fcx_tile_kernel<fcx::MaxwellModel<6, 3>, 128, true>"),
-    "drucker_prager_classic_tile_128": ("fcx_api.o", r"fcx_tile_kernel<fcx::DruckerPragerModel<false>, 128, true>"),
+    "drucker_prager_classic_tile_128": ("fcx_api.o", r"fcx_tile_kernel<fcx::DruckerPragerModel<false, 1>, 128, true>"),
+    "drucker_prager_classic_reference_spelling_tile_128": ("fcx_api.o", r"fcx_tile_kernel<fcx::DruckerPragerModel<false, 0>, 128, true>"),
     "mises_form_p2_q2": ("fcx_api.o", r"fcx_mises_form_kernel<10, 4, 64, 8>"),
     "gather_staged_p2_q2": ("fcx_gather.o", r"gather_staged_kernel<3, 10, 4, false>"),
     "gather_cell_p2": ("fcx_gather.o", r"gather_cell_kernel<10, false>"),
