@@ -51,6 +51,8 @@ ap.add_argument("--driver", choices=["device", "python"], default="device",
                 help="Krylov loop: device = csrc/fcx_krylov.cu (peer-memory reduction / ghost push, driven from C), "
                      "python = kernel by kernel from Python with NCCL")
 ap.add_argument("--check-every", type=int, default=10)
+ap.add_argument("--eta-max", type=float, default=None, help="upper bound of the Eisenstat-Walker forcing term")
+ap.add_argument("--eta-gamma", type=float, default=None)
 args = ap.parse_args()
 
 rank, local_rank, world = env_rank_world()
@@ -89,6 +91,10 @@ solver.cg_rtol = args.cg_rtol
 solver.cg_forcing = "eisenstat-walker" if args.forcing == "ew" else None
 solver.cg_driver = args.driver
 solver.cg_check_every = args.check_every
+if args.eta_max is not None:
+    solver.cg_eta_max = args.eta_max
+if args.eta_gamma is not None:
+    solver.cg_eta_gamma = args.eta_gamma
 solver.reduce_over_ranks = world > 1
 if part is not None:
     part.attach(solver)
