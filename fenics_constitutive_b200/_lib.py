@@ -60,6 +60,9 @@ SIGNATURES = {
     "fcx_krylov_iterate": (_ci, [_vp, _ci, _vp]),
     "fcx_krylov_status": (_ci, [_vp, _vp]),
     "fcx_krylov_solution": (_ci, [_vp, _dp, _vp]),
+    "fcx_krylov_set_tolerance": (_ci, [_vp, _cd]),
+    "fcx_krylov_snapshot": (_ci, [_vp, _ci, _vp]),
+    "fcx_krylov_wait_snapshot": (_ci, [_vp, _ci, _vp]),
     "fcx_krylov_halo_update": (_ci, [_vp, _dp, _vp]),
     "fcx_krylov_destroy": (None, [_vp]),
     "fcx_elastic_evaluate_host": (_ci, [_ci, _dp, _sz, _dp, _dp, _dp]),

@@ -72,8 +72,10 @@ __global__ void __launch_bounds__(ASM_THREADS)
                 const double *__restrict__ dphi_ref, const double *__restrict__ weights,
                 const double *__restrict__ Jinv, const double *__restrict__ detJ,
                 const double *__restrict__ qvec, const double *__restrict__ tangent,
-                double *__restrict__ fe, const unsigned long long ncells)
+                double *__restrict__ fe, const unsigned long long ncells, const double *__restrict__ gate)
 {
+    if (gate != nullptr && *gate != 0.0)
+        return;  // frozen Krylov loop (fcx_internal.h: fem_set_launch_gate)
     __shared__ double tab[NQ * ND * G];
     __shared__ double wq[NQ];
     for (int i = threadIdx.x; i < NQ * ND * G; i += ASM_THREADS)
@@ -240,6 +242,10 @@ __global__ void __launch_bounds__(256)
 }
 
 
+// Launch gate of the element kernels (fcx_internal.h), per host thread.
+static thread_local const double *t_gate = nullptr;
+void fem_set_launch_gate(const double *gate) { t_gate = gate; }
+
 // ---------------------------------------------------------------------------
 // QP-parallel element kernel (fem_variant 1)
 // ---------------------------------------------------------------------------
@@ -256,6 +262,7 @@ struct CellArgs {
     unsigned long long ncells;
     unsigned long long *ticket;
     int bulk_ok;             // Jinv, detJ, dofmap, pos, qarr 16-byte aligned
+    const double *gate;      // nullptr, or: return at once if *gate != 0 (fem_set_launch_gate)
 };
 
 template <int G, int S, int ND, int NQ, int MODE>
@@ -296,6 +303,8 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_wq + NQ);  // [2]
     __shared__ unsigned long long s_next[2];  // slot = iteration parity (SHFL: one CTA barrier per tile)
 
+    if (A.gate != nullptr && *A.gate != 0.0)
+        return;  // frozen Krylov loop: uniform over the grid (the word changes only between launches)
     const int tid = threadIdx.x;
     for (int i = tid; i < NQ * ND * G; i += TILE)
         s_tab[i] = A.dphi_ref[i];
@@ -516,6 +525,7 @@ static int launch_qp_cell(const CellArgs &A0, cudaStream_t st)
     if (grid > ntiles)
         grid = ntiles;
     A.ticket = (ntiles > grid) ? tile_ticket(st) : nullptr;
+    A.gate = t_gate;
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     A.bulk_ok = al16(A.Jinv) && al16(A.detJ) && al16(A.qarr) && (!Cfg::GATHER || al16(A.dofmap)) &&
                 (A.pos == nullptr || al16(A.pos));
@@ -534,7 +544,7 @@ static int launch_cell(int mode, size_t ncells, const int *dofmap, const double 
 {
     if (fem_variant() != 0) {
         CellArgs A{dofmap, p, dphi, w, Jinv, detJ, mode == 0 ? qvec : tangent, fe, pos,
-                   (unsigned long long)ncells, nullptr, 0};
+                   (unsigned long long)ncells, nullptr, 0, nullptr};
         switch (mode) {
         case 0: return launch_qp_cell<G, S, ND, NQ, 0>(A, st);
         case 1: return launch_qp_cell<G, S, ND, NQ, 1>(A, st);
@@ -556,15 +566,15 @@ static int launch_cell(int mode, size_t ncells, const int *dofmap, const double 
     switch (mode) {
     case 0:
         cell_kernel<G, S, ND, NQ, 0><<<(unsigned)grid, ASM_THREADS, 0, st>>>(
-            dofmap, p, dphi, w, Jinv, detJ, qvec, tangent, fe, nc);
+            dofmap, p, dphi, w, Jinv, detJ, qvec, tangent, fe, nc, t_gate);
         break;
     case 1:
         cell_kernel<G, S, ND, NQ, 1><<<(unsigned)grid, ASM_THREADS, 0, st>>>(
-            dofmap, p, dphi, w, Jinv, detJ, qvec, tangent, fe, nc);
+            dofmap, p, dphi, w, Jinv, detJ, qvec, tangent, fe, nc, t_gate);
         break;
     default:
         cell_kernel<G, S, ND, NQ, 2><<<(unsigned)grid, ASM_THREADS, 0, st>>>(
-            dofmap, p, dphi, w, Jinv, detJ, qvec, tangent, fe, nc);
+            dofmap, p, dphi, w, Jinv, detJ, qvec, tangent, fe, nc, t_gate);
         break;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);

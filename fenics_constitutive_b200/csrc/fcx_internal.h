@@ -18,6 +18,11 @@ int tuned_ctas_per_sm();
 int fem_variant();
 // fcx_tune "gather_variant": 1 = gather_staged_kernel (cp.async-staged nodal values), 0 = gather_kernel.
 int gather_variant();
+// Launch gate of the FEM element kernels (fcx_assemble.cu): while set (per host thread), every element kernel
+// launched by this thread returns at once if *gate != 0 when it starts -- the device-resident Krylov loop
+// (fcx_krylov.cu) freezes its iterations on the device once the residual test has passed, so the host may
+// enqueue blocks of iterations ahead of reading the test's outcome.  nullptr = no gate.
+void fem_set_launch_gate(const double *gate);
 
 // Resident CTAs per SM of `kern` at (threads, smem), with the opt-in to > 48 KB of dynamic shared
 // memory set first.  Both are properties of (kernel, DEVICE): a process may drive several GPUs (the

@@ -48,6 +48,7 @@ namespace fcx {
 constexpr int KR_THREADS = 256;
 constexpr int KR_MAX_WORLD = 16;
 constexpr int KR_HIST = 1 << 16;  // residual history entries (ring)
+constexpr int KR_CTL = 8;         // doubles in the control block (see Krylov::ctl)
 
 // One rank's communication block (a single cudaMalloc, exported through an IPC handle):
 //   [ red[2][W][4] doubles | redflag[2][W] u64 | haloflag[W] u64 | pad to 256 B | u vector: n doubles ]
@@ -85,6 +86,15 @@ struct Krylov {
     double *scal = nullptr;              // [2]: alpha, beta of the iteration in flight (K2 -> K3)
     double *hist = nullptr;              // [KR_HIST]: r.r at the start of iteration it
     int *err = nullptr;                  // sticky: 1 = a peer's flag never arrived (bounded spin timed out)
+    // Control block [KR_CTL] of the solve in flight, written by K2's finishing thread only:
+    //   [0] frozen (0 / 1): the residual test passed or the operator broke down -- every later kernel of the
+    //       iteration loop returns at once (same decision on every rank: it is taken from the all-gathered sums)
+    //   [1] iteration at which it froze   [2] r.r at the start of the latest live iteration   [3] r.r of iteration 0
+    //   [4] breakdown (p.Ap <= 0) seen     [5] live iterations so far
+    double *ctl = nullptr;
+    double rtol2 = 0.0;                  // freeze when r.r <= rtol2 * (r.r of iteration 0); 0 = never
+    double *snap_host = nullptr;         // pinned [2][KR_CTL + 1]: snapshots of ctl (+ err) for the host
+    cudaEvent_t snap_ev[2] = {nullptr, nullptr};
     // halo plan (device): flattened send entries over all neighbours
     int n_nbr = 0, n_send = 0;
     int nbr_rank[KR_MAX_WORLD] = {};
@@ -101,6 +111,7 @@ struct Krylov {
     unsigned long long epoch = 0;  // reductions / pushes done since creation (same on every rank)
     unsigned long long push_epoch = 0;  // epoch of the last ghost push
     bool push_waited = true;            // ... and whether the neighbours' pushes of that epoch have been waited for
+    bool push_gated = false;            // ... and whether that push was an iteration's (skipped once the solve is frozen)
     size_t ncells_interior = 0;         // local cells [0, ncells_interior) touch no ghost node
     unsigned long long it = 0;     // iterations of the current solve
     unsigned grid = 1;
@@ -162,8 +173,10 @@ __device__ __forceinline__ double kr_block_sum(double v, double *sh)
 __global__ void __launch_bounds__(KR_THREADS)
     kr_begin_kernel(size_t n, size_t n_owned, const double *__restrict__ rhs, const double *__restrict__ minv_in,
                     double *__restrict__ minv, double *__restrict__ x, double *__restrict__ r,
-                    double *__restrict__ u, double *__restrict__ p, double *__restrict__ s)
+                    double *__restrict__ u, double *__restrict__ p, double *__restrict__ s, double *__restrict__ ctl)
 {
+    if (blockIdx.x == 0 && threadIdx.x < KR_CTL)
+        ctl[threadIdx.x] = 0.0;  // a new solve: not frozen (the kernels of the previous solve are behind us in stream order)
     const size_t stride = (size_t)gridDim.x * KR_THREADS;
     for (size_t i = (size_t)blockIdx.x * KR_THREADS + threadIdx.x; i < n; i += stride) {
         const double m = minv_in[i];
@@ -187,10 +200,14 @@ __global__ void __launch_bounds__(KR_THREADS)
                      const double *__restrict__ minv, double *__restrict__ w, unsigned long long nnodes,
                      double *partials, unsigned *ticket, PeerPtrs peers, CommLayout lay, int rank, int world,
                      unsigned long long epoch, int first, double *state, double *scal, double *hist,
-                     unsigned long long it, int *err)
+                     unsigned long long it, int *err, double *ctl, double rtol2)
 {
     __shared__ double sh[KR_THREADS / 32];
     __shared__ bool last;
+    // frozen solve: nothing to do.  Uniform over the grid and over the ranks: ctl[0] is written by the finishing
+    // thread of an EARLIER launch only, from sums every rank holds bit for bit.
+    if (ctl[0] != 0.0)
+        return;
     double g = 0.0, d = 0.0, q = 0.0;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < nnodes; v += stride) {
@@ -283,7 +300,23 @@ __global__ void __launch_bounds__(KR_THREADS)
         }
         // den <= 0: the operator is not positive definite on the free dofs (or the solve has converged to
         // round-off): stop moving and flag it; the host decides
-        const double alpha = den > 0.0 ? gs / den : 0.0;
+        double alpha = den > 0.0 ? gs / den : 0.0;
+        // residual test on the device: r.r at the start of this iteration against rtol^2 times that of iteration 0
+        const double rr0 = first ? qs : ctl[3];
+        const bool passed = rtol2 > 0.0 && qs <= rtol2 * rr0;
+        if (passed)
+            alpha = 0.0;  // x is the answer as it stands (K3 of this iteration is skipped anyway)
+        if (first)
+            ctl[3] = qs;
+        ctl[2] = qs;
+        ctl[5] = (double)it;
+        if (!(den > 0.0))
+            ctl[4] = 1.0;
+        if (passed || !(den > 0.0)) {
+            ctl[1] = (double)it;
+            __threadfence();
+            ctl[0] = 1.0;  // freeze: every later kernel of the loop returns at once
+        }
         scal[0] = alpha;
         scal[1] = beta;
         double *cur = state + (size_t)par * 4;
@@ -303,8 +336,10 @@ __global__ void __launch_bounds__(KR_THREADS)
 __global__ void __launch_bounds__(KR_THREADS)
     cg_update_kernel(size_t n, size_t n_owned, double *__restrict__ x, double *__restrict__ r, double *__restrict__ u,
                      const double *__restrict__ w, double *__restrict__ p, double *__restrict__ s,
-                     const double *__restrict__ minv, const double *__restrict__ scal)
+                     const double *__restrict__ minv, const double *__restrict__ scal, const double *__restrict__ ctl)
 {
+    if (ctl[0] != 0.0)
+        return;  // frozen
     const double alpha = scal[0], beta = scal[1];
     const size_t n2 = n / 2;
     double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
@@ -351,9 +386,11 @@ __global__ void __launch_bounds__(KR_THREADS)
     halo_push_kernel(const double *__restrict__ u, const int *__restrict__ send_src, const int *__restrict__ send_dst,
                      const int *__restrict__ send_nbr, int n_send, PeerPtrs nbr_base, CommLayout lay, int n_nbr,
                      int rank, char *comm, const int *__restrict__ nbr_rank_dev, unsigned *ticket,
-                     unsigned long long epoch, int do_wait, int *err)
+                     unsigned long long epoch, int do_wait, int *err, const double *__restrict__ gate)
 {
     __shared__ bool last;
+    if (gate != nullptr && *gate != 0.0)
+        return;  // push of a frozen iteration: every rank skips it (and the wait that goes with it)
     const int stride = gridDim.x * blockDim.x;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_send; e += stride) {
         double *dst = reinterpret_cast<double *>(nbr_base.base[send_nbr[e]] + lay.off_u) + (size_t)send_dst[e] * G;
@@ -381,8 +418,10 @@ __global__ void __launch_bounds__(KR_THREADS)
 
 // The wait half of a push issued with do_wait = 0: one thread, until every neighbour's flag has reached `epoch`.
 __global__ void halo_wait_kernel(const char *comm, CommLayout lay, int n_nbr, const int *__restrict__ nbr_rank_dev,
-                                 unsigned long long epoch, int *err)
+                                 unsigned long long epoch, int *err, const double *__restrict__ gate)
 {
+    if (gate != nullptr && *gate != 0.0)
+        return;  // the push this wait belongs to was skipped on every rank (frozen solve)
     if (threadIdx.x == 0) {
         const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(comm + lay.off_haloflag);
         for (int k = 0; k < n_nbr; ++k)
@@ -406,12 +445,15 @@ static unsigned kr_grid(size_t work)
     return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
-static int kr_push(Krylov *K, cudaStream_t st, int do_wait = 1)
+// gated = true: a push inside the iteration loop (skipped once the solve is frozen); false: the begin / halo-update
+// pushes, which always run.
+static int kr_push(Krylov *K, cudaStream_t st, int do_wait = 1, bool gated = false)
 {
     if (K->world == 1 || K->n_nbr == 0)
         return FCX_OK;
     K->push_epoch = K->epoch;
     K->push_waited = do_wait != 0;
+    K->push_gated = gated;
     PeerPtrs nb{};
     for (int k = 0; k < K->n_nbr; ++k)
         nb.base[k] = K->peers.base[K->nbr_rank[k]];
@@ -422,7 +464,7 @@ static int kr_push(Krylov *K, cudaStream_t st, int do_wait = 1)
 #define FCX_PUSH(G) \
     halo_push_kernel<G><<<grid, KR_THREADS, 0, st>>>(u, K->send_src, K->send_dst, K->send_nbr, K->n_send, nb, K->lay, \
                                                      K->n_nbr, K->rank, K->comm, nbr_rank_dev, K->ticket + 1, K->epoch, \
-                                                     do_wait, K->err)
+                                                     do_wait, K->err, gated ? K->ctl : nullptr)
     if (K->gdim == 1)
         FCX_PUSH(1);
     else if (K->gdim == 2)
@@ -439,7 +481,9 @@ static int kr_wait(Krylov *K, cudaStream_t st)
 {
     if (K->world == 1 || K->n_nbr == 0 || K->push_waited)
         return FCX_OK;
-    halo_wait_kernel<<<1, 32, 0, st>>>(K->comm, K->lay, K->n_nbr, K->send_nbr + K->n_send, K->push_epoch, K->err);
+    // gated by the control block when the owed push was an iteration's: a frozen iteration neither pushed nor waits
+    halo_wait_kernel<<<1, 32, 0, st>>>(K->comm, K->lay, K->n_nbr, K->send_nbr + K->n_send, K->push_epoch, K->err,
+                                       K->push_gated ? K->ctl : nullptr);
     K->push_waited = true;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return note_cuda_error(cudaGetLastError(), "halo_wait_kernel launch");
@@ -493,6 +537,14 @@ int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, size_t nnode
         e = cudaMalloc((void **)&K->err, sizeof(int));
     if (e == cudaSuccess)
         e = cudaMemset(K->err, 0, sizeof(int));
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&K->ctl, sizeof(double) * KR_CTL);
+    if (e == cudaSuccess)
+        e = cudaMemset(K->ctl, 0, sizeof(double) * KR_CTL);
+    if (e == cudaSuccess)
+        e = cudaMallocHost((void **)&K->snap_host, sizeof(double) * 2 * (KR_CTL + 1));
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k)
+        e = cudaEventCreateWithFlags(&K->snap_ev[k], cudaEventDisableTiming);
     if (e == cudaSuccess) {
         cudaIpcMemHandle_t h;
         memset(&h, 0, sizeof h);
@@ -612,7 +664,8 @@ int fcx_krylov_begin(void *handle, const double *rhs, const double *minv, void *
     double *u = reinterpret_cast<double *>(K->comm + K->lay.off_u);
     if (int rc = kr_wait(K, st))  // a previous solve's last push is still owed its wait
         return rc;
-    kr_begin_kernel<<<kr_grid(K->n), KR_THREADS, 0, st>>>(K->n, K->n_owned, rhs, minv, K->minv, K->x, K->r, u, K->p, K->s);
+    kr_begin_kernel<<<kr_grid(K->n), KR_THREADS, 0, st>>>(K->n, K->n_owned, rhs, minv, K->minv, K->x, K->r, u, K->p, K->s,
+                                                          K->ctl);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
@@ -649,6 +702,10 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
                                        K->weights, K->Jinv + c0 * K->gdim * K->gdim, K->detJ + c0,
                                        K->tang + c0 * K->nq * rl, fe, pos, stream);
     };
+    struct GateGuard {  // the element kernels of this loop return at once when the solve is frozen
+        explicit GateGuard(const double *g) { fem_set_launch_gate(g); }
+        ~GateGuard() { fem_set_launch_gate(nullptr); }
+    } gate_guard(K->ctl);
     for (int k = 0; k < iters; ++k) {
         // K1: cells that touch no ghost node first -- the neighbours' ghost stores of the previous update arrive
         // behind them; then the wait (one thread), then the boundary cells
@@ -665,7 +722,7 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
 #define FCX_GSUM(G) \
     gsum_dots_kernel<G><<<ggrid, KR_THREADS, 0, st>>>(K->adj_ptr, K->adj_idx, K->fe, K->r, u, K->minv, K->w, K->nnodes, \
                                                       K->partials, K->ticket, K->peers, K->lay, K->rank, K->world, K->epoch, \
-                                                      first, K->state, K->scal, K->hist, K->it, K->err)
+                                                      first, K->state, K->scal, K->hist, K->it, K->err, K->ctl, K->rtol2)
         if (K->gdim == 1)
             FCX_GSUM(1);
         else if (K->gdim == 2)
@@ -673,13 +730,14 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
         else
             FCX_GSUM(3);
 #undef FCX_GSUM
-        cg_update_kernel<<<K->grid, KR_THREADS, 0, st>>>(K->n, K->n_owned, K->x, K->r, u, K->w, K->p, K->s, K->minv, K->scal);
+        cg_update_kernel<<<K->grid, KR_THREADS, 0, st>>>(K->n, K->n_owned, K->x, K->r, u, K->w, K->p, K->s, K->minv, K->scal,
+                                                         K->ctl);
         g_launches.fetch_add(2, std::memory_order_relaxed);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess)
             return note_cuda_error(e, "krylov iteration launch");
         K->it += 1;
-        rc = kr_push(K, st, 0);  // push and go on: the wait sits behind the next iteration's interior cells
+        rc = kr_push(K, st, 0, true);  // push and go on: the wait sits behind the next iteration's interior cells
         if (rc != FCX_OK)
             return rc;
     }
@@ -741,6 +799,61 @@ int fcx_krylov_status(void *handle, double *out4)
     return note_cuda_error(e, "fcx_krylov_status");
 }
 
+/* Residual test ON THE DEVICE: the solve freezes itself once r.r <= rtol^2 * (r.r of iteration 0) -- the
+ * iteration that sees it leaves x untouched and every later kernel of the loop returns at once (also after a
+ * breakdown, p.Ap <= 0).  The host may therefore enqueue blocks of iterations AHEAD of knowing the outcome
+ * (fcx_krylov_snapshot / fcx_krylov_wait_snapshot) instead of draining the stream at every check: the answer and
+ * the iteration count are those of the exact stopping iteration, not of the end of a block.  rtol <= 0: never
+ * freeze (the host-driven stop rule of fcx_krylov_status).  Takes effect with the next fcx_krylov_begin. */
+int fcx_krylov_set_tolerance(void *handle, double rtol)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K)
+        return FCX_ERR_NULL;
+    K->rtol2 = rtol > 0.0 ? rtol * rtol : 0.0;
+    return FCX_OK;
+}
+
+/* Enqueue a snapshot of the control block into pinned host slot `slot` (0 / 1) on `stream`, with an event behind. */
+int fcx_krylov_snapshot(void *handle, int slot, void *stream)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K)
+        return FCX_ERR_NULL;
+    if (slot < 0 || slot > 1)
+        return FCX_ERR_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double *dst = K->snap_host + (size_t)slot * (KR_CTL + 1);
+    cudaError_t e = cudaMemcpyAsync(dst, K->ctl, sizeof(double) * KR_CTL, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)  // the sticky error word (an int) travels in the last double's storage
+        e = cudaMemcpyAsync(dst + KR_CTL, K->err, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+        e = cudaEventRecord(K->snap_ev[slot], st);
+    return note_cuda_error(e, "fcx_krylov_snapshot");
+}
+
+/* Wait for snapshot `slot`; out6 = {frozen, iteration at which it froze, r.r at the start of the latest live
+ * iteration, r.r of iteration 0, breakdown seen (2 = a peer never arrived), live iterations so far}. */
+int fcx_krylov_wait_snapshot(void *handle, int slot, double *out6)
+{
+    Krylov *K = static_cast<Krylov *>(handle);
+    if (!K || !out6)
+        return FCX_ERR_NULL;
+    if (slot < 0 || slot > 1)
+        return FCX_ERR_ARG;
+    cudaError_t e = cudaEventSynchronize(K->snap_ev[slot]);
+    if (e != cudaSuccess)
+        return note_cuda_error(e, "fcx_krylov_wait_snapshot");
+    const double *src = K->snap_host + (size_t)slot * (KR_CTL + 1);
+    for (int k = 0; k < 6; ++k)
+        out6[k] = src[k];
+    int err = 0;
+    memcpy(&err, src + KR_CTL, sizeof err);
+    if (err != 0)
+        out6[4] = 2.0;
+    return FCX_OK;
+}
+
 /* x (DEVICE, n doubles) <- the current iterate, on `stream`. */
 int fcx_krylov_solution(void *handle, double *x_out, void *stream)
 {
@@ -762,10 +875,15 @@ void fcx_krylov_destroy(void *handle)
         if (K->peer_open[t])
             cudaIpcCloseMemHandle(K->peers.base[t]);
     void *ptrs[] = {K->comm, K->x, K->r, K->w, K->p, K->s, K->minv, K->partials, K->ticket, K->state, K->scal, K->hist, K->err,
-                    K->send_src, K->send_dst, K->send_nbr};
+                    K->ctl, K->send_src, K->send_dst, K->send_nbr};
     for (void *q : ptrs)
         if (q)
             cudaFree(q);
+    if (K->snap_host)
+        cudaFreeHost(K->snap_host);
+    for (cudaEvent_t ev : K->snap_ev)
+        if (ev)
+            cudaEventDestroy(ev);
     delete K;
 }
 

@@ -10,6 +10,7 @@ The only collective left on the host side is the one-off exchange of the 64-byte
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -74,6 +75,7 @@ class DeviceKrylov:
                                    else problem.num_cells)
         self._x = torch.empty(V.num_dofs, dtype=torch.float64, device=self.device)
         self._status = (ctypes.c_double * 4)()
+        self._snap = (ctypes.c_double * 6)()
 
     def _set_operator(self) -> None:
         pb, L = self.problem, self.L
@@ -87,6 +89,12 @@ class DeviceKrylov:
             pb._fe.data_ptr(), pos, pb._adj_ptr.data_ptr(), None if pos is not None else pb._adj_idx.data_ptr(),
             self.num_interior_cells), "fcx_krylov_set_operator")
 
+    # True: the residual test runs on the device (fcx_krylov_set_tolerance) and the host enqueues the next block
+    # of iterations BEFORE it reads the outcome of the previous one -- no drained stream per check; the answer and
+    # the iteration count are those of the exact stopping iteration.  False: drain and test on the host after
+    # every block (the first version; iteration counts are multiples of check_every).
+    lookahead = os.environ.get("FCX_KRYLOV_LOOKAHEAD", "1") != "0"
+
     def solve(self, rhs, minv, rtol: float, max_it: int, check_every: int):
         """Solve J x = rhs on the dofs where minv != 0.  Returns (x, iterations, converged, relres, breakdown);
         x is this object's workspace, valid until the next solve."""
@@ -94,10 +102,49 @@ class DeviceKrylov:
         check(L.fcx_set_device(self.device.index), "fcx_set_device")
         stream = B.current_stream_ptr(self.device.index)
         self._set_operator()
+        K = max(1, int(check_every))
+        if not self.lookahead:
+            return self._solve_drained(rhs, minv, rtol, max_it, K, stream)
+        check(L.fcx_krylov_set_tolerance(h, float(rtol)), "fcx_krylov_set_tolerance")
         check(L.fcx_krylov_begin(h, rhs.data_ptr(), minv.data_ptr(), stream), "fcx_krylov_begin")
+        snap = self._snap
+        it, ok, relres, brk = 0, False, 1.0, False
+        check(L.fcx_krylov_iterate(h, K, stream), "fcx_krylov_iterate")
+        check(L.fcx_krylov_snapshot(h, 0, stream), "fcx_krylov_snapshot")
+        enq, blk = K, 0
+        while True:
+            more = enq < max_it
+            if more:  # the next block goes out before this one's outcome is known
+                check(L.fcx_krylov_iterate(h, K, stream), "fcx_krylov_iterate")
+                check(L.fcx_krylov_snapshot(h, (blk + 1) & 1, stream), "fcx_krylov_snapshot")
+                enq += K
+            check(L.fcx_krylov_wait_snapshot(h, blk & 1, snap), "fcx_krylov_wait_snapshot")
+            frozen, stop_it, rr, rr0, flag, live = (float(v) for v in snap)
+            if flag == 2.0:
+                raise RuntimeError("device Krylov loop: a peer rank never arrived (peer-memory flag timed out)")
+            it = int(stop_it) if frozen != 0.0 else min(enq - (K if more else 0), int(live) + 1)
+            if rr0 == 0.0:
+                ok, relres = True, 0.0
+                break
+            relres = float(np.sqrt(max(rr, 0.0) / rr0))
+            if flag != 0.0:
+                brk = True
+                break
+            if frozen != 0.0 or relres <= rtol:
+                ok = True
+                break
+            if not more:
+                break
+            blk += 1
+        check(L.fcx_krylov_solution(h, self._x.data_ptr(), stream), "fcx_krylov_solution")
+        return self._x, it, ok, relres, brk
+
+    def _solve_drained(self, rhs, minv, rtol, max_it, K, stream):
         import torch
 
-        K = max(1, int(check_every))
+        L, h = self.L, self.handle
+        check(L.fcx_krylov_set_tolerance(h, 0.0), "fcx_krylov_set_tolerance")
+        check(L.fcx_krylov_begin(h, rhs.data_ptr(), minv.data_ptr(), stream), "fcx_krylov_begin")
         it, ok, relres, brk = 0, False, 1.0, False
         while it < max_it:
             check(L.fcx_krylov_iterate(h, K, stream), "fcx_krylov_iterate")

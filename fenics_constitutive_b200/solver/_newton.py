@@ -72,6 +72,10 @@ class NewtonSolver:
         # ghost exchange over peer memory inside the kernels; no NCCL, no Python per iteration).
         # "python": two-reduction PCG issued kernel by kernel from here, NCCL all-reduces and send/recv.
         self.cg_driver = "device"
+        # device driver: True = residual test on the device, blocks of iterations enqueued ahead of its outcome,
+        # exact stopping iteration; False = stream drained and tested on the host after every block; None = the
+        # driver's default (on; FCX_KRYLOV_LOOKAHEAD=0 switches it off)
+        self.cg_lookahead = None
         self._device_krylov = None
         self.reduce_over_ranks = False  # sum norms/dots over torch.distributed ranks
         # solver/partitioned.py MeshPartition (set by MeshPartition.attach): norms and dot products run
@@ -266,6 +270,8 @@ class NewtonSolver:
                 return self._solve_cg(self.problem.J_apply, rhs, free_mask, diag, rtol)
             torch.cuda.synchronize()
             self.krylov_setup_s += time.perf_counter() - t0
+        if self.cg_lookahead is not None:
+            self._device_krylov.lookahead = bool(self.cg_lookahead)
         tol = self.cg_rtol if rtol is None else rtol
         x, it, ok, relres, brk = self._device_krylov.solve(rhs, minv, tol, self.cg_max_it, self.cg_check_every)
         why = None

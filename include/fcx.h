@@ -314,7 +314,16 @@ int fcx_pcg_update_p(size_t n, double *p, const double *r, const double *minv, c
  *   fcx_krylov_status    (after a stream synchronisation) out[0] iterations done, out[1] r.r at the start
  *                        of the last one, out[2] r.r of the right-hand side, out[3] 1 = breakdown (p.Ap <= 0),
  *                        2 = a peer rank never arrived (bounded spin timed out)
- *   fcx_krylov_solution  x_out <- x */
+ *   fcx_krylov_solution  x_out <- x
+ *   fcx_krylov_set_tolerance  residual test ON THE DEVICE: with rtol > 0 the solve freezes itself once
+ *                        r.r <= rtol^2 (r.r of iteration 0) -- the iteration that sees it leaves x untouched, every
+ *                        later kernel of the loop returns at once (also after a breakdown) -- so the host may
+ *                        enqueue blocks of iterations AHEAD of knowing the outcome instead of draining the
+ *                        stream at every check; takes effect with the next fcx_krylov_begin; rtol <= 0 = never
+ *   fcx_krylov_snapshot / fcx_krylov_wait_snapshot  enqueue a copy of the control block into pinned host slot
+ *                        0 / 1 with an event behind it / wait for that event: out6 = {frozen, iteration at which
+ *                        it froze, r.r at the start of the latest live iteration, r.r of iteration 0,
+ *                        1 = breakdown / 2 = a peer never arrived, live iterations so far} */
 int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, size_t nnodes_owned, void **handle_out,
                       void **comm_out, unsigned char *ipc_handle_out);
 int fcx_krylov_connect(void *handle, const unsigned char *ipc_handles);
@@ -328,6 +337,9 @@ int fcx_krylov_begin(void *handle, const double *rhs, const double *minv, void *
 int fcx_krylov_iterate(void *handle, int iters, void *stream);
 int fcx_krylov_status(void *handle, double *out4);
 int fcx_krylov_solution(void *handle, double *x_out, void *stream);
+int fcx_krylov_set_tolerance(void *handle, double rtol);
+int fcx_krylov_snapshot(void *handle, int slot, void *stream);
+int fcx_krylov_wait_snapshot(void *handle, int slot, double *out6);
 /* Ghost entries of the nodal vector x (owned nodes first) <- their owners' values, through the same peer-memory
  * push (reference: PETSc ghostUpdate / scatter_forward of the displacement, solver/_incrementalunknowns.py:36-38).
  * Collective over the ranks of the solver; enqueue-only; not during a solve. */

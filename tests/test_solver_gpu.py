@@ -603,12 +603,16 @@ def test_partition_hooks_single_rank():
     assert float(np.abs(sols[0][2]).max()) > 1200.0  # the second step went plastic
 
 
-@pytest.mark.parametrize("forcing", [None, "eisenstat-walker"])
-def test_device_krylov_driver_equals_python_driver(forcing):
+@pytest.mark.parametrize("forcing,lookahead", [(None, True), (None, False), ("eisenstat-walker", False),
+                                               ("eisenstat-walker", True)],
+                         ids=["fixed-lookahead", "fixed-drained", "ew-drained", "ew-lookahead"])
+def test_device_krylov_driver_equals_python_driver(forcing, lookahead):
     """The device-resident Krylov loop (csrc/fcx_krylov.cu: single-reduction PCG driven from C) against the
-    kernel-by-kernel two-reduction PCG issued from Python: same Newton iteration counts, same displacement
-    and stresses to the Krylov tolerance, Mises plasticity across the yield point on a P2 mesh (CG path:
-    more than 3000 dofs).  Also: every linear solve reports convergence."""
+    kernel-by-kernel two-reduction PCG issued from Python: same displacement and stresses to the Krylov tolerance,
+    Mises plasticity across the yield point on a P2 mesh (CG path: more than 3000 dofs); every linear solve reports
+    convergence.  lookahead = the residual test runs on the device and the host enqueues blocks of iterations
+    ahead of knowing its outcome (the solve stops at the exact iteration); drained = the stream is drained and the
+    test is made on the host after every block, like the Python driver does (iteration counts in blocks of 10)."""
     sols = []
     for driver in ("device", "python"):
         mesh = S.create_unit_cube(7, 6, 5)
@@ -621,19 +625,26 @@ def test_device_krylov_driver_equals_python_driver(forcing):
         solver = S.NewtonSolver(None, pb)
         solver.linear_solver = "cg"
         solver.cg_driver = driver
+        solver.cg_lookahead = lookahead
         solver.cg_rtol = 1e-11
         solver.cg_forcing = forcing
-        its = []
+        its, kits = [], []
         for step in (1, 2):
             ux.value = 0.006 * step
             k, ok = solver.solve(u)
             assert ok and all(solver.krylov_converged)
             its.append(k)
+            kits.append(list(solver.krylov_iterations))
             pb.update()
         sols.append((its, np_(u.x.array).copy(), np_(pb.stress_0.x.array).copy(),
-                     float((pb._history_0[0]["alpha"].x.array > 0).double().mean().item())))
-    (ia, ua, sa, pa), (ib, ub, sb, _) = sols
-    assert ia == ib
+                     float((pb._history_0[0]["alpha"].x.array > 0).double().mean().item()), kits))
+    (ia, ua, sa, pa, ka), (ib, ub, sb, _, kb) = sols
+    if forcing is None or not lookahead:
+        assert ia == ib
+    else:  # loose linear solves stopped at the exact iteration instead of the end of a block: a Newton step may move
+        assert all(abs(a - b) <= 1 for a, b in zip(ia, ib))
+    if not lookahead:  # host test after every block of cg_check_every = 10 iterations
+        assert all(k % 10 == 0 for ks in ka for k in ks)
     assert 0.05 < pa < 1.0
     # fixed Krylov tolerance (1e-11): the two solves agree to it.  Inexact Newton (Eisenstat-Walker): the two PCG
     # variants stop their loose linear solves at different iterates, so the Newton paths differ and agree only to
