@@ -245,6 +245,13 @@ __global__ void __launch_bounds__(256)
 // Launch gate of the element kernels (fcx_internal.h), per host thread.
 static thread_local const double *t_gate = nullptr;
 void fem_set_launch_gate(const double *gate) { t_gate = gate; }
+static thread_local unsigned long long *t_tickets = nullptr;
+static thread_local unsigned *t_ticket_launches = nullptr;
+void fem_set_launch_tickets(unsigned long long *pair, unsigned *launches)
+{
+    t_tickets = launches != nullptr ? pair : nullptr;
+    t_ticket_launches = launches;
+}
 
 // ---------------------------------------------------------------------------
 // QP-parallel element kernel (fem_variant 1)
@@ -263,6 +270,7 @@ struct CellArgs {
     unsigned long long *ticket;
     int bulk_ok;             // Jinv, detJ, dofmap, pos, qarr 16-byte aligned
     const double *gate;      // nullptr, or: return at once if *gate != 0 (fem_set_launch_gate)
+    unsigned long long *ticket_reset;  // nullptr, or the NEXT launch's ticket counter, zeroed by this one
 };
 
 template <int G, int S, int ND, int NQ, int MODE>
@@ -303,6 +311,8 @@ __global__ void __launch_bounds__(fem_tile<NQ>())
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_wq + NQ);  // [2]
     __shared__ unsigned long long s_next[2];  // slot = iteration parity (SHFL: one CTA barrier per tile)
 
+    if (A.ticket_reset != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+        *A.ticket_reset = 0ULL;  // also on the gated path: the counters keep alternating cleanly
     if (A.gate != nullptr && *A.gate != 0.0)
         return;  // frozen Krylov loop: uniform over the grid (the word changes only between launches)
     const int tid = threadIdx.x;
@@ -524,7 +534,14 @@ static int launch_qp_cell(const CellArgs &A0, cudaStream_t st)
     unsigned long long grid = (unsigned long long)sm_count() * per_sm;
     if (grid > ntiles)
         grid = ntiles;
-    A.ticket = (ntiles > grid) ? tile_ticket(st) : nullptr;
+    if (t_tickets != nullptr) {  // alternating pair, no memset (fcx_internal.h)
+        A.ticket = t_tickets + (*t_ticket_launches & 1u);
+        A.ticket_reset = t_tickets + ((*t_ticket_launches + 1u) & 1u);
+        ++*t_ticket_launches;
+    } else {
+        A.ticket = (ntiles > grid) ? tile_ticket(st) : nullptr;
+        A.ticket_reset = nullptr;
+    }
     A.gate = t_gate;
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     A.bulk_ok = al16(A.Jinv) && al16(A.detJ) && al16(A.qarr) && (!Cfg::GATHER || al16(A.dofmap)) &&
@@ -544,7 +561,7 @@ static int launch_cell(int mode, size_t ncells, const int *dofmap, const double 
 {
     if (fem_variant() != 0) {
         CellArgs A{dofmap, p, dphi, w, Jinv, detJ, mode == 0 ? qvec : tangent, fe, pos,
-                   (unsigned long long)ncells, nullptr, 0, nullptr};
+                   (unsigned long long)ncells, nullptr, 0, nullptr, nullptr};
         switch (mode) {
         case 0: return launch_qp_cell<G, S, ND, NQ, 0>(A, st);
         case 1: return launch_qp_cell<G, S, ND, NQ, 1>(A, st);

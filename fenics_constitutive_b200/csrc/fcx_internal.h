@@ -23,6 +23,12 @@ int gather_variant();
 // (fcx_krylov.cu) freezes its iterations on the device once the residual test has passed, so the host may
 // enqueue blocks of iterations ahead of reading the test's outcome.  nullptr = no gate.
 void fem_set_launch_gate(const double *gate);
+// Tile tickets of the element kernels without a memset per launch: while set (per host thread), launch i takes
+// pair[i & 1] as its ticket counter and zeroes pair[(i + 1) & 1] -- the counter of the NEXT launch on the same
+// stream, which the previous launch has finished with.  Both counters must be zero when the pair is first used.
+// `launches` (host memory of the pair's owner) counts the launches the pair has served, across calls.
+// nullptr = the per-stream counter with its cudaMemsetAsync (tile_ticket).
+void fem_set_launch_tickets(unsigned long long *pair, unsigned *launches);
 
 // Resident CTAs per SM of `kern` at (threads, smem), with the opt-in to > 48 KB of dynamic shared
 // memory set first.  Both are properties of (kernel, DEVICE): a process may drive several GPUs (the

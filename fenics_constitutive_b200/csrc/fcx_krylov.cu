@@ -92,6 +92,8 @@ struct Krylov {
     //   [1] iteration at which it froze   [2] r.r at the start of the latest live iteration   [3] r.r of iteration 0
     //   [4] breakdown (p.Ap <= 0) seen     [5] live iterations so far
     double *ctl = nullptr;
+    unsigned long long *tile_tickets = nullptr;  // [2]: alternating tile-ticket counters of the element kernels
+    unsigned tile_launches = 0;                  // launches they have served (parity = whose turn it is)
     double rtol2 = 0.0;                  // freeze when r.r <= rtol2 * (r.r of iteration 0); 0 = never
     double *snap_host = nullptr;         // pinned [2][KR_CTL + 1]: snapshots of ctl (+ err) for the host
     cudaEvent_t snap_ev[2] = {nullptr, nullptr};
@@ -542,6 +544,10 @@ int fcx_krylov_create(int rank, int world, int gdim, size_t nnodes, size_t nnode
     if (e == cudaSuccess)
         e = cudaMemset(K->ctl, 0, sizeof(double) * KR_CTL);
     if (e == cudaSuccess)
+        e = cudaMalloc((void **)&K->tile_tickets, sizeof(unsigned long long) * 2);
+    if (e == cudaSuccess)
+        e = cudaMemset(K->tile_tickets, 0, sizeof(unsigned long long) * 2);
+    if (e == cudaSuccess)
         e = cudaMallocHost((void **)&K->snap_host, sizeof(double) * 2 * (KR_CTL + 1));
     for (int k = 0; k < 2 && e == cudaSuccess; ++k)
         e = cudaEventCreateWithFlags(&K->snap_ev[k], cudaEventDisableTiming);
@@ -702,10 +708,19 @@ int fcx_krylov_iterate(void *handle, int iters, void *stream)
                                        K->weights, K->Jinv + c0 * K->gdim * K->gdim, K->detJ + c0,
                                        K->tang + c0 * K->nq * rl, fe, pos, stream);
     };
-    struct GateGuard {  // the element kernels of this loop return at once when the solve is frozen
-        explicit GateGuard(const double *g) { fem_set_launch_gate(g); }
-        ~GateGuard() { fem_set_launch_gate(nullptr); }
-    } gate_guard(K->ctl);
+    struct GateGuard {  // the element kernels of this loop return at once when the solve is frozen, and hand
+                        // out their tiles from an alternating pair of counters (no memset per launch)
+        GateGuard(const double *g, unsigned long long *t, unsigned *n)
+        {
+            fem_set_launch_gate(g);
+            fem_set_launch_tickets(t, n);
+        }
+        ~GateGuard()
+        {
+            fem_set_launch_gate(nullptr);
+            fem_set_launch_tickets(nullptr, nullptr);
+        }
+    } gate_guard(K->ctl, K->tile_tickets, &K->tile_launches);
     for (int k = 0; k < iters; ++k) {
         // K1: cells that touch no ghost node first -- the neighbours' ghost stores of the previous update arrive
         // behind them; then the wait (one thread), then the boundary cells
@@ -875,7 +890,7 @@ void fcx_krylov_destroy(void *handle)
         if (K->peer_open[t])
             cudaIpcCloseMemHandle(K->peers.base[t]);
     void *ptrs[] = {K->comm, K->x, K->r, K->w, K->p, K->s, K->minv, K->partials, K->ticket, K->state, K->scal, K->hist, K->err,
-                    K->ctl, K->send_src, K->send_dst, K->send_nbr};
+                    K->ctl, K->tile_tickets, K->send_src, K->send_dst, K->send_nbr};
     for (void *q : ptrs)
         if (q)
             cudaFree(q);

@@ -2,10 +2,10 @@
 # Round-2 session ab (2 GPUs): look-ahead Krylov loop on a partitioned mesh: driver-equivalence tests (one GPU), partition
 # check, config 5.
 N=${1:-2}
-TAG=r2ab_n$N
+TAG=${2:-r2ab}_n$N
 OUT=gpurun_out; mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
-echo "== driver tests (1 GPU)"; timeout 600 python -m pytest tests/test_solver_gpu.py -m gpu -q -k "krylov" > $OUT/pytest_krylov_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest_krylov_$TAG.log
+echo "== driver tests (1 GPU)"; timeout 600 python -m pytest tests/test_solver_gpu.py -m gpu -q -k "krylov or cg or newton or readme or two_law" > $OUT/pytest_krylov_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest_krylov_$TAG.log
 echo "== check_partitioned_newton"
 timeout 420 $TR scripts/check_partitioned_newton.py > $OUT/check_partitioned_$TAG.log 2>&1; echo "check rc=$?"
 grep -E "degree|twin|ok|Error|error|assert" $OUT/check_partitioned_$TAG.log | cut -c1-330 | tail -9
