@@ -11,10 +11,13 @@
 // two GPUs against 0.18 ms of kernels.  Here one iteration is
 //     K1  element kernel        fe = B^T C B u_e             (fcx_tangent_apply[_rec], unchanged)
 //     K2  gsum_dots_kernel      w = sum fe (node-wise, fixed order);  partial (r.u, w.u, r.r) over
-//                               owned free dofs; the last CTA adds the CTA partials in index order,
-//                               STORES the three sums into every rank's reduction slot, waits for
-//                               the other ranks' sums and adds them in RANK order (every rank gets
-//                               the same bits): alpha / beta
+//                               owned free dofs; the last CTA adds the CTA partials (all its threads, in
+//                               a fixed order), STORES the three sums into every rank's reduction slot,
+//                               waits for the other ranks' sums and adds them in RANK order (every rank
+//                               gets the same bits): alpha / beta -- and the RESIDUAL TEST: once
+//                               r.r <= rtol^2 r0.r0 the solve freezes itself (control block `ctl`), every
+//                               later kernel of the loop returns at once, on every rank in the same
+//                               iteration
 //     K3  cg_update_kernel      p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;
 //                               u = minv r
 //     K4  halo_push_kernel      u of the nodes that are ghosts elsewhere is stored straight into the
@@ -25,8 +28,10 @@
 //                               ~90 % of the element work; then K1 on the boundary cells
 // with  gamma = r.u, delta = w.u:  beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)
 // -- ONE reduction per iteration instead of two, one fused vector pass instead of three kernels.
-// Four launches per iteration (three on one rank); fcx_krylov_iterate enqueues a block of iterations from C; the host looks at the residual history
-// once per block.  One process per GPU: peers' buffers come from CUDA IPC handles.
+// Six launches per iteration (three on one rank); fcx_krylov_iterate enqueues a block of iterations from C, and
+// because the stop rule runs on the device the host enqueues the NEXT block before it reads the snapshot of the
+// previous one (fcx_krylov_snapshot / fcx_krylov_wait_snapshot): the stream is never drained inside a solve.
+// One process per GPU: peers' buffers come from CUDA IPC handles.
 //
 // Ordering between ranks: a reduction slot / flag pair is double-buffered by iteration parity; a rank
 // can only run ahead to iteration i+2's K2 after every rank has finished iteration i's K3 (it needs
