@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from _util import TOL_PLASTIC, assert_close
-from test_drucker_prager import CASES, make_grad
+from test_drucker_prager import CASES, make_grad, mandel, mandel_to_grad
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_harness")
 SO = os.path.join(HERE, "libdp_host.so")
@@ -85,3 +85,39 @@ def test_product_point_update_on_host_apex_failure(harness):
     assert rc == 1
     assert np.all(sig.reshape(n, 6)[17] == 0.0) and np.all(hist.reshape(n, 7)[17] == 0.0)
     assert np.abs(sig.reshape(n, 6)[16]).max() > 0.0
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["reference_spelling", "shipped"])
+@pytest.mark.parametrize("name,gcls,ocls,prm", CASES, ids=[c[0] for c in CASES])
+def test_product_tangent_is_consistent_on_host(harness, name, gcls, ocls, prm, variant):
+    """tangent[i][j] = d sigma_i / d eps_j of the PRODUCT's point update (record + entry(), what the tile kernel
+    expands into the dense 6x6 block) against central differences of its own stress update -- no oracle involved."""
+    n = 200
+    e = mandel(make_grad(n, 5))
+    sig0 = np.random.default_rng(6).standard_normal(n * 6) * 20.0
+    hyp = int("d" in prm)
+    keys = ("mu", "kappa", "a", "b", "d", "b_flow") if hyp else ("mu", "kappa", "a", "b", "b_flow")
+    pv = np.array([float(prm[k][0]) for k in keys])
+
+    def run(strain, with_tangent):
+        g = mandel_to_grad(strain)
+        sig, hist, tan = sig0.copy(), np.zeros(n * 7), np.full(n * 36, np.nan)
+        flag = np.zeros(n, dtype=np.uint8)
+        rc = harness.dp_host_evaluate(hyp, variant, _p(pv), n, _p(g), _p(sig), _p(tan) if with_tangent else None,
+                                      _p(hist), flag.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)))
+        assert rc == 0
+        return sig.reshape(n, 6), tan.reshape(n, 6, 6), flag.astype(bool)
+
+    _, tan, pl = run(e, True)
+    assert pl.sum() > 40
+    h = 1e-7
+    fd = np.zeros((n, 6, 6))
+    for j in range(6):
+        ep, em = e.copy(), e.copy()
+        ep[:, j] += h
+        em[:, j] -= h
+        fd[:, :, j] = (run(ep, False)[0] - run(em, False)[0]) / (2 * h)
+    err = np.linalg.norm((tan - fd).reshape(n, -1), axis=1) / np.linalg.norm(fd.reshape(n, -1), axis=1)
+    assert err.max() < 2e-6
+    if float(prm["b"][0]) != float(prm["b_flow"][0]):  # non-associated flow: unsymmetric tangent
+        assert np.abs(tan[pl] - tan[pl].transpose(0, 2, 1)).max() > 1.0

@@ -222,6 +222,59 @@ def test_gpu_drucker_prager_vs_oracle(name, gcls, ocls, prm, n):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("variant", [1, 0], ids=["shipped", "reference_spelling"])
+@pytest.mark.parametrize("name,gcls,ocls,prm", CASES, ids=[c[0] for c in CASES])
+def test_gpu_drucker_prager_tangent_finite_difference(name, gcls, ocls, prm, variant):
+    """The CUDA path itself: the dense tangent the tile kernel stores against central differences
+    of the kernel's own stress update (stress-only calls), from a pre-stressed state, both spellings of the slow
+    operations (fcx_tune dp_variant); non-associated flow gives an unsymmetric tangent."""
+    import torch
+
+    from fenics_constitutive_b200 import models as M
+    from fenics_constitutive_b200._lib import lib
+
+    n = 3000
+    e = mandel(make_grad(n, 5))
+    sig0 = np.random.default_rng(6).standard_normal(n * 6) * 20.0
+    law = getattr(M, gcls)(prm)
+    law.record_plastic_flag = True
+    old = lib().fcx_tune(b"dp_variant", variant)
+    try:
+        def run(strain, with_tangent):
+            g = torch.from_numpy(mandel_to_grad(strain)).cuda()
+            sig = torch.from_numpy(sig0.copy()).cuda()
+            hist = torch.zeros(n * 7, dtype=torch.float64, device="cuda")
+            tan = torch.full((n * 36,), float("nan"), dtype=torch.float64, device="cuda") if with_tangent else None
+            law.evaluate(0.0, 1.0, g, sig, tan, {"history": hist})
+            return (sig.cpu().numpy().reshape(n, 6), tan.cpu().numpy().reshape(n, 6, 6) if with_tangent else None,
+                    law.plastic_flag.cpu().numpy().astype(bool))
+
+        _, tan, pl = run(e, True)
+        assert pl.sum() > 600
+        h = 1e-7
+        fd = np.zeros((n, 6, 6))
+        for j in range(6):
+            ep, em = e.copy(), e.copy()
+            ep[:, j] += h
+            em[:, j] -= h
+            fd[:, :, j] = (run(ep, False)[0] - run(em, False)[0]) / (2 * h)
+    finally:
+        lib().fcx_tune(b"dp_variant", old)
+    # points whose classification flips inside [e - h, e + h] have no derivative there: leave them out
+    steady = np.ones(n, dtype=bool)
+    for j in range(6):
+        for sgn in (1.0, -1.0):
+            ej = e.copy()
+            ej[:, j] += sgn * h
+            steady &= run(ej, False)[2] == pl
+    assert steady.mean() > 0.99
+    err = np.linalg.norm((tan - fd).reshape(n, -1), axis=1) / np.linalg.norm(fd.reshape(n, -1), axis=1)
+    assert err[steady].max() < 2e-6
+    if float(prm["b"][0]) != float(prm["b_flow"][0]):
+        assert np.abs(tan[pl] - tan[pl].transpose(0, 2, 1)).max() > 1.0
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n", [1000, 20_000], ids=["plain_d2h", "download_wire"])
 def test_gpu_drucker_prager_failure_reporting(n):
     """Points where the Rust code would panic (apex assert of the classic model) raise RuntimeError on
