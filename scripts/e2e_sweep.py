@@ -36,6 +36,9 @@ ap.add_argument("--mix", default=None,
                 help="only this: record wire (1) with these shares (percent, comma separated) of the chunks by plain "
                      "DMA (fcx_host_wire_mix), optionally x --mix-threads pool threads")
 ap.add_argument("--mix-threads", default="0")
+ap.add_argument("--custom", default=None,
+                help="only these: semicolon-separated slots:chunk_qps[:threads] points (0 = leave the default), after a "
+                     "run with the defaults and with one more of it at the end (drift of the box)")
 args = ap.parse_args()
 rank, local_rank, world = env_rank_world()
 torch.cuda.set_device(local_rank)
@@ -91,6 +94,21 @@ def run(kind, A, tag, **knobs):
               flush=True)
 
 
+for kind in args.kinds.split(",") if args.custom else ():
+    A = arrays(kind)
+    run(kind, A, "defaults (wire auto)")
+    for pt in args.custom.split(";"):
+        v = [int(x) for x in pt.split(":")]
+        kn = {}
+        if v[0] > 0:
+            kn["slots"] = v[0]
+        if len(v) > 1 and v[1] > 0:
+            kn["chunk_qps"] = v[1]
+        if len(v) > 2 and v[2] > 0:
+            kn["threads"] = v[2]
+        run(kind, A, "custom", **kn)
+    run(kind, A, "defaults again")
+    del A
 for kind in args.kinds.split(",") if args.mix else ():
     A = arrays(kind)
     for threads in [int(t) for t in args.mix_threads.split(",")]:
@@ -100,7 +118,7 @@ for kind in args.kinds.split(",") if args.mix else ():
                 kn["threads"] = threads
             run(kind, A, "mix", **kn)
     del A
-for kind in args.kinds.split(",") if not args.mix else ():
+for kind in args.kinds.split(",") if not (args.mix or args.custom) else ():
     A = arrays(kind)
     run(kind, A, "defaults (wire auto)")
     for wire in (0, 1, 2):
