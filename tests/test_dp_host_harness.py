@@ -21,9 +21,15 @@ CSRC = os.path.join(os.path.dirname(HERE), os.pardir, "fenics_constitutive_b200"
 
 
 def _build():
+    import shutil
+
     deps = [SRC] + [os.path.join(CSRC, f) for f in ("fcx_models.cuh", "fcx_tile.cuh", "fcx_ptx.cuh")]
     if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return
+    if shutil.which("nvcc") is None:
+        if os.path.exists(SO):
+            return  # a prebuilt harness travelled with the tree; nothing to rebuild it with
+        pytest.skip("nvcc not found: the host harness of the Drucker-Prager point update cannot be built")
     cmd = ["nvcc", "-O2", "-std=c++17", "-fmad=false", "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-o", SO, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
