@@ -853,7 +853,7 @@ struct PlasticWire {
     // Mixed download: `mix` percent of the chunks leave by plain DMA straight into the caller's page-locked
     // arrays (392 B per point over the link, no host-thread byte), the others by records (161 B per point over
     // the link, 392 B per point written by the host threads): the link and the pool threads work side by side
-    // on DIFFERENT chunks instead of the threads alone bounding the call (see g_wire_mix).
+    // on DIFFERENT chunks (an option, measured slower on this pool's hosts: see g_wire_mix).
     int mix = 0;
     bool plain(size_t q0) const
     {
@@ -969,9 +969,11 @@ static void plastic_wire_expand(const PlasticWire &W, size_t q0, size_t cnt, con
 // records plus streaming fills.  Threshold: FCX_WIRE_AUTO_RANKS (default 4).
 static int g_wire = 3;
 // Share (percent) of the chunks of a record-wire call (1) that leave by plain DMA instead, when every result
-// array of the call is page-locked.  With records alone a call on page-locked arrays is bound by the pool
-// threads' stores (392 B per point, ~8 GB/s per thread) while the link idles at 161 B per point; a plain-DMA
-// chunk costs the link 392 B per point and the threads nothing.  -1 = AUTO.
+// array of the call is page-locked.  The idea: with records alone the link idles at 161 B per point while the
+// pool threads write 392 B per point; a plain-DMA chunk costs the link 392 B per point and the threads nothing,
+// so the two could work side by side on different chunks.  (The premise was wrong: four pool threads already
+// keep up with the record expansion -- profiles/r2b_e2e_sweep_pinned.jsonl -- and no single phase bounds the
+// call, the phases slow each other down through the host's memory system)  -1 = AUTO.
 // MEASURED (16 M points, page-locked arrays, one GPU on a 16-core host, profiles/r2s_e2e_mix_pinned.jsonl):
 // 0 / 15 / 25 / 35 / 50 / 100 % = 158 / 150 / 144 / 139 / 131 / 122 M QP/s, the same with 12 pool threads --
 // the call time grows linearly with the share, i.e. the plain chunks and the record chunks do not overlap the
