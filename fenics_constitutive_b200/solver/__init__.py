@@ -14,7 +14,7 @@ from ._problem import (
     QuadratureFunction,
     SimulationTime,
 )
-from .maps import IdentityMap, SubSpaceMap, build_subspace_map
+from .maps import IdentityMap, SpaceMap, SubSpaceMap, build_subspace_map
 from .partitioned import MeshPartition
 from .mesh import (
     Constant,
@@ -36,7 +36,7 @@ from .mesh import (
 
 __all__ = [
     "IncrSmallStrainProblem", "KrylovError", "NewtonSolver", "SimulationTime", "IncrementalDisplacement",
-    "IncrementalStress", "History", "LawOnSubMesh", "QuadratureFunction", "IdentityMap", "SubSpaceMap",
+    "IncrementalStress", "History", "LawOnSubMesh", "QuadratureFunction", "IdentityMap", "SpaceMap", "SubSpaceMap",
     "build_subspace_map", "Mesh", "FunctionSpace", "Function", "Constant", "DirichletBC", "ElementTables",
     "create_unit_interval", "create_unit_square", "create_rectangle", "create_unit_cube", "create_box",
     "functionspace", "dirichletbc", "locate_dofs_geometrical", "MeshPartition", "surface_load",

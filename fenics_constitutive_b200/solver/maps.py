@@ -11,7 +11,22 @@ tests/solver/test_maps.py:119-121), so the map of a law that owns the cell list
 """
 from __future__ import annotations
 
+from typing import Protocol, runtime_checkable
+
 import numpy as np
+
+__all__ = ["IdentityMap", "SpaceMap", "SubSpaceMap", "build_subspace_map"]  # reference maps.py:11
+
+
+@runtime_checkable
+class SpaceMap(Protocol):
+    """What a parent <-> sub-space map offers (reference solver/maps.py:14-26); arrays are CUDA tensors here."""
+
+    def map_to_parent(self, sub, parent) -> None:
+        """sub -> the rows of parent this map covers."""
+
+    def map_to_sub(self, parent, sub) -> None:
+        """the rows of parent this map covers -> sub."""
 
 
 class IdentityMap:

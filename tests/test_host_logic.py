@@ -122,3 +122,12 @@ def test_shard_range_partitions_exactly(n, world):
     assert all(lo % 2 == 0 for lo, _ in spans)
     sizes = [hi - lo for lo, hi in spans]
     assert max(sizes) - min(sizes) <= 3
+
+
+def test_solver_maps_surface_matches_reference():
+    """The names of the reference's solver/maps.py:11 exist here and both maps satisfy its SpaceMap protocol."""
+    from fenics_constitutive_b200.solver import maps
+
+    assert sorted(maps.__all__) == ["IdentityMap", "SpaceMap", "SubSpaceMap", "build_subspace_map"]
+    assert isinstance(maps.IdentityMap(), maps.SpaceMap)
+    assert issubclass(maps.SubSpaceMap, maps.SpaceMap)
